@@ -1,0 +1,141 @@
+/* rss_b200.h — C ABI of the B200-native (sm_100a) RSSFormer training hot path.
+ *
+ * The reference (Rongtao-Xu/RepresentationLearning, RSSFormer-TIP2023) has NO FFI on this path: the
+ * seam it offers is the Python nn.Module surface.  This header therefore defines the
+ * boundary a maintainer binds from those modules (ctypes stub shown in INTEGRATION.md); every entry
+ * point names the reference code it replaces.  The only FFI precedent in the reference tree is the
+ * SWIG signature `void bilateralfilter_batch(float* images,int, float* ins,int, float* outs,int, int N,
+ * int K,int H,int W, float,float)` (SCD-AAAI2023/wrapper/bilateralfilter/bilateralfilter.hpp:12,
+ * bilateralfilter.i:21-25): caller-allocated flat arrays, in-place outputs.  The same conventions hold
+ * here, plus an int status:
+ *
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator); the library
+ *     allocates nothing, keeps no state between calls, and launches only on the `stream` it is given;
+ *   - no host synchronisation, no host reads of device data;
+ *   - activations are NHWC (== token-major (B, H*W, C)), element type selected by `dtype`
+ *     (RSS_F32 or RSS_BF16); parameters, statistics and all accumulation are fp32;
+ *   - return value: RSS_OK (0) or a negative rss_status; the CUDA error code of a failed launch is kept
+ *     in rss_last_cuda_error().  Nothing throws or exits;
+ *   - `*_acc` gradient outputs are ACCUMULATED into (caller zeroes them once per step).
+ *
+ * Paths below are relative to RSSFormer-TIP2023/module/baseline/ in the reference tree.
+ */
+#ifndef RSS_B200_H_
+#define RSS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+typedef enum { RSS_OK = 0, RSS_ERR_SHAPE = -1, RSS_ERR_DTYPE = -2, RSS_ERR_CUDA = -3, RSS_ERR_WORKSPACE = -4,
+               RSS_ERR_ARCH = -5 } rss_status;
+typedef enum { RSS_F32 = 0, RSS_BF16 = 1 } rss_dtype;
+typedef enum { RSS_ACT_NONE = 0, RSS_ACT_RELU = 1, RSS_ACT_GELU = 2 } rss_act;
+
+int rss_version(void);
+int rss_last_cuda_error(void);
+/* 0 when the current device is sm_100 (B200); RSS_ERR_ARCH otherwise. There is no fallback path. */
+int rss_check_device(void);
+
+/* ---- LayerNorm over channels of (rows, C) tokens: base_hrnet/modules/MTFM.py:64,78-79,107,109 ---- */
+int rss_layernorm_fwd(const void* x, void* y, float* mean /*[rows] or NULL*/, float* rstd /*[rows]*/,
+                      const float* gamma, const float* beta, float eps, int64_t rows, int C, int dtype, cudaStream_t stream);
+/* dx = LN'(dy) (+ dx_add if not NULL); dgamma_acc/dbeta_acc accumulate */
+int rss_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                      const void* dx_add, void* dx, float* dgamma_acc, float* dbeta_acc,
+                      int64_t rows, int C, int dtype, cudaStream_t stream);
+
+/* ---- gate + window cross-attention region: MTFM.py:101-107 (norm1 on both inputs, residual),
+ *      base_hrnet/modules/multihead_isa_pool_attention.py:148-188 (InterlacedPoolAttention2.forward),
+ *      multihead_isa_attention.py:373-426 (PadBlock, LocalPermuteModule), DAL.py:785-1030 (Mhca) ---- */
+typedef struct {
+    const float *ln_w, *ln_b;                  /* transformer.norm1 (C)                        */
+    const float *sa1_w, *sa2_w;                /* attn.atrous_block{1,2}.conv1.weight (1,2,7,7) */
+    const float *lvl_w, *lvl_b;                /* attn.weight_levels (2,2,1,1), (2)            */
+    const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b;   /* attn.attn.{q,k,v,out}_proj (C,C),(C) */
+    float ln_eps;
+    int C, num_heads, window;                  /* must be 32, 2, 7 (the only geometry the reference builds: _hrnet_rssformer.py:308) */
+} rss_attn_params;
+typedef struct {
+    float *ln_w, *ln_b, *sa1_w, *sa2_w, *lvl_w, *lvl_b, *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b;
+} rss_attn_grads;
+
+/* out = x + Attn(LN1(x), LN1(y)).  Saved for backward (caller-owned): xn, yn (B,HW,C) dtype;
+ * ln_stats [4][B*HW] f32; pooled [B][4][HW] f32; amax [B][2][HW] u8; smap, gmap [B][2][HW] f32. */
+#define RSS_ATTN_NO_RESIDUAL 1   /* flags bit 0: out = Attn(...) without "+ x" (InterlacedPoolAttention2.forward alone) */
+/* p->ln_w == NULL skips norm1 (x, y are then the already-normalised tokens; xn, yn, ln_stats unused). */
+int rss_attn_fwd(const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int dtype, int flags,
+                 void* xn, void* yn, float* ln_stats, float* pooled, uint8_t* amax, float* smap, float* gmap,
+                 void* out, cudaStream_t stream);
+size_t rss_attn_bwd_workspace_bytes(int B, int H, int W, int dtype);
+int rss_attn_bwd(const void* dout, const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int dtype, int flags,
+                 const void* xn, const void* yn, const float* ln_stats, const float* pooled, const uint8_t* amax,
+                 const float* smap, const float* gmap, void* workspace, size_t workspace_bytes,
+                 void* dx, void* dy, const rss_attn_grads* grads_acc, cudaStream_t stream);
+
+/* ---- BatchNorm / SyncBatchNorm (training) fused with the following activation and residual add:
+ *      _hrnet_rssformer.py:216-287 (BasicBlock/Bottleneck), ffn_block.py:222,231,234,246-263 (MlpDWBN) ---- */
+int rss_bn_stats_nparts(int64_t rows, int C);          /* number of partials rss_bn_stats writes */
+int rss_bn_stats(const void* x, float* partials /*[nparts][C][2] (mean,M2)*/, float* counts /*[nparts]*/,
+                 int64_t rows, int C, int dtype, cudaStream_t stream);
+int rss_bn_combine(const float* partials, const float* counts, int nparts, int C, float* stat /*[C][2]*/, float* total /*[1]*/,
+                   cudaStream_t stream);
+int rss_bn_finalize(const float* stat, const float* total, const float* gamma, const float* beta,
+                    float* running_mean /*may be NULL*/, float* running_var, float momentum, float eps, int C,
+                    float* mean_out, float* invstd_out, float* scale, float* shift, cudaStream_t stream);
+int rss_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, int C, float* mean_out, float* invstd_out, float* scale, float* shift, cudaStream_t stream);
+int rss_bn_act_fwd(const void* x, const void* residual /*may be NULL*/, void* y, const float* scale, const float* shift,
+                   int64_t rows, int C, int act, int dtype, cudaStream_t stream);
+/* sums[0..C) = sum dz, sums[C..2C) = sum dz*xhat with dz = dy*act'(.) (== dbeta, dgamma). y is needed for RELU only. */
+int rss_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, float* sums, int64_t rows, int C, int act, int dtype,
+                      cudaStream_t stream);
+int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
+                     const float* mean, const float* invstd, const float* sums, float inv_count,
+                     void* dx, void* dresidual /*may be NULL: receives dz*/, int64_t rows, int C, int act, int dtype,
+                     cudaStream_t stream);
+
+/* ---- neck: hrnet_aux.py:51-68 (SimpleFusion8: 3x bilinear align_corners=True + concat), NHWC ---- */
+int rss_neck_gather_fwd(const void* f0, const void* f1, const void* f2, const void* f3, void* out_cat,
+                        int B, const int* C /*[4]*/, const int* h /*[4]*/, const int* w /*[4]*/, int dtype, cudaStream_t stream);
+int rss_neck_gather_bwd(const void* dcat, void* d0, void* d1, void* d2, void* d3,
+                        int B, const int* C, const int* h, const int* w, int dtype, cudaStream_t stream);
+
+/* ---- head: hrnet_aux.py:78-81 (Conv2d(480,7,1)); logits are kept at LOW resolution, (pixels, 8) fp32
+ *      (class 7 is padding); the x4 UpsamplingBilinear2d is fused into rss_seg_loss_fwd / rss_head_probs ---- */
+int rss_head_fwd(const void* x, const float* w /*(7,C)*/, const float* bias, float* logits_lr, int64_t pixels, int C,
+                 int dtype, cudaStream_t stream);
+int rss_head_bwd(const void* x, const float* dlogits_lr, const float* w, void* dx, float* dw_acc, float* db_acc,
+                 int64_t pixels, int C, int dtype, cudaStream_t stream);
+/* eval output, hrnet_aux.py:109-110: probs (B,7,h*scale,w*scale) NCHW fp32 = softmax(upsample(logits)); argmax u8 optional */
+int rss_head_probs(const float* logits_lr, float* probs, uint8_t* argmax, int B, int h, int w, int scale, cudaStream_t stream);
+/* headaux, hrnet_aux.py:86-87,99-101: AdaptiveAvgPool2d(1) + Linear(C,7) (receives no gradient in the reference) */
+int rss_headaux_fwd(const void* f0, const float* w /*(7,C)*/, const float* bias, float* colsum_ws /*[B*C]*/, float* scores /*(B,7)*/,
+                    int B, int HW, int C, int dtype, cudaStream_t stream);
+
+/* ---- loss: module/CGFL.py:201-227,72-101 + losses/auxloss.py:257-305 (closed form in loss_optim.cu) ----
+ * out4 = {loss, grad scale, CE, n_valid}; gdir (B,h,w,8) f32 = un-scaled d loss/d logits_lr */
+size_t rss_seg_loss_acc_floats(int B);
+int rss_seg_loss_fwd(const float* logits_lr, const int64_t* labels /*(B,h*scale,w*scale)*/, const float* aux_scores /*(B,7)*/,
+                     float* acc_ws, float* gdir, float* out4, int B, int h, int w, int scale, int ignore_index, cudaStream_t stream);
+int rss_seg_loss_bwd(const float* gdir, const float* out4, const float* upstream /*scalar or NULL*/, float* dlogits_lr,
+                     int B, int h, int w, cudaStream_t stream);
+
+/* ---- optimiser step: configs/base/loveda.py:68-99 (clip_grad_norm_(35,L2) + SGD(m=.9, wd=1e-4)) on ONE flat buffer ---- */
+int rss_grad_sumsq(const float* grads, int64_t n, float grad_scale, double* sumsq, cudaStream_t stream);
+int rss_sgd_step(float* params, float* grads, float* momentum_buf, int64_t n, const double* sumsq, float grad_scale,
+                 float max_norm, float lr, float momentum, float weight_decay, int first_step, int zero_grad,
+                 void* bf16_shadow /*may be NULL*/, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSS_B200_H_ */

@@ -113,6 +113,21 @@ def main():
         np.savez_compressed(os.path.join(OUT, "loss_%s_B%d_S%d_seed%d.npz" % (case, B, S, seed)),
                             loss=np.float64(l.item()), dlogits=_np(logits.grad))
 
+    # ---------------- head up-sampling + loss from LOW-resolution logits (hrnet_aux.py:80 + CGFL), reference run
+    up = torch.nn.UpsamplingBilinear2d(scale_factor=4.0)
+    for case, B, h, seed in [("rand", 2, 16, 31), ("edge", 4, 8, 32)]:
+        g = torch.Generator().manual_seed(seed)
+        lr = 2.0 * torch.randn(B, 7, h, h, generator=g, dtype=torch.float64)
+        labels = torch.randint(-1, 7, (B, 4 * h, 4 * h), generator=g, dtype=torch.int64)
+        aux = torch.randn(B, 7, generator=g, dtype=torch.float64)
+        if case == "edge":
+            labels[0] = 0; labels[1] = -1; labels[2] = 3
+        lr.requires_grad_(True)
+        l = loss_mod(up(lr), labels, aux)["fc_loss"]
+        l.backward()
+        np.savez_compressed(os.path.join(OUT, "headloss_%s_B%d_h%d_seed%d.npz" % (case, B, h, seed)),
+                            loss=np.float64(l.item()), dlogits_lr=_np(lr.grad))
+
     # ---------------- full model, S=64 B=2 (train + eval), reference run ----------------------
     img, lbl = R.synth_batch(2, 64, dtype=torch.float64)
     model.eval()

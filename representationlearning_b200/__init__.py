@@ -1,0 +1,22 @@
+"""representationlearning_b200 — B200-native (sm_100a) RSSFormer training hot path.
+
+Drop-in for the `RSSFormer` model path of Rongtao-Xu/RepresentationLearning (RSSFormer-TIP2023):
+same module names / state_dict keys / forward contract, arithmetic in hand-written CUDA behind the
+C ABI of include/rss_b200.h.  No CPU fallback: importing is cheap, but every op raises unless
+librss_b200.so is built and an sm_100 GPU is present.
+"""
+import torch
+
+from . import _lib  # noqa: F401
+
+# strict fp32 parity runs must not silently drop to TF32 inside library convolutions
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+from .model import HRNetFusion, MODEL, RSSFORMER_CONFIG, build_rssformer  # noqa: F401
+from .modules import (FusedBNAct, GeneralTransformerBlock, InterlacedPoolAttention2, Mhca, MlpDWBN,  # noqa: F401
+                      SimpleFusion8, SpatialAttention)
+from .trainer import FlatSGD, poly_lr, train_step  # noqa: F401
+
+__all__ = ["HRNetFusion", "MODEL", "RSSFORMER_CONFIG", "build_rssformer", "GeneralTransformerBlock",
+           "InterlacedPoolAttention2", "Mhca", "MlpDWBN", "SimpleFusion8", "SpatialAttention", "FusedBNAct",
+           "FlatSGD", "poly_lr", "train_step"]

@@ -1,0 +1,742 @@
+// Fused gate + 7x7 window cross-attention region of the RSSFormer transformer block.
+//
+// Reference semantics (paths under RSSFormer-TIP2023/module/baseline/base_hrnet/modules/):
+//   LayerNorm1 on both inputs ................. MTFM.py:107 (same norm1 for x and y)
+//   saliency gate on the re-interpreted view ... multihead_isa_pool_attention.py:148-167
+//   centre zero-pad + 7x7 window gather ........ multihead_isa_attention.py:373-426 (no mask: pad tokens are live keys)
+//   Mhca: q/k/v proj, softmax(QK^T)V, sigmoid(mean+max(Q^T K)) gate, out proj .. DAL.py:873-1020
+//   residual add ............................... MTFM.py:107
+//
+// Data layout: tokens (B, H*W, 32) == NHWC.  One CTA owns one window at a time (persistent loop);
+// the window's 49 tokens, q/k/v and the four 32x32 weights live in shared memory (row stride 36
+// floats keeps every 128-bit access conflict-free); each attention row is owned by ONE thread so
+// the softmax needs no cross-lane traffic and S/P never leave registers (the reference
+// materialises (722*B,49,49) fp32 scores in HBM).  The region is HBM/issue-bound, not tensor-bound
+// (49x16 tiles, K=16): see DESIGN.md.
+#include "common.cuh"
+
+namespace rss {
+
+constexpr int kC = 32, kHD = 16, kL = 49, kWS = 7, kLD = 36, kPS = 49;
+constexpr int kTok = kL * kLD;                 // floats per token buffer
+constexpr int kThreads = 128;
+
+struct WinGeom { int B, H, W, HW, ph, pw, qh, qw, nWin; };
+
+static inline WinGeom make_geom(int B, int H, int W) {
+    WinGeom g; g.B = B; g.H = H; g.W = W; g.HW = H * W;
+    const int Hp = (H + kWS - 1) / kWS * kWS, Wp = (W + kWS - 1) / kWS * kWS;
+    g.ph = (Hp - H) / 2; g.pw = (Wp - W) / 2; g.qh = Hp / kWS; g.qw = Wp / kWS; g.nWin = B * g.qh * g.qw;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------
+// gate: pooled maps over the flat view, 7x7 conv + sigmoid, 1x1 conv + softmax
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gate_pool_kernel(const T* __restrict__ xn, const T* __restrict__ yn, float* __restrict__ pooled,
+                                 uint8_t* __restrict__ amax, int HW) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= HW) return;
+    const int b = blockIdx.y, z = blockIdx.z;
+    const T* base = (z == 0 ? xn : yn) + (size_t)b * HW * kC;
+    float s = 0.f, mx = -INFINITY;
+    int am = 0;
+#pragma unroll 8
+    for (int k = 0; k < kC; ++k) {
+        const float v = to_f(base[(size_t)k * HW + j]);
+        s += v;
+        if (v > mx) { mx = v; am = k; }
+    }
+    pooled[((size_t)b * 4 + z * 2 + 0) * HW + j] = s * (1.0f / kC);
+    pooled[((size_t)b * 4 + z * 2 + 1) * HW + j] = mx;
+    amax[((size_t)b * 2 + z) * HW + j] = (uint8_t)am;
+}
+
+__global__ void gate_map_kernel(const float* __restrict__ pooled, const float* __restrict__ w_sa1, const float* __restrict__ w_sa2,
+                                const float* __restrict__ lvl_w, const float* __restrict__ lvl_b,
+                                float* __restrict__ smap, float* __restrict__ gmap, int H, int W) {
+    __shared__ float ws[2][98];
+    for (int i = threadIdx.x; i < 196; i += blockDim.x) ws[i / 98][i % 98] = (i < 98 ? w_sa1[i] : w_sa2[i - 98]);
+    __syncthreads();
+    const int HW = H * W, b = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const int h = pix / W, w = pix % W;
+    float s[2];
+#pragma unroll
+    for (int z = 0; z < 2; ++z) {
+        float acc = 0.f;
+        for (int ci = 0; ci < 2; ++ci) {
+            const float* src = pooled + ((size_t)b * 4 + z * 2 + ci) * HW;
+            for (int dy = 0; dy < 7; ++dy) {
+                const int yy = h + dy - 3;
+                if (yy < 0 || yy >= H) continue;
+                for (int dx = 0; dx < 7; ++dx) {
+                    const int xx = w + dx - 3;
+                    if (xx < 0 || xx >= W) continue;
+                    acc += src[yy * W + xx] * ws[z][ci * 49 + dy * 7 + dx];
+                }
+            }
+        }
+        s[z] = 1.0f / (1.0f + expf(-acc));
+    }
+    const float l0 = lvl_w[0] * s[0] + lvl_w[1] * s[1] + lvl_b[0];
+    const float l1 = lvl_w[2] * s[0] + lvl_w[3] * s[1] + lvl_b[1];
+    const float g0 = 1.0f / (1.0f + expf(l1 - l0));
+    smap[((size_t)b * 2 + 0) * HW + pix] = s[0];
+    smap[((size_t)b * 2 + 1) * HW + pix] = s[1];
+    gmap[((size_t)b * 2 + 0) * HW + pix] = g0;
+    gmap[((size_t)b * 2 + 1) * HW + pix] = 1.0f - g0;
+}
+
+// ------------------------------------------------------------------------------------------
+// window helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int token_pixel(const WinGeom& g, int wi, int wj, int t) {
+    const int hy = wi * kWS + t / kWS - g.ph, wx = wj * kWS + t % kWS - g.pw;
+    return (hy >= 0 && hy < g.H && wx >= 0 && wx < g.W) ? hy * g.W + wx : -1;
+}
+
+// gated tokens of one window -> dst[49][36]; pad tokens are zeros
+template <typename T>
+__device__ __forceinline__ void load_window(const T* __restrict__ src, const float* __restrict__ gate_b, float* dst,
+                                            const WinGeom& g, int b, int wi, int wj) {
+    for (int idx = threadIdx.x; idx < kL * 4; idx += kThreads) {
+        const int t = idx >> 2, part = idx & 3;
+        const int n = token_pixel(g, wi, wj, t);
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (n >= 0) {
+            load8(src + ((size_t)b * g.HW + n) * kC + part * 8, v);
+            if (gate_b) {
+                int gi = (int)(((int64_t)n * kC + part * 8) % g.HW);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { v[i] *= gate_b[gi]; if (++gi == g.HW) gi = 0; }
+            }
+        }
+        float4* d = reinterpret_cast<float4*>(dst + t * kLD + part * 8);
+        d[0] = make_float4(v[0], v[1], v[2], v[3]);
+        d[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// dst[t][lane] = (sum_i src[t][i] * Wm[lane][i] + bias) * scale   for the 7 tokens of group tg
+__device__ __forceinline__ void proj7(const float* src, const float* Wm, float bias, float scale, float* dst, int tg, int lane) {
+    float acc[7];
+#pragma unroll
+    for (int tt = 0; tt < 7; ++tt) acc[tt] = bias;
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 w = *reinterpret_cast<const float4*>(Wm + lane * kLD + i4 * 4);
+#pragma unroll
+        for (int tt = 0; tt < 7; ++tt) {
+            const float4 xv = *reinterpret_cast<const float4*>(src + (tg * 7 + tt) * kLD + i4 * 4);
+            acc[tt] += xv.x * w.x + xv.y * w.y + xv.z * w.z + xv.w * w.w;
+        }
+    }
+#pragma unroll
+    for (int tt = 0; tt < 7; ++tt) dst[(tg * 7 + tt) * kLD + lane] = acc[tt] * scale;
+}
+
+// acc[tt] += sum_c G[t][c] * Wm[c][lane]
+__device__ __forceinline__ void projT7(const float* G, const float* Wm, float acc[7], int tg, int lane) {
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const float w0 = Wm[(c4 * 4 + 0) * kLD + lane], w1 = Wm[(c4 * 4 + 1) * kLD + lane];
+        const float w2 = Wm[(c4 * 4 + 2) * kLD + lane], w3 = Wm[(c4 * 4 + 3) * kLD + lane];
+#pragma unroll
+        for (int tt = 0; tt < 7; ++tt) {
+            const float4 gv = *reinterpret_cast<const float4*>(G + (tg * 7 + tt) * kLD + c4 * 4);
+            acc[tt] += gv.x * w0 + gv.y * w1 + gv.z * w2 + gv.w * w3;
+        }
+    }
+}
+
+__device__ __forceinline__ void load_weights(float* Wsm, float* bsm, const rss_attn_params& p) {
+    const float* wsrc[4] = {p.q_w, p.k_w, p.v_w, p.o_w};
+    const float* bsrc[4] = {p.q_b, p.k_b, p.v_b, p.o_b};
+    for (int idx = threadIdx.x; idx < 4 * kC * kC; idx += kThreads) {
+        const int m = idx / (kC * kC), r = (idx / kC) % kC, c = idx % kC;
+        Wsm[(m * kC + r) * kLD + c] = wsrc[m][r * kC + c];
+    }
+    for (int idx = threadIdx.x; idx < 4 * kC; idx += kThreads) bsm[idx] = bsrc[idx / kC][idx % kC];
+}
+
+__device__ __forceinline__ void load16(const float* p, float v[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 f = reinterpret_cast<const float4*>(p)[i];
+        v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+    }
+}
+
+// channel gate of DAL.py:1003-1010: S2 = q_h^T k_h (16x16), gate = sigmoid(mean(S2) + max(S2)).
+// Also returns the arg-max (first occurrence, row-major a*16+b) for the backward.
+__device__ __forceinline__ void channel_gate(const float* q, const float* k, float* red /*>=16 floats*/,
+                                             float* gate /*[2]*/, int* amax_idx /*[2]*/) {
+    const int tid = threadIdx.x, h = tid >> 6, a = (tid & 63) >> 2, b0 = (tid & 3) * 4;
+    float s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 7
+    for (int t = 0; t < kL; ++t) {
+        const float qa = q[t * kLD + h * kHD + a];
+        const float4 kb = *reinterpret_cast<const float4*>(k + t * kLD + h * kHD + b0);
+        s2[0] += qa * kb.x; s2[1] += qa * kb.y; s2[2] += qa * kb.z; s2[3] += qa * kb.w;
+    }
+    float sum = s2[0] + s2[1] + s2[2] + s2[3];
+    float mx = s2[0];
+    int mi = a * 16 + b0;
+#pragma unroll
+    for (int e = 1; e < 4; ++e) if (s2[e] > mx) { mx = s2[e]; mi = a * 16 + b0 + e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (om > mx || (om == mx && oi < mi)) { mx = om; mi = oi; }
+    }
+    const int warp = tid >> 5;
+    if ((tid & 31) == 0) { red[warp] = sum; red[4 + warp] = mx; reinterpret_cast<int*>(red)[8 + warp] = mi; }
+    __syncthreads();
+    if (tid < 2) {
+        const float s = red[2 * tid] + red[2 * tid + 1];
+        float m0 = red[4 + 2 * tid], m1 = red[4 + 2 * tid + 1];
+        int i0 = reinterpret_cast<int*>(red)[8 + 2 * tid], i1 = reinterpret_cast<int*>(red)[8 + 2 * tid + 1];
+        if (m1 > m0 || (m1 == m0 && i1 < i0)) { m0 = m1; i0 = i1; }
+        gate[tid] = 1.0f / (1.0f + expf(-(s * (1.0f / 256.0f) + m0)));
+        amax_idx[tid] = i0;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+constexpr int kFwdSmemFloats = 5 * kTok + 4 * kC * kLD + 4 * kC + 32;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 4)
+win_attn_fwd_kernel(const T* __restrict__ xn, const T* __restrict__ yn, const float* __restrict__ gmap,
+                    const T* __restrict__ xres, T* __restrict__ out, rss_attn_params p, WinGeom g) {
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;
+    float* ys = xs + kTok;
+    float* q = ys + kTok;
+    float* k = q + kTok;
+    float* v = k + kTok;
+    float* Wsm = v + kTok;
+    float* bsm = Wsm + 4 * kC * kLD;
+    float* misc = bsm + 4 * kC;            // [0..15] reduction scratch, [16..17] gate, [18..19] argmax
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    load_weights(Wsm, bsm, p);
+
+    for (int win = blockIdx.x; win < g.nWin; win += gridDim.x) {
+        const int b = win / (g.qh * g.qw), wi = (win / g.qw) % g.qh, wj = win % g.qw;
+        load_window(xn, gmap + ((size_t)b * 2 + 0) * g.HW, xs, g, b, wi, wj);
+        load_window(yn, gmap + ((size_t)b * 2 + 1) * g.HW, ys, g, b, wi, wj);
+        __syncthreads();
+        for (int task = warp; task < 21; task += 4) {      // q,k,v projections (DAL.py:873-875)
+            const int m = task / 7, tg = task % 7;
+            proj7(m == 0 ? xs : ys, Wsm + m * kC * kLD, bsm[m * kC + lane], m == 0 ? 0.25f : 1.0f,
+                  m == 0 ? q : (m == 1 ? k : v), tg, lane);
+        }
+        __syncthreads();
+        channel_gate(q, k, misc, misc + 16, reinterpret_cast<int*>(misc + 18));
+        {   // one attention row per thread: S = q_i k^T, softmax, O_i = P_i v (DAL.py:959,996,1012)
+            const int h = tid >> 6, i = tid & 63;
+            if (i < kL) {
+                float qi[16], S[kL], O[16];
+                load16(q + i * kLD + h * kHD, qi);
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < kL; ++j) {
+                    float kj[16];
+                    load16(k + j * kLD + h * kHD, kj);
+                    float s = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 16; ++d) s += qi[d] * kj[d];
+                    S[j] = s;
+                    mx = fmaxf(mx, s);
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < kL; ++j) { S[j] = __expf(S[j] - mx); sum += S[j]; }
+#pragma unroll
+                for (int d = 0; d < 16; ++d) O[d] = 0.f;
+#pragma unroll
+                for (int j = 0; j < kL; ++j) {
+                    float vj[16];
+                    load16(v + j * kLD + h * kHD, vj);
+#pragma unroll
+                    for (int d = 0; d < 16; ++d) O[d] += S[j] * vj[d];
+                }
+                const float sc = misc[16 + h] / sum;          // channel gate folded into the normaliser (DAL:1013)
+#pragma unroll
+                for (int d = 0; d < 16; ++d) xs[i * kLD + h * kHD + d] = O[d] * sc;   // xs is dead: reuse as merged O
+            }
+        }
+        __syncthreads();
+        for (int tg = warp; tg < 7; tg += 4)                 // out_proj (DAL.py:1020) -> ys (dead) as staging
+            proj7(xs, Wsm + 3 * kC * kLD, bsm[3 * kC + lane], 1.0f, ys, tg, lane);
+        __syncthreads();
+        for (int idx = tid; idx < kL * 4; idx += kThreads) {   // un-window, crop, + residual (isa:384-390,415-426; MTFM:107)
+            const int t = idx >> 2, part = idx & 3;
+            const int n = token_pixel(g, wi, wj, t);
+            if (n < 0) continue;
+            const size_t off = ((size_t)b * g.HW + n) * kC + part * 8;
+            float r[8];
+            if (xres) load8(xres + off, r);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] += ys[t * kLD + part * 8 + i];
+            store8(out + off, r);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of the windowed Mhca: produces d(gated x tokens), d(gated y tokens), dW/db of the 4 projections
+// ------------------------------------------------------------------------------------------
+constexpr int kBwdSmemFloats = 7 * kTok + 2 * 2 * kL * kPS + 4 * kC * kLD + 4 * kC + 32;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+win_attn_bwd_kernel(const T* __restrict__ xn, const T* __restrict__ yn, const float* __restrict__ gmap,
+                    const T* __restrict__ dout, T* __restrict__ dxg, T* __restrict__ dyg,
+                    rss_attn_params p, rss_attn_grads gr, WinGeom g) {
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;
+    float* ys = xs + kTok;
+    float* q = ys + kTok;
+    float* k = q + kTok;
+    float* v = k + kTok;
+    float* Om = v + kTok;
+    float* dOm = Om + kTok;
+    float* Pb = dOm + kTok;                 // [2][49][49]   (first used to stage the dout tile)
+    float* dSb = Pb + 2 * kL * kPS;         // [2][49][49]
+    float* Wsm = dSb + 2 * kL * kPS;
+    float* bsm = Wsm + 4 * kC * kLD;
+    float* misc = bsm + 4 * kC;             // [0..15] scratch, [16..17] gate, [18..19] argmax, [20..23] dgate partials
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    load_weights(Wsm, bsm, p);
+
+    // persistent per-thread weight-gradient accumulators: matrix m = warp, output channel c = lane
+    float accW[kC], accB = 0.f;
+#pragma unroll
+    for (int i = 0; i < kC; ++i) accW[i] = 0.f;
+
+    for (int win = blockIdx.x; win < g.nWin; win += gridDim.x) {
+        const int b = win / (g.qh * g.qw), wi = (win / g.qw) % g.qh, wj = win % g.qw;
+        load_window(xn, gmap + ((size_t)b * 2 + 0) * g.HW, xs, g, b, wi, wj);
+        load_window(yn, gmap + ((size_t)b * 2 + 1) * g.HW, ys, g, b, wi, wj);
+        load_window(dout, (const float*)nullptr, Pb, g, b, wi, wj);     // cropped grad: pad queries get 0
+        __syncthreads();
+        for (int task = warp; task < 28; task += 4) {
+            const int m = task / 7, tg = task % 7;
+            if (m < 3) {
+                proj7(m == 0 ? xs : ys, Wsm + m * kC * kLD, bsm[m * kC + lane], m == 0 ? 0.25f : 1.0f,
+                      m == 0 ? q : (m == 1 ? k : v), tg, lane);
+            } else {                                                    // dOm = dout . Wo
+                float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                projT7(Pb, Wsm + 3 * kC * kLD, acc, tg, lane);
+#pragma unroll
+                for (int tt = 0; tt < 7; ++tt) dOm[(tg * 7 + tt) * kLD + lane] = acc[tt];
+            }
+        }
+        __syncthreads();
+        channel_gate(q, k, misc, misc + 16, reinterpret_cast<int*>(misc + 18));
+
+        const int h = tid >> 6, i = tid & 63;
+        const bool row_live = i < kL;
+        float dq[16];
+#pragma unroll
+        for (int d = 0; d < 16; ++d) dq[d] = 0.f;
+        float dgate_part = 0.f;
+        if (row_live) {
+            // scores/probabilities of this thread's row live in Pb (own row only, stride 49: conflict-free)
+            float qi[16], A[16], dA[16];
+            float* Prow = Pb + (h * kL + i) * kPS;
+            float* dSrow = dSb + (h * kL + i) * kPS;
+            load16(q + i * kLD + h * kHD, qi);
+            float mx = -INFINITY;
+#pragma unroll 7
+            for (int j = 0; j < kL; ++j) {
+                float kj[16];
+                load16(k + j * kLD + h * kHD, kj);
+                float s = 0.f;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) s += qi[d] * kj[d];
+                Prow[j] = s;
+                mx = fmaxf(mx, s);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) A[d] = 0.f;
+#pragma unroll 7
+            for (int j = 0; j < kL; ++j) {
+                const float e = __expf(Prow[j] - mx);
+                sum += e;
+                Prow[j] = e;
+                float vj[16];
+                load16(v + j * kLD + h * kHD, vj);
+#pragma unroll
+                for (int d = 0; d < 16; ++d) A[d] += e * vj[d];
+            }
+            const float inv = 1.0f / sum;
+            const float gate = misc[16 + h];
+            float rowdot = 0.f;
+            load16(dOm + i * kLD + h * kHD, dA);
+#pragma unroll
+            for (int d = 0; d < 16; ++d) {
+                A[d] *= inv;                                           // A = P v (un-gated)
+                Om[i * kLD + h * kHD + d] = A[d] * gate;
+                dgate_part += dA[d] * A[d];
+                dA[d] *= gate;                                         // dA = dO * gate
+                rowdot += dA[d] * A[d];                                // = sum_j P_ij dP_ij
+                dOm[i * kLD + h * kHD + d] = dA[d];
+            }
+#pragma unroll 7
+            for (int j = 0; j < kL; ++j) {
+                float vj[16], kj[16];
+                load16(v + j * kLD + h * kHD, vj);
+                float dP = 0.f;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) dP += dA[d] * vj[d];
+                const float pij = Prow[j] * inv;
+                const float dS = pij * (dP - rowdot);
+                Prow[j] = pij;
+                dSrow[j] = dS;
+                load16(k + j * kLD + h * kHD, kj);
+#pragma unroll
+                for (int d = 0; d < 16; ++d) dq[d] += dS * kj[d];
+            }
+        }
+        dgate_part = warp_sum(dgate_part);
+        if (lane == 0) misc[20 + warp] = dgate_part;
+        __syncthreads();
+        {   // key/value side: thread owns key j=i of head h; plus the Q^T K gate terms (DAL.py:1003-1010)
+            float dk[16], dv[16];
+#pragma unroll
+            for (int d = 0; d < 16; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+            if (row_live) {
+                for (int r = 0; r < kL; ++r) {
+                    const float ds = dSb[(h * kL + r) * kPS + i], pp = Pb[(h * kL + r) * kPS + i];
+                    float qr[16], dAr[16];
+                    load16(q + r * kLD + h * kHD, qr);
+                    load16(dOm + r * kLD + h * kHD, dAr);
+#pragma unroll
+                    for (int d = 0; d < 16; ++d) { dk[d] += ds * qr[d]; dv[d] += pp * dAr[d]; }
+                }
+                const float gate = misc[16 + h];
+                const float dz = (misc[20 + 2 * h] + misc[20 + 2 * h + 1]) * gate * (1.0f - gate);
+                const int am = reinterpret_cast<int*>(misc + 18)[h], as = am >> 4, bs = am & 15;
+                float qt[16], kt[16];
+                load16(q + i * kLD + h * kHD, qt);
+                load16(k + i * kLD + h * kHD, kt);
+                float qsum = 0.f, ksum = 0.f, q_as = 0.f, k_bs = 0.f;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) {
+                    qsum += qt[d]; ksum += kt[d];
+                    q_as = (d == as) ? qt[d] : q_as;
+                    k_bs = (d == bs) ? kt[d] : k_bs;
+                }
+                const float u = dz * (1.0f / 256.0f);
+#pragma unroll
+                for (int d = 0; d < 16; ++d) {
+                    dq[d] += u * ksum + ((d == as) ? dz * k_bs : 0.f);
+                    dk[d] += u * qsum + ((d == bs) ? dz * q_as : 0.f);
+                }
+            }
+            __syncthreads();                 // every read of q/k/v is done: recycle them as gradient tiles
+            if (row_live) {
+#pragma unroll
+                for (int d = 0; d < 16; ++d) {
+                    q[i * kLD + h * kHD + d] = 0.25f * dq[d];          // grad at q_proj output (scaling, DAL:873)
+                    k[i * kLD + h * kHD + d] = dk[d];
+                    v[i * kLD + h * kHD + d] = dv[d];
+                }
+            }
+        }
+        __syncthreads();
+        for (int task = warp; task < 14; task += 4) {                   // grads w.r.t. the gated tokens
+            const int side = task / 7, tg = task % 7;
+            float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (side == 0) projT7(q, Wsm + 0 * kC * kLD, acc, tg, lane);
+            else { projT7(k, Wsm + 1 * kC * kLD, acc, tg, lane); projT7(v, Wsm + 2 * kC * kLD, acc, tg, lane); }
+            T* dst = side == 0 ? dxg : dyg;
+#pragma unroll
+            for (int tt = 0; tt < 7; ++tt) {
+                const int n = token_pixel(g, wi, wj, tg * 7 + tt);
+                if (n >= 0) dst[((size_t)b * g.HW + n) * kC + lane] = from_f<T>(acc[tt]);
+            }
+        }
+        {   // weight / bias gradients: thread (m=warp, c=lane) accumulates dW_m[c][:] += sum_t G_m[t][c] * X_m[t][:]
+            const float* G = warp == 0 ? q : (warp == 1 ? k : v);
+            const float* X = warp == 0 ? xs : (warp == 3 ? Om : ys);
+            for (int t = 0; t < kL; ++t) {
+                float gv;
+                if (warp < 3) gv = G[t * kLD + lane];
+                else {
+                    const int n = token_pixel(g, wi, wj, t);
+                    gv = n >= 0 ? to_f(dout[((size_t)b * g.HW + n) * kC + lane]) : 0.f;
+                }
+                accB += gv;
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(X + t * kLD + i4 * 4);
+                    accW[i4 * 4 + 0] += gv * xv.x; accW[i4 * 4 + 1] += gv * xv.y;
+                    accW[i4 * 4 + 2] += gv * xv.z; accW[i4 * 4 + 3] += gv * xv.w;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float* dW = warp == 0 ? gr.q_w : (warp == 1 ? gr.k_w : (warp == 2 ? gr.v_w : gr.o_w));
+    float* dB = warp == 0 ? gr.q_b : (warp == 1 ? gr.k_b : (warp == 2 ? gr.v_b : gr.o_b));
+#pragma unroll
+    for (int i = 0; i < kC; ++i) atomicAdd(dW + lane * kC + i, accW[i]);
+    atomicAdd(dB + lane, accB);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of the saliency gate
+// ------------------------------------------------------------------------------------------
+// dgmap[b][z][j] = sum_k dgated_flat[k*HW+j] * normed_flat[k*HW+j]
+template <typename T>
+__global__ void gate_bwd_reduce_kernel(const T* __restrict__ dxg, const T* __restrict__ dyg, const T* __restrict__ xn,
+                                       const T* __restrict__ yn, float* __restrict__ dgmap, int HW) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= HW) return;
+    const int b = blockIdx.y, z = blockIdx.z;
+    const T* d = (z == 0 ? dxg : dyg) + (size_t)b * HW * kC;
+    const T* n = (z == 0 ? xn : yn) + (size_t)b * HW * kC;
+    float s = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < kC; ++k) s += to_f(d[(size_t)k * HW + j]) * to_f(n[(size_t)k * HW + j]);
+    dgmap[((size_t)b * 2 + z) * HW + j] = s;
+}
+
+// softmax(2) -> 1x1 conv -> sigmoid backward; writes dpre (grad at the 7x7 conv outputs), accumulates dlvl_w/dlvl_b
+__global__ void gate_bwd_map_kernel(const float* __restrict__ dgmap, const float* __restrict__ gmap, const float* __restrict__ smap,
+                                    const float* __restrict__ lvl_w, float* __restrict__ dpre,
+                                    float* __restrict__ dlvl_w, float* __restrict__ dlvl_b, int HW) {
+    __shared__ float red[6][8];
+    const int b = blockIdx.y, pix = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // dW00 dW01 dW10 dW11 db0 db1
+    if (pix < HW) {
+        const size_t o0 = ((size_t)b * 2 + 0) * HW + pix, o1 = ((size_t)b * 2 + 1) * HW + pix;
+        const float g0 = gmap[o0], g1 = gmap[o1], dg0 = dgmap[o0], dg1 = dgmap[o1];
+        const float dot = dg0 * g0 + dg1 * g1;
+        const float dl0 = g0 * (dg0 - dot), dl1 = g1 * (dg1 - dot);
+        const float s0 = smap[o0], s1 = smap[o1];
+        acc[0] = dl0 * s0; acc[1] = dl0 * s1; acc[2] = dl1 * s0; acc[3] = dl1 * s1; acc[4] = dl0; acc[5] = dl1;
+        const float ds0 = lvl_w[0] * dl0 + lvl_w[2] * dl1, ds1 = lvl_w[1] * dl0 + lvl_w[3] * dl1;
+        dpre[o0] = ds0 * s0 * (1.0f - s0);
+        dpre[o1] = ds1 * s1 * (1.0f - s1);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { const float r = warp_sum(acc[e]); if (lane == 0) red[e][warp] = r; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
+        atomicAdd(threadIdx.x < 4 ? dlvl_w + threadIdx.x : dlvl_b + (threadIdx.x - 4), s);
+    }
+}
+
+// 7x7 conv backward on 32x32 tiles: dpooled (data grad) and dw_sa (weight grad, one thread per tap)
+__global__ void __launch_bounds__(256) gate_bwd_conv_kernel(const float* __restrict__ dpre, const float* __restrict__ pooled,
+                                                            const float* __restrict__ w_sa1, const float* __restrict__ w_sa2,
+                                                            float* __restrict__ dpooled, float* __restrict__ dw_sa1,
+                                                            float* __restrict__ dw_sa2, int H, int W) {
+    constexpr int TS = 32, HS = TS + 6;
+    __shared__ float dp[HS][HS + 1];
+    __shared__ float pl[2][HS][HS + 1];
+    __shared__ float wsm[98];
+    const int tiles_x = (W + TS - 1) / TS;
+    const int ty0 = (blockIdx.x / tiles_x) * TS, tx0 = (blockIdx.x % tiles_x) * TS;
+    const int b = blockIdx.y, z = blockIdx.z, HW = H * W;
+    const float* wsrc = z == 0 ? w_sa1 : w_sa2;
+    if (threadIdx.x < 98) wsm[threadIdx.x] = wsrc[threadIdx.x];
+    for (int idx = threadIdx.x; idx < HS * HS; idx += blockDim.x) {
+        const int yy = ty0 + idx / HS - 3, xx = tx0 + idx % HS - 3;
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        dp[idx / HS][idx % HS] = in ? dpre[((size_t)b * 2 + z) * HW + yy * W + xx] : 0.f;
+        pl[0][idx / HS][idx % HS] = in ? pooled[((size_t)b * 4 + z * 2 + 0) * HW + yy * W + xx] : 0.f;
+        pl[1][idx / HS][idx % HS] = in ? pooled[((size_t)b * 4 + z * 2 + 1) * HW + yy * W + xx] : 0.f;
+    }
+    __syncthreads();
+    // data grad: dpooled[ci][y][x] = sum_{dy,dx} dpre[y-dy+3][x-dx+3] * w[ci][dy][dx]
+    for (int idx = threadIdx.x; idx < TS * TS; idx += blockDim.x) {
+        const int ly = idx / TS, lx = idx % TS, yy = ty0 + ly, xx = tx0 + lx;
+        if (yy >= H || xx >= W) continue;
+        float a0 = 0.f, a1 = 0.f;
+        for (int dy = 0; dy < 7; ++dy)
+            for (int dx = 0; dx < 7; ++dx) {
+                const float d = dp[ly + 6 - dy][lx + 6 - dx];
+                a0 += d * wsm[dy * 7 + dx];
+                a1 += d * wsm[49 + dy * 7 + dx];
+            }
+        dpooled[((size_t)b * 4 + z * 2 + 0) * HW + yy * W + xx] = a0;
+        dpooled[((size_t)b * 4 + z * 2 + 1) * HW + yy * W + xx] = a1;
+    }
+    // weight grad: dw[ci][dy][dx] += sum_{y,x in tile} dpre[y][x] * pooled[ci][y+dy-3][x+dx-3]
+    if (threadIdx.x < 98) {
+        const int ci = threadIdx.x / 49, dy = (threadIdx.x % 49) / 7, dx = threadIdx.x % 7;
+        float a = 0.f;
+        for (int ly = 0; ly < TS; ++ly)
+            for (int lx = 0; lx < TS; ++lx) a += dp[ly + 3][lx + 3] * pl[ci][ly + dy][lx + dx];
+        atomicAdd((z == 0 ? dw_sa1 : dw_sa2) + threadIdx.x, a);
+    }
+}
+
+// d(normed)[f] = d(gated)[f]*g[f mod HW] + dpooled_avg[j]/C + dpooled_max[j]*[k == argmax[j]],  f = k*HW + j
+template <typename T>
+__global__ void gate_bwd_apply_kernel(const T* __restrict__ dxg, const T* __restrict__ dyg, const float* __restrict__ gmap,
+                                      const float* __restrict__ dpooled, const uint8_t* __restrict__ amax,
+                                      const T* __restrict__ x_add, T* __restrict__ dxn, T* __restrict__ dyn, int HW) {
+    const int b = blockIdx.y, z = blockIdx.z;
+    const size_t img = (size_t)b * HW * kC;
+    const T* src = (z == 0 ? dxg : dyg) + img;
+    T* dst = (z == 0 ? dxn : dyn) + img;
+    const T* add = (z == 0 && x_add) ? x_add + img : nullptr;
+    const float* gm = gmap + ((size_t)b * 2 + z) * HW;
+    const float* da = dpooled + ((size_t)b * 4 + z * 2 + 0) * HW;
+    const float* dm = dpooled + ((size_t)b * 4 + z * 2 + 1) * HW;
+    const uint8_t* am = amax + ((size_t)b * 2 + z) * HW;
+    const int64_t total8 = (int64_t)HW * kC / 8;
+    for (int64_t i8 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i8 < total8; i8 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f0 = i8 * 8;
+        float v[8];
+        load8(src + f0, v);
+        int j = (int)(f0 % HW), kk = (int)(f0 / HW);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[i] = v[i] * gm[j] + da[j] * (1.0f / kC) + ((int)am[j] == kk ? dm[j] : 0.f);
+            if (++j == HW) { j = 0; ++kk; }
+        }
+        if (add) {
+            float a[8];
+            load8(add + f0, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += a[i];
+        }
+        store8(dst + f0, v);
+    }
+}
+
+template <typename T>
+static int attn_fwd_impl(const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int flags,
+                         void* xn_, void* yn_, float* ln_stats, float* pooled, uint8_t* amax, float* smap, float* gmap,
+                         void* out, cudaStream_t st) {
+    const WinGeom g = make_geom(B, H, W);
+    const int64_t rows = (int64_t)B * g.HW;
+    int rc;
+    const void* xn = xn_; const void* yn = yn_;
+    if (p->ln_w) {
+        if ((rc = rss_layernorm_fwd(x, xn_, ln_stats, ln_stats + rows, p->ln_w, p->ln_b, p->ln_eps, rows, kC,
+                                    sizeof(T) == 4 ? RSS_F32 : RSS_BF16, st)) != RSS_OK) return rc;
+        if ((rc = rss_layernorm_fwd(y, yn_, ln_stats + 2 * rows, ln_stats + 3 * rows, p->ln_w, p->ln_b, p->ln_eps, rows, kC,
+                                    sizeof(T) == 4 ? RSS_F32 : RSS_BF16, st)) != RSS_OK) return rc;
+    } else { xn = x; yn = y; }                 // no norm1: the inputs ARE the normalised tokens
+    dim3 pg((g.HW + 255) / 256, B, 2);
+    gate_pool_kernel<T><<<pg, 256, 0, st>>>((const T*)xn, (const T*)yn, pooled, amax, g.HW);
+    dim3 mg((g.HW + 127) / 128, B);
+    gate_map_kernel<<<mg, 128, 0, st>>>(pooled, p->sa1_w, p->sa2_w, p->lvl_w, p->lvl_b, smap, gmap, H, W);
+    const size_t smem = kFwdSmemFloats * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(win_attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(win_attn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    int grid = num_sms() * 4;
+    if (grid > g.nWin) grid = g.nWin;
+    win_attn_fwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)xn, (const T*)yn, gmap,
+                                                         (flags & RSS_ATTN_NO_RESIDUAL) ? (const T*)nullptr : (const T*)x, (T*)out, *p, g);
+    return check_launch();
+}
+
+template <typename T>
+static int attn_bwd_impl(const void* dout, const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int flags,
+                         const void* xn, const void* yn, const float* ln_stats, const float* pooled, const uint8_t* amax,
+                         const float* smap, const float* gmap, void* workspace, void* dx, void* dy, const rss_attn_grads* gr,
+                         cudaStream_t st) {
+    const WinGeom g = make_geom(B, H, W);
+    const int64_t rows = (int64_t)B * g.HW;
+    const size_t tok_bytes = (size_t)rows * kC * sizeof(T);
+    char* ws = (char*)workspace;
+    T* dxg = (T*)ws;  ws += tok_bytes;
+    T* dyg = (T*)ws;  ws += tok_bytes;
+    float* dgmap = (float*)ws;  ws += (size_t)B * 2 * g.HW * sizeof(float);
+    float* dpre = (float*)ws;   ws += (size_t)B * 2 * g.HW * sizeof(float);
+    float* dpooled = (float*)ws;
+    const bool has_ln = p->ln_w != nullptr, has_res = !(flags & RSS_ATTN_NO_RESIDUAL);
+    if (!has_ln) { xn = x; yn = y; }
+    // the apply kernel is elementwise: in place when LayerNorm backward follows, else straight into dx/dy
+    T* dxn = has_ln ? dxg : (T*)dx; T* dyn = has_ln ? dyg : (T*)dy;
+    const int dt = sizeof(T) == 4 ? RSS_F32 : RSS_BF16;
+
+    const size_t smem = kBwdSmemFloats * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(win_attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(win_attn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    int grid = num_sms() * 2;
+    if (grid > g.nWin) grid = g.nWin;
+    win_attn_bwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)xn, (const T*)yn, gmap, (const T*)dout, dxg, dyg, *p, *gr, g);
+    dim3 pg((g.HW + 255) / 256, B, 2);
+    gate_bwd_reduce_kernel<T><<<pg, 256, 0, st>>>(dxg, dyg, (const T*)xn, (const T*)yn, dgmap, g.HW);
+    dim3 mg((g.HW + 255) / 256, B);
+    gate_bwd_map_kernel<<<mg, 256, 0, st>>>(dgmap, gmap, smap, p->lvl_w, dpre, gr->lvl_w, gr->lvl_b, g.HW);
+    dim3 cg(((H + 31) / 32) * ((W + 31) / 32), B, 2);
+    gate_bwd_conv_kernel<<<cg, 256, 0, st>>>(dpre, pooled, p->sa1_w, p->sa2_w, dpooled, gr->sa1_w, gr->sa2_w, H, W);
+    int ag = (int)(((int64_t)g.HW * kC / 8 + 255) / 256);
+    if (ag > 1024) ag = 1024;
+    dim3 apg(ag, B, 2);
+    gate_bwd_apply_kernel<T><<<apg, 256, 0, st>>>(dxg, dyg, gmap, dpooled, amax,
+                                                  (!has_ln && has_res) ? (const T*)dout : (const T*)nullptr, dxn, dyn, g.HW);
+    int rc = check_launch();
+    if (rc != RSS_OK || !has_ln) return rc;
+    // LayerNorm1 backward for both streams (shared gamma/beta grads); dx also takes the residual path (MTFM:107)
+    if ((rc = rss_layernorm_bwd(dxn, x, ln_stats, ln_stats + rows, p->ln_w, has_res ? dout : nullptr, dx, gr->ln_w, gr->ln_b, rows, kC, dt, st)) != RSS_OK) return rc;
+    return rss_layernorm_bwd(dyn, y, ln_stats + 2 * rows, ln_stats + 3 * rows, p->ln_w, nullptr, dy, gr->ln_w, gr->ln_b, rows, kC, dt, st);
+}
+
+}  // namespace rss
+
+using namespace rss;
+
+extern "C" size_t rss_attn_bwd_workspace_bytes(int B, int H, int W, int dtype) {
+    const size_t esz = dtype == RSS_F32 ? 4 : 2;
+    const size_t HW = (size_t)H * W;
+    return 2 * (size_t)B * HW * kC * esz + (size_t)B * HW * (2 + 2 + 4) * sizeof(float) + 256;
+}
+
+extern "C" int rss_attn_fwd(const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int dtype, int flags,
+                            void* xn, void* yn, float* ln_stats, float* pooled, uint8_t* amax, float* smap, float* gmap,
+                            void* out, cudaStream_t stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || !p) return RSS_ERR_SHAPE;
+    if (p->C != kC || p->num_heads != 2 || p->window != kWS) return RSS_ERR_SHAPE;
+    if (((int64_t)H * W * kC) % 8) return RSS_ERR_SHAPE;
+    RSS_DISPATCH_DTYPE(dtype, return attn_fwd_impl<T>(x, y, p, B, H, W, flags, xn, yn, ln_stats, pooled, amax, smap, gmap, out, stream));
+}
+
+extern "C" int rss_attn_bwd(const void* dout, const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int dtype, int flags,
+                            const void* xn, const void* yn, const float* ln_stats, const float* pooled, const uint8_t* amax,
+                            const float* smap, const float* gmap, void* workspace, size_t workspace_bytes,
+                            void* dx, void* dy, const rss_attn_grads* grads, cudaStream_t stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || !p || !grads) return RSS_ERR_SHAPE;
+    if (p->C != kC || p->num_heads != 2 || p->window != kWS) return RSS_ERR_SHAPE;
+    if (workspace_bytes < rss_attn_bwd_workspace_bytes(B, H, W, dtype)) return RSS_ERR_WORKSPACE;
+    RSS_DISPATCH_DTYPE(dtype, return attn_bwd_impl<T>(dout, x, y, p, B, H, W, flags, xn, yn, ln_stats, pooled, amax, smap, gmap,
+                                                        workspace, dx, dy, grads, stream));
+}

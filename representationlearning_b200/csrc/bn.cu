@@ -1,0 +1,326 @@
+// Training-mode BatchNorm / SyncBatchNorm over NHWC activations, fused with the activation that
+// follows it in the reference (ReLU in HRNet: _hrnet_rssformer.py:226-245; exact-erf GELU in the
+// FFN: modules/ffn_block.py:246-263) and with the residual add of BasicBlock/Bottleneck.
+//
+//   stats    : per-block shifted (mean, M2) partials per channel          -> rss_bn_stats
+//   combine  : Chan-combine partials (also across ranks for SyncBN)       -> rss_bn_combine
+//   finalize : scale/shift, saved mean/invstd, running-stat update        -> rss_bn_finalize
+//   apply    : y = act(x*scale + shift [+ residual])                      -> rss_bn_act_fwd
+//   backward : dz = dy*act'(.), sums (sum dz, sum dz*xhat)                -> rss_bn_bwd_reduce
+//              dx = gamma*invstd*(dz - sum_dz/n - xhat*sum_dzxhat/n)      -> rss_bn_bwd_apply
+// All kernels are HBM-bound: each thread owns 8 consecutive channels (one 16/32-byte vector).
+#include "common.cuh"
+
+namespace rss {
+
+struct BnGeom { int cg; int rpb; int threads; };
+static inline BnGeom bn_geom(int C) {
+    BnGeom g; g.cg = C / 8; g.rpb = 256 / g.cg; if (g.rpb < 1) g.rpb = 1; g.threads = g.cg * g.rpb; return g;
+}
+static inline int bn_grid(int64_t rows, int rpb, int per_sm) {
+    int64_t g = (rows + rpb - 1) / rpb;
+    const int64_t cap = (int64_t)num_sms() * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void bn_stats_kernel(const T* __restrict__ x, float* __restrict__ part /*[grid][C][2]*/,
+                                float* __restrict__ cnt /*[grid]*/, int64_t rows, int C, int cg, int rpb) {
+    extern __shared__ float sm[];           // [rpb][C][3]  (n, mean, M2)
+    const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
+    float K[8], s[8], q[8];
+    int64_t n = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { K[i] = 0.f; s[i] = 0.f; q[i] = 0.f; }
+    // contiguous chunk of rows per block keeps the shift K representative
+    const int64_t chunk = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * chunk;
+    const int64_t r1 = (r0 + chunk < rows) ? r0 + chunk : rows;
+    for (int64_t row = r0 + r; row < r1; row += rpb) {
+        float v[8];
+        load8(x + row * C + sub * 8, v);
+        if (n == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) K[i] = v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - K[i]; s[i] += d; q[i] += d * d; }
+        ++n;
+    }
+    const float fn = (float)n;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float* e = sm + ((size_t)r * C + sub * 8 + i) * 3;
+        const float md = n ? s[i] / fn : 0.f;
+        e[0] = fn; e[1] = K[i] + md; e[2] = n ? fmaxf(q[i] - s[i] * md, 0.f) : 0.f;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float na = 0.f, ma = 0.f, qa = 0.f;
+        for (int rr = 0; rr < rpb; ++rr) {
+            const float* e = sm + ((size_t)rr * C + c) * 3;
+            const float nb = e[0];
+            if (nb > 0.f) {
+                const float nn = na + nb, d = e[1] - ma;
+                ma += d * (nb / nn);
+                qa += e[2] + d * d * (na * nb / nn);
+                na = nn;
+            }
+        }
+        part[((size_t)blockIdx.x * C + c) * 2] = ma;
+        part[((size_t)blockIdx.x * C + c) * 2 + 1] = qa;
+        if (c == 0) cnt[blockIdx.x] = na;
+    }
+}
+
+// Chan-combine nparts partials -> stat[C][2] = (mean, M2), total[0] = count.  One thread per channel.
+__global__ void bn_combine_kernel(const float* __restrict__ part, const float* __restrict__ cnt, int nparts, int C,
+                                  float* __restrict__ stat, float* __restrict__ total) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double na = 0.0, ma = 0.0, qa = 0.0;
+    for (int p = 0; p < nparts; ++p) {
+        const double nb = cnt[p];
+        if (nb > 0.0) {
+            const double mb = part[((size_t)p * C + c) * 2], qb = part[((size_t)p * C + c) * 2 + 1];
+            const double nn = na + nb, d = mb - ma;
+            ma += d * (nb / nn);
+            qa += qb + d * d * (na * nb / nn);
+            na = nn;
+        }
+    }
+    stat[c * 2] = (float)ma;
+    stat[c * 2 + 1] = (float)qa;
+    if (c == 0) total[0] = (float)na;
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stat, const float* __restrict__ total,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float momentum, float eps, int C,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float n = total[0];
+    const float mean = stat[c * 2];
+    const float var = stat[c * 2 + 1] / n;                      // biased (normalisation)
+    const float invstd = rsqrtf(var + eps);
+    mean_out[c] = mean;
+    invstd_out[c] = invstd;
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    if (running_mean) {
+        const float unb = stat[c * 2 + 1] / fmaxf(n - 1.f, 1.f);  // unbiased (running estimate)
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+    }
+}
+
+__global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C,
+                                      float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float invstd = rsqrtf(rv[c] + eps);
+    const float sc = gamma[c] * invstd;
+    mean_out[c] = rm[c]; invstd_out[c] = invstd; scale[c] = sc; shift[c] = beta[c] - rm[c] * sc;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T, int ACT>   // ACT: 0 none, 1 relu, 2 gelu
+__global__ void bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                  int64_t rows, int C, int cg, int rpb) {
+    const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = scale[sub * 8 + i]; sh[i] = shift[sub * 8 + i]; }
+    for (int64_t row = (int64_t)blockIdx.x * rpb + r; row < rows; row += (int64_t)gridDim.x * rpb) {
+        float v[8];
+        load8(x + row * C + sub * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = v[i] * sc[i] + sh[i];
+        if (res) {
+            float a[8];
+            load8(res + row * C + sub * 8, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += a[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (ACT == 1) v[i] = fmaxf(v[i], 0.f);
+            if (ACT == 2) v[i] = gelu_f(v[i]);
+        }
+        store8(y + row * C + sub * 8, v);
+    }
+}
+
+// dz = dy * act'(z).  relu: mask from the saved output y (>0); gelu: z recomputed from x.
+template <typename T, int ACT>
+__device__ __forceinline__ void bn_dz(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+                                      int64_t off, const float sc[8], const float sh[8], const float mu[8], const float is[8],
+                                      float dz[8], float xh[8]) {
+    float v[8];
+    load8(x + off, v);
+    load8(dy + off, dz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xh[i] = (v[i] - mu[i]) * is[i];
+    if (ACT == 1) {
+        float o[8];
+        load8(y + off, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dz[i] = o[i] > 0.f ? dz[i] : 0.f;
+    }
+    if (ACT == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dz[i] *= gelu_grad_f(v[i] * sc[i] + sh[i]);
+    }
+}
+
+template <typename T, int ACT>
+__global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     float* __restrict__ sums /*[2][C]: sum dz, sum dz*xhat*/,
+                                     int64_t rows, int C, int cg, int rpb) {
+    extern __shared__ float sm[];           // [rpb][2][C]
+    const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
+    float sc[8], sh[8], mu[8], is[8], a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = scale[sub * 8 + i]; sh[i] = shift[sub * 8 + i]; mu[i] = mean[sub * 8 + i]; is[i] = invstd[sub * 8 + i];
+        a0[i] = 0.f; a1[i] = 0.f;
+    }
+    for (int64_t row = (int64_t)blockIdx.x * rpb + r; row < rows; row += (int64_t)gridDim.x * rpb) {
+        float dz[8], xh[8];
+        bn_dz<T, ACT>(x, y, dy, row * C + sub * 8, sc, sh, mu, is, dz, xh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a0[i] += dz[i]; a1[i] += dz[i] * xh[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sm[((size_t)r * 2 + 0) * C + sub * 8 + i] = a0[i];
+        sm[((size_t)r * 2 + 1) * C + sub * 8 + i] = a1[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+        const int which = c / C, ch = c % C;
+        float s = 0.f;
+        for (int rr = 0; rr < rpb; ++rr) s += sm[((size_t)rr * 2 + which) * C + ch];
+        atomicAdd(sums + which * C + ch, s);
+    }
+}
+
+template <typename T, int ACT>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ sums, float inv_count,
+                                    T* __restrict__ dx, T* __restrict__ dres, int64_t rows, int C, int cg, int rpb) {
+    const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
+    float sc[8], sh[8], mu[8], is[8], m0[8], m1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = scale[sub * 8 + i]; sh[i] = shift[sub * 8 + i]; mu[i] = mean[sub * 8 + i]; is[i] = invstd[sub * 8 + i];
+        m0[i] = sums[sub * 8 + i] * inv_count; m1[i] = sums[C + sub * 8 + i] * inv_count;
+    }
+    for (int64_t row = (int64_t)blockIdx.x * rpb + r; row < rows; row += (int64_t)gridDim.x * rpb) {
+        float dz[8], xh[8], o[8];
+        const int64_t off = row * C + sub * 8;
+        bn_dz<T, ACT>(x, y, dy, off, sc, sh, mu, is, dz, xh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = sc[i] * (dz[i] - m0[i] - xh[i] * m1[i]);
+        store8(dx + off, o);
+        if (dres) store8(dres + off, dz);
+    }
+}
+
+}  // namespace rss
+
+using namespace rss;
+
+extern "C" int rss_bn_stats_nparts(int64_t rows, int C) {
+    if (C <= 0 || C % 8) return RSS_ERR_SHAPE;
+    const BnGeom g = bn_geom(C);
+    return bn_grid(rows, g.rpb * 8, 4);
+}
+
+extern "C" int rss_bn_stats(const void* x, float* partials, float* counts, int64_t rows, int C, int dtype, cudaStream_t st) {
+    if (C <= 0 || C % 8 || C > 2048 || rows <= 0) return RSS_ERR_SHAPE;
+    const BnGeom g = bn_geom(C);
+    const int grid = rss_bn_stats_nparts(rows, C);
+    const size_t smem = (size_t)g.rpb * C * 3 * sizeof(float);
+    RSS_DISPATCH_DTYPE(dtype, bn_stats_kernel<T><<<grid, g.threads, smem, st>>>((const T*)x, partials, counts, rows, C, g.cg, g.rpb));
+    return check_launch();
+}
+
+extern "C" int rss_bn_combine(const float* partials, const float* counts, int nparts, int C, float* stat, float* total,
+                              cudaStream_t st) {
+    if (C <= 0 || nparts <= 0) return RSS_ERR_SHAPE;
+    bn_combine_kernel<<<(C + 127) / 128, 128, 0, st>>>(partials, counts, nparts, C, stat, total);
+    return check_launch();
+}
+
+extern "C" int rss_bn_finalize(const float* stat, const float* total, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps, int C,
+                               float* mean_out, float* invstd_out, float* scale, float* shift, cudaStream_t st) {
+    if (C <= 0) return RSS_ERR_SHAPE;
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stat, total, gamma, beta, running_mean, running_var, momentum, eps, C,
+                                                        mean_out, invstd_out, scale, shift);
+    return check_launch();
+}
+
+extern "C" int rss_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                                  float eps, int C, float* mean_out, float* invstd_out, float* scale, float* shift, cudaStream_t st) {
+    if (C <= 0) return RSS_ERR_SHAPE;
+    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(gamma, beta, running_mean, running_var, eps, C, mean_out, invstd_out, scale, shift);
+    return check_launch();
+}
+
+#define BN_ACT_SWITCH(KERNEL, ...)                                                   \
+    switch (act) {                                                                   \
+        case RSS_ACT_NONE: KERNEL<T, 0> __VA_ARGS__; break;                          \
+        case RSS_ACT_RELU: KERNEL<T, 1> __VA_ARGS__; break;                          \
+        case RSS_ACT_GELU: KERNEL<T, 2> __VA_ARGS__; break;                          \
+        default: return RSS_ERR_SHAPE;                                               \
+    }
+
+extern "C" int rss_bn_act_fwd(const void* x, const void* residual, void* y, const float* scale, const float* shift,
+                              int64_t rows, int C, int act, int dtype, cudaStream_t st) {
+    if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
+    const BnGeom g = bn_geom(C);
+    const int grid = bn_grid(rows, g.rpb * 4, 8);
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_act_fwd_kernel, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, rows, C, g.cg, g.rpb)));
+    return check_launch();
+}
+
+extern "C" int rss_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
+                                 const float* mean, const float* invstd, float* sums, int64_t rows, int C, int act, int dtype,
+                                 cudaStream_t st) {
+    if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
+    if (act == RSS_ACT_RELU && !y) return RSS_ERR_SHAPE;
+    const BnGeom g = bn_geom(C);
+    const int grid = bn_grid(rows, g.rpb * 8, 4);
+    const size_t smem = (size_t)g.rpb * 2 * C * sizeof(float);
+    cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st);
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return RSS_ERR_CUDA; }
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_reduce_kernel, <<<grid, g.threads, smem, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, rows, C, g.cg, g.rpb)));
+    return check_launch();
+}
+
+extern "C" int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
+                                const float* mean, const float* invstd, const float* sums, float inv_count,
+                                void* dx, void* dres, int64_t rows, int C, int act, int dtype, cudaStream_t st) {
+    if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
+    if (act == RSS_ACT_RELU && !y) return RSS_ERR_SHAPE;
+    const BnGeom g = bn_geom(C);
+    const int grid = bn_grid(rows, g.rpb * 4, 8);
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb)));
+    return check_launch();
+}

@@ -1,0 +1,353 @@
+// Fusion neck gather, 1x1 classifier head and auxiliary head of RSSFormer (NHWC, HBM-bound kernels).
+//
+// Reference: RSSFormer-TIP2023/module/baseline/hrnet_aux.py
+//   SimpleFusion8.forward :51-68  3x F.interpolate(bilinear, align_corners=True) + cat -> 480 channels
+//   head :78-81                   Conv2d(480,7,1) + UpsamplingBilinear2d(x4) (== align_corners=True)
+//   eval output :109-110          softmax(dim=1) of the up-sampled logits
+//   headaux :86-87,99-101         AdaptiveAvgPool2d(1) + Linear(32,7)
+// The concat is written once, directly in its final NHWC place (the reference writes three
+// up-sampled tensors and then copies all four into the concat); the x4 up-sampling of the logits
+// is never materialised in training (it is fused into the loss kernel, loss.cu).
+#include "common.cuh"
+
+namespace rss {
+
+// PyTorch's align_corners=True source index (area_pixel_compute_source_index): src = o * (in-1)/(out-1)
+__device__ __forceinline__ void bilinear_src(int o, float scale, int in, int& i0, int& i1, float& l1) {
+    const float src = scale * (float)o;
+    i0 = (int)src;
+    if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+}
+static inline float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+
+struct NeckGeom {
+    int B, H, W;                 // output (level-0) size
+    int C[4], h[4], w[4], coff[4];
+    int Ctot;
+    float sy[4], sx[4];
+};
+
+template <typename T>
+__global__ void neck_gather_fwd_kernel(const T* __restrict__ f0, const T* __restrict__ f1, const T* __restrict__ f2,
+                                       const T* __restrict__ f3, T* __restrict__ out, NeckGeom g) {
+    const int groups = g.Ctot / 8;
+    const int64_t total = (int64_t)g.B * g.H * g.W * groups;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int grp = (int)(idx % groups);
+        const int64_t pix = idx / groups;
+        const int ox = (int)(pix % g.W), oy = (int)((pix / g.W) % g.H), b = (int)(pix / ((int64_t)g.W * g.H));
+        const int ch = grp * 8;
+        int l = 0;
+        if (ch >= g.coff[3]) l = 3; else if (ch >= g.coff[2]) l = 2; else if (ch >= g.coff[1]) l = 1;
+        const T* src = l == 0 ? f0 : (l == 1 ? f1 : (l == 2 ? f2 : f3));
+        const int c = ch - g.coff[l], Cl = g.C[l], hl = g.h[l], wl = g.w[l];
+        float v[8];
+        if (l == 0) {
+            load8(src + (((int64_t)b * hl + oy) * wl + ox) * Cl + c, v);
+        } else {
+            int y0, y1, x0, x1; float ly, lx;
+            bilinear_src(oy, g.sy[l], hl, y0, y1, ly);
+            bilinear_src(ox, g.sx[l], wl, x0, x1, lx);
+            float a[8], bb[8], cc[8], d[8];
+            const T* base = src + (int64_t)b * hl * wl * Cl + c;
+            load8(base + ((int64_t)y0 * wl + x0) * Cl, a);
+            load8(base + ((int64_t)y0 * wl + x1) * Cl, bb);
+            load8(base + ((int64_t)y1 * wl + x0) * Cl, cc);
+            load8(base + ((int64_t)y1 * wl + x1) * Cl, d);
+            const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = hy * (hx * a[i] + lx * bb[i]) + ly * (hx * cc[i] + lx * d[i]);
+        }
+        store8(out + pix * g.Ctot + ch, v);
+    }
+}
+
+// gather-form transpose of the bilinear up-sampling: one thread per (input pixel, 8 channels)
+template <typename T>
+__global__ void neck_gather_bwd_kernel(const T* __restrict__ dcat, T* __restrict__ d0, T* __restrict__ d1,
+                                       T* __restrict__ d2, T* __restrict__ d3, NeckGeom g, int level) {
+    const int l = level, Cl = g.C[l], hl = g.h[l], wl = g.w[l], groups = Cl / 8;
+    T* dst = l == 0 ? d0 : (l == 1 ? d1 : (l == 2 ? d2 : d3));
+    const int64_t total = (int64_t)g.B * hl * wl * groups;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int grp = (int)(idx % groups);
+        const int64_t pix = idx / groups;
+        const int ix = (int)(pix % wl), iy = (int)((pix / wl) % hl), b = (int)(pix / ((int64_t)wl * hl));
+        const T* src = dcat + (int64_t)b * g.H * g.W * g.Ctot + g.coff[l] + grp * 8;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        if (l == 0) {
+            load8(src + ((int64_t)iy * g.W + ix) * g.Ctot, acc);
+        } else {
+            const float sy = g.sy[l], sx = g.sx[l];
+            int oy_lo = sy > 0.f ? (int)floorf((iy - 1) / sy) - 1 : 0, oy_hi = sy > 0.f ? (int)ceilf((iy + 1) / sy) + 1 : g.H - 1;
+            int ox_lo = sx > 0.f ? (int)floorf((ix - 1) / sx) - 1 : 0, ox_hi = sx > 0.f ? (int)ceilf((ix + 1) / sx) + 1 : g.W - 1;
+            if (oy_lo < 0) oy_lo = 0; if (ox_lo < 0) ox_lo = 0;
+            if (oy_hi > g.H - 1) oy_hi = g.H - 1; if (ox_hi > g.W - 1) ox_hi = g.W - 1;
+            for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+                int y0, y1; float ly;
+                bilinear_src(oy, sy, hl, y0, y1, ly);
+                const float wy = (y0 == iy ? 1.f - ly : 0.f) + (y1 == iy ? ly : 0.f);
+                if (wy == 0.f) continue;
+                for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                    int x0, x1; float lx;
+                    bilinear_src(ox, sx, wl, x0, x1, lx);
+                    const float wx = (x0 == ix ? 1.f - lx : 0.f) + (x1 == ix ? lx : 0.f);
+                    if (wx == 0.f) continue;
+                    float v[8];
+                    load8(src + ((int64_t)oy * g.W + ox) * g.Ctot, v);
+                    const float wgt = wy * wx;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] += wgt * v[i];
+                }
+            }
+        }
+        store8(dst + pix * Cl + grp * 8, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// head: logits_lr[pix][o] = sum_c x[pix][c] * W[o][c] + b[o]   (o<7, padded to 8 floats per pixel)
+// ---------------------------------------------------------------------------------------------
+constexpr int kNC = 7, kNCP = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ logits, int64_t pixels, int C) {
+    extern __shared__ float wsm[];                    // [7][C]
+    for (int i = threadIdx.x; i < kNC * C; i += blockDim.x) wsm[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int chunks = C / 8;
+    for (int64_t pix = (int64_t)blockIdx.x * wpb + warp; pix < pixels; pix += (int64_t)gridDim.x * wpb) {
+        float acc[kNC];
+#pragma unroll
+        for (int o = 0; o < kNC; ++o) acc[o] = 0.f;
+        for (int ck = lane; ck < chunks; ck += 32) {
+            float v[8];
+            load8(x + pix * C + ck * 8, v);
+#pragma unroll
+            for (int o = 0; o < kNC; ++o) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wsm + o * C + ck * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(wsm + o * C + ck * 8 + 4);
+                acc[o] += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kNC; ++o) acc[o] = warp_sum(acc[o]);
+        if (lane < kNCP) {
+            float r = 0.f;
+#pragma unroll
+            for (int o = 0; o < kNC; ++o) if (lane == o) r = acc[o] + bias[o];
+            logits[pix * kNCP + lane] = r;
+        }
+    }
+}
+
+// dx[pix][c] = sum_o dl[pix][o] W[o][c];  dW[o][c] += sum_pix dl[pix][o] x[pix][c];  db[o] += sum_pix dl[pix][o]
+template <typename T>
+__global__ void head_bwd_kernel(const T* __restrict__ x, const float* __restrict__ dl, const float* __restrict__ w,
+                                T* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
+                                int64_t pixels, int C, int cg, int rpb) {
+    extern __shared__ float red[];                    // [rpb][7][C]
+    const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
+    float wr[kNC][8], aw[kNC][8], ab[kNC];
+#pragma unroll
+    for (int o = 0; o < kNC; ++o) {
+        ab[o] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { wr[o][i] = w[o * C + sub * 8 + i]; aw[o][i] = 0.f; }
+    }
+    for (int64_t pix = (int64_t)blockIdx.x * rpb + r; pix < pixels; pix += (int64_t)gridDim.x * rpb) {
+        const float4 d0 = __ldg(reinterpret_cast<const float4*>(dl + pix * kNCP));
+        const float4 d1 = __ldg(reinterpret_cast<const float4*>(dl + pix * kNCP) + 1);
+        const float d[kNC] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z};
+        float v[8], o8[8];
+        load8(x + pix * C + sub * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o8[i] = 0.f;
+#pragma unroll
+        for (int o = 0; o < kNC; ++o) {
+            if (sub == 0) ab[o] += d[o];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { o8[i] += d[o] * wr[o][i]; aw[o][i] += d[o] * v[i]; }
+        }
+        store8(dx + pix * C + sub * 8, o8);
+    }
+#pragma unroll
+    for (int o = 0; o < kNC; ++o)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[((size_t)r * kNC + o) * C + sub * 8 + i] = aw[o][i];
+    __syncthreads();
+    for (int e = threadIdx.x; e < kNC * C; e += blockDim.x) {
+        float s = 0.f;
+        for (int rr = 0; rr < rpb; ++rr) s += red[(size_t)rr * kNC * C + e];
+        atomicAdd(dw + e, s);
+    }
+    __syncthreads();
+    if (sub == 0) {
+#pragma unroll
+        for (int o = 0; o < kNC; ++o) red[r * kNC + o] = ab[o];
+    }
+    __syncthreads();
+    if (threadIdx.x < kNC) {
+        float s = 0.f;
+        for (int rr = 0; rr < rpb; ++rr) s += red[rr * kNC + threadIdx.x];
+        atomicAdd(db + threadIdx.x, s);
+    }
+}
+
+// eval: probs[b][c][oy][ox] = softmax_c(bilinear_x4(logits_lr))   (NCHW fp32, as the reference returns), argmax optional
+__global__ void head_probs_kernel(const float* __restrict__ logits, float* __restrict__ probs, uint8_t* __restrict__ argmax,
+                                  int B, int h, int w, int H, int W, float sy, float sx) {
+    const int64_t total = (int64_t)B * H * W;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(idx % W), oy = (int)((idx / W) % H), b = (int)(idx / ((int64_t)W * H));
+        int y0, y1, x0, x1; float ly, lx;
+        bilinear_src(oy, sy, h, y0, y1, ly);
+        bilinear_src(ox, sx, w, x0, x1, lx);
+        const float* base = logits + (int64_t)b * h * w * kNCP;
+        const float* p00 = base + ((int64_t)y0 * w + x0) * kNCP; const float* p01 = base + ((int64_t)y0 * w + x1) * kNCP;
+        const float* p10 = base + ((int64_t)y1 * w + x0) * kNCP; const float* p11 = base + ((int64_t)y1 * w + x1) * kNCP;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        float z[kNC], mx = -INFINITY;
+        int am = 0;
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) {
+            z[c] = hy * (hx * p00[c] + lx * p01[c]) + ly * (hx * p10[c] + lx * p11[c]);
+            if (z[c] > mx) { mx = z[c]; am = c; }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) { z[c] = expf(z[c] - mx); s += z[c]; }
+        const float inv = 1.f / s;
+        const int64_t plane = (int64_t)H * W;
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) probs[((int64_t)b * kNC + c) * plane + (int64_t)oy * W + ox] = z[c] * inv;
+        if (argmax) argmax[idx] = (uint8_t)am;
+    }
+}
+
+// headaux: per-image channel sums of f0, then Linear(C -> 7)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ sums /*[B][C]*/, int HW, int C, int cg, int rpb) {
+    extern __shared__ float red[];                    // [rpb][C]
+    const int b = blockIdx.y, sub = threadIdx.x % cg, r = threadIdx.x / cg;
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0.f;
+    for (int row = blockIdx.x * rpb + r; row < HW; row += gridDim.x * rpb) {
+        float v[8];
+        load8(x + ((int64_t)b * HW + row) * C + sub * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[r * C + sub * 8 + i] = a[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int rr = 0; rr < rpb; ++rr) s += red[rr * C + c];
+        atomicAdd(sums + b * C + c, s);
+    }
+}
+
+__global__ void headaux_linear_kernel(const float* __restrict__ sums, const float* __restrict__ w, const float* __restrict__ bias,
+                                      float* __restrict__ scores, int B, int C, float inv_hw) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * kNC) return;
+    const int b = idx / kNC, o = idx % kNC;
+    float s = bias[o];
+    for (int c = 0; c < C; ++c) s += w[o * C + c] * (sums[b * C + c] * inv_hw);
+    scores[idx] = s;
+}
+
+static NeckGeom neck_geom(int B, int H, int W, const int* C, const int* h, const int* w) {
+    NeckGeom g; g.B = B; g.H = H; g.W = W; g.Ctot = 0;
+    for (int l = 0; l < 4; ++l) {
+        g.C[l] = C[l]; g.h[l] = h[l]; g.w[l] = w[l]; g.coff[l] = g.Ctot; g.Ctot += C[l];
+        g.sy[l] = ac_scale(h[l], H); g.sx[l] = ac_scale(w[l], W);
+    }
+    return g;
+}
+
+}  // namespace rss
+
+using namespace rss;
+
+extern "C" int rss_neck_gather_fwd(const void* f0, const void* f1, const void* f2, const void* f3, void* out,
+                                   int B, const int* C, const int* h, const int* w, int dtype, cudaStream_t st) {
+    if (B <= 0 || !C || !h || !w) return RSS_ERR_SHAPE;
+    for (int l = 0; l < 4; ++l) if (C[l] <= 0 || C[l] % 8 || h[l] <= 0 || w[l] <= 0) return RSS_ERR_SHAPE;
+    const NeckGeom g = neck_geom(B, h[0], w[0], C, h, w);
+    const int64_t total = (int64_t)B * g.H * g.W * (g.Ctot / 8);
+    int grid = (int)((total + 255) / 256);
+    if (grid > num_sms() * 16) grid = num_sms() * 16;
+    RSS_DISPATCH_DTYPE(dtype, neck_gather_fwd_kernel<T><<<grid, 256, 0, st>>>((const T*)f0, (const T*)f1, (const T*)f2, (const T*)f3, (T*)out, g));
+    return check_launch();
+}
+
+extern "C" int rss_neck_gather_bwd(const void* dcat, void* d0, void* d1, void* d2, void* d3,
+                                   int B, const int* C, const int* h, const int* w, int dtype, cudaStream_t st) {
+    if (B <= 0 || !C || !h || !w) return RSS_ERR_SHAPE;
+    for (int l = 0; l < 4; ++l) if (C[l] <= 0 || C[l] % 8 || h[l] <= 0 || w[l] <= 0) return RSS_ERR_SHAPE;
+    const NeckGeom g = neck_geom(B, h[0], w[0], C, h, w);
+    for (int l = 0; l < 4; ++l) {
+        const int64_t total = (int64_t)B * h[l] * w[l] * (C[l] / 8);
+        int grid = (int)((total + 255) / 256);
+        if (grid > num_sms() * 16) grid = num_sms() * 16;
+        RSS_DISPATCH_DTYPE(dtype, neck_gather_bwd_kernel<T><<<grid, 256, 0, st>>>((const T*)dcat, (T*)d0, (T*)d1, (T*)d2, (T*)d3, g, l));
+    }
+    return check_launch();
+}
+
+extern "C" int rss_head_fwd(const void* x, const float* w, const float* bias, float* logits_lr, int64_t pixels, int C,
+                            int dtype, cudaStream_t st) {
+    if (pixels <= 0 || C <= 0 || C % 8 || (size_t)kNC * C * sizeof(float) > 48 * 1024) return RSS_ERR_SHAPE;
+    int grid = (int)((pixels + 7) / 8);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    RSS_DISPATCH_DTYPE(dtype, head_fwd_kernel<T><<<grid, 256, kNC * C * sizeof(float), st>>>((const T*)x, w, bias, logits_lr, pixels, C));
+    return check_launch();
+}
+
+extern "C" int rss_head_bwd(const void* x, const float* dlogits_lr, const float* w, void* dx, float* dw_acc, float* db_acc,
+                            int64_t pixels, int C, int dtype, cudaStream_t st) {
+    if (pixels <= 0 || C <= 0 || C % 8) return RSS_ERR_SHAPE;
+    const int cg = C / 8;
+    int rpb = 256 / cg; if (rpb < 1) rpb = 1; if (rpb > 4) rpb = 4;
+    while (rpb > 1 && (size_t)rpb * kNC * C * sizeof(float) > 48 * 1024) --rpb;
+    const size_t smem = (size_t)rpb * kNC * C * sizeof(float);
+    if (smem > 48 * 1024) return RSS_ERR_SHAPE;
+    int grid = (int)((pixels + rpb - 1) / rpb);
+    if (grid > num_sms() * 4) grid = num_sms() * 4;
+    RSS_DISPATCH_DTYPE(dtype, head_bwd_kernel<T><<<grid, cg * rpb, smem, st>>>((const T*)x, dlogits_lr, w, (T*)dx, dw_acc, db_acc, pixels, C, cg, rpb));
+    return check_launch();
+}
+
+extern "C" int rss_head_probs(const float* logits_lr, float* probs, uint8_t* argmax, int B, int h, int w, int scale,
+                              cudaStream_t st) {
+    if (B <= 0 || h <= 0 || w <= 0 || scale <= 0) return RSS_ERR_SHAPE;
+    const int H = h * scale, W = w * scale;
+    const int64_t total = (int64_t)B * H * W;
+    int grid = (int)((total + 255) / 256);
+    if (grid > num_sms() * 16) grid = num_sms() * 16;
+    head_probs_kernel<<<grid, 256, 0, st>>>(logits_lr, probs, argmax, B, h, w, H, W, ac_scale(h, H), ac_scale(w, W));
+    return check_launch();
+}
+
+extern "C" int rss_headaux_fwd(const void* f0, const float* w, const float* bias, float* colsum_ws, float* scores,
+                               int B, int HW, int C, int dtype, cudaStream_t st) {
+    if (B <= 0 || HW <= 0 || C <= 0 || C % 8 || C > 1024) return RSS_ERR_SHAPE;
+    cudaError_t e = cudaMemsetAsync(colsum_ws, 0, (size_t)B * C * sizeof(float), st);
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return RSS_ERR_CUDA; }
+    const int cg = C / 8;
+    int rpb = 256 / cg; if (rpb < 1) rpb = 1;
+    int gx = (HW + rpb * 16 - 1) / (rpb * 16); if (gx < 1) gx = 1; if (gx > 64) gx = 64;
+    dim3 grid(gx, B);
+    RSS_DISPATCH_DTYPE(dtype, colsum_kernel<T><<<grid, cg * rpb, (size_t)rpb * C * sizeof(float), st>>>((const T*)f0, colsum_ws, HW, C, cg, rpb));
+    headaux_linear_kernel<<<(B * kNC + 127) / 128, 128, 0, st>>>(colsum_ws, w, bias, scores, B, C, 1.0f / (float)HW);
+    return check_launch();
+}

@@ -1,0 +1,267 @@
+"""HRNetV2-W32 backbone with one transformer block per multi-branch module, NHWC / sm_100a.
+
+Mirror of RSSFormer-TIP2023/module/baseline/base_hrnet/_hrnet_rssformer.py (class names, constructor
+signatures and state_dict keys preserved; file:line cited per class).  Every conv -> BN -> ReLU
+(+ residual) chain runs as  conv kernel -> fused BN-statistics -> one fused apply pass.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .conv import conv2d
+from .modules import FusedBNAct, GeneralTransformerBlock, BN_MOMENTUM
+
+# _hrnet_rssformer.py:97-125 (only the widths RSSFormer's configs use are listed: hrnetw32.py:9, hrnetw40.py)
+MODEL_EXTRA = {
+    "hrnetv2_w32": dict(
+        stage1=dict(num_modules=1, num_branches=1, block="BOTTLENECK", num_blocks=(4,), num_channels=(64,), fuse_method="SUM"),
+        stage2=dict(num_modules=1, num_branches=2, block="BASIC", num_blocks=(4, 4), num_channels=(32, 64), fuse_method="SUM"),
+        stage3=dict(num_modules=4, num_branches=3, block="BASIC", num_blocks=(4, 4, 4), num_channels=(32, 64, 128), fuse_method="SUM"),
+        stage4=dict(num_modules=3, num_branches=4, block="BASIC", num_blocks=(4, 4, 4, 4), num_channels=(32, 64, 128, 256), fuse_method="SUM")),
+}
+
+
+def _conv(cin, cout, k, stride=1, padding=0):
+    return nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=padding, bias=False)
+
+
+def _run(conv, bn, x, residual=None):
+    """conv (no bias) -> fused BN(+act)(+residual)."""
+    return bn(conv2d(x, conv.weight, None, conv.stride[0], conv.padding[0], conv.dilation[0]), residual)
+
+
+class BasicBlock(nn.Module):
+    """_hrnet_rssformer.py:216-246"""
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = _conv(inplanes, planes, 3, stride, 1)
+        self.bn1 = FusedBNAct(planes, _lib.ACT_RELU)
+        self.conv2 = _conv(planes, planes, 3, 1, 1)
+        self.bn2 = FusedBNAct(planes, _lib.ACT_RELU)          # relu(bn2(.) + residual)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        residual = x if self.downsample is None else _run(self.downsample[0], self.downsample[1], x)
+        out = _run(self.conv1, self.bn1, x)
+        return _run(self.conv2, self.bn2, out, residual)
+
+
+class Bottleneck(nn.Module):
+    """_hrnet_rssformer.py:249-287"""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = _conv(inplanes, planes, 1)
+        self.bn1 = FusedBNAct(planes, _lib.ACT_RELU)
+        self.conv2 = _conv(planes, planes, 3, stride, 1)
+        self.bn2 = FusedBNAct(planes, _lib.ACT_RELU)
+        self.conv3 = _conv(planes, planes * self.expansion, 1)
+        self.bn3 = FusedBNAct(planes * self.expansion, _lib.ACT_RELU)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        residual = x if self.downsample is None else _run(self.downsample[0], self.downsample[1], x)
+        out = _run(self.conv1, self.bn1, x)
+        out = _run(self.conv2, self.bn2, out)
+        return _run(self.conv3, self.bn3, out, residual)
+
+
+blocks_dict = {"BASIC": BasicBlock, "BOTTLENECK": Bottleneck}
+
+
+def _downsample(cin, cout, stride):
+    return nn.Sequential(_conv(cin, cout, 1, stride), FusedBNAct(cout, _lib.ACT_NONE))
+
+
+class HighResolutionModule(nn.Module):
+    """_hrnet_rssformer.py:290-437"""
+
+    def __init__(self, num_branches, blocks, num_blocks, num_inchannels, num_channels, fuse_method, multi_scale_output=True):
+        super().__init__()
+        if not (num_branches == len(num_blocks) == len(num_channels) == len(num_inchannels)):
+            raise ValueError("NUM_BRANCHES({}) <> NUM_BLOCKS/NUM_CHANNELS/NUM_INCHANNELS".format(num_branches))
+        self.num_inchannels = num_inchannels
+        self.fuse_method = fuse_method
+        self.num_branches = num_branches
+        self.multi_scale_output = multi_scale_output
+        self.branches = nn.ModuleList([self._make_one_branch(i, blocks, num_blocks, num_channels) for i in range(num_branches)])
+        self.fuse_layers = self._make_fuse_layers()
+        self.relu = nn.ReLU(False)
+        self.transformer = GeneralTransformerBlock(num_channels[0], planes=num_channels[0], num_heads=2)   # :308
+
+    def _make_one_branch(self, i, block, num_blocks, num_channels, stride=1):
+        downsample = None
+        if stride != 1 or self.num_inchannels[i] != num_channels[i] * block.expansion:
+            downsample = _downsample(self.num_inchannels[i], num_channels[i] * block.expansion, stride)
+        layers = [block(self.num_inchannels[i], num_channels[i], stride, downsample)]
+        self.num_inchannels[i] = num_channels[i] * block.expansion
+        layers += [block(self.num_inchannels[i], num_channels[i]) for _ in range(1, num_blocks[i])]
+        return nn.Sequential(*layers)
+
+    def _make_fuse_layers(self):
+        if self.num_branches == 1:
+            return None
+        nb, ch = self.num_branches, self.num_inchannels
+        fuse_layers = []
+        for i in range(nb if self.multi_scale_output else 1):
+            row = []
+            for j in range(nb):
+                if j > i:       # 1x1 conv + BN + nearest up-sampling (:372-380)
+                    row.append(nn.Sequential(_conv(ch[j], ch[i], 1), FusedBNAct(ch[i], _lib.ACT_NONE),
+                                             nn.Upsample(scale_factor=2 ** (j - i), mode="nearest")))
+                elif j == i:
+                    row.append(None)
+                else:           # chain of stride-2 3x3 convs, ReLU on all but the last (:384-402)
+                    chain = []
+                    for k in range(i - j):
+                        last = k == i - j - 1
+                        cout = ch[i] if last else ch[j]
+                        seq = [_conv(ch[j], cout, 3, 2, 1), FusedBNAct(cout, _lib.ACT_NONE if last else _lib.ACT_RELU)]
+                        if not last:
+                            seq.append(nn.Identity())       # was nn.ReLU(False): fused into the BN pass
+                        chain.append(nn.Sequential(*seq))
+                    row.append(nn.Sequential(*chain))
+            fuse_layers.append(nn.ModuleList(row))
+        return nn.ModuleList(fuse_layers)
+
+    def get_num_inchannels(self):
+        return self.num_inchannels
+
+    def _fuse(self, i, j, x):
+        layer = self.fuse_layers[i][j]
+        if j > i:
+            return layer[2](_run(layer[0], layer[1], x))
+        for seq in layer:
+            x = _run(seq[0], seq[1], x)
+        return x
+
+    def forward(self, x):
+        if self.num_branches == 1:
+            return [self.branches[0](x[0])]
+        x = [self.branches[i](x[i]) for i in range(self.num_branches)]
+        x_fuse = []
+        for i in range(len(self.fuse_layers)):
+            low = None
+            for j in range(1, self.num_branches):
+                term = x[j] if i == j else self._fuse(i, j, x[j])
+                low = term if low is None else low + term
+            if i == 0:
+                y = self.transformer(low, x[0])              # (:430-431) x[0] enters only as keys/values
+            else:
+                y = self._fuse(i, 0, x[0]) + low
+            x_fuse.append(F.relu(y))
+        return x_fuse
+
+
+class HighResolutionNet(nn.Module):
+    """_hrnet_rssformer.py:446-650"""
+
+    def __init__(self, extra, norm_eval=True, zero_init_residual=False, frozen_stages=-1):
+        super().__init__()
+        self.norm_eval, self.frozen_stages, self.zero_init_residual, self.extra = norm_eval, frozen_stages, zero_init_residual, extra
+        self.conv1 = _conv(3, 64, 3, 2, 1)
+        self.bn1 = FusedBNAct(64, _lib.ACT_RELU)
+        self.conv2 = _conv(64, 64, 3, 2, 1)
+        self.bn2 = FusedBNAct(64, _lib.ACT_RELU)
+        self.relu = nn.ReLU(inplace=True)
+
+        self.stage1_cfg = extra["stage1"]
+        block = blocks_dict[self.stage1_cfg["block"]]
+        nch = self.stage1_cfg["num_channels"][0]
+        self.layer1 = self._make_layer(block, 64, nch, self.stage1_cfg["num_blocks"][0])
+        pre = [nch * block.expansion]
+        for s in (2, 3, 4):
+            cfg = extra["stage%d" % s]
+            setattr(self, "stage%d_cfg" % s, cfg)
+            block = blocks_dict[cfg["block"]]
+            nch = [c * block.expansion for c in cfg["num_channels"]]
+            setattr(self, "transition%d" % (s - 1), self._make_transition_layer(pre, nch))
+            stage, pre = self._make_stage(cfg, nch)
+            setattr(self, "stage%d" % s, stage)
+        if frozen_stages >= 0:
+            raise NotImplementedError("frozen_stages >= 0 is not used by the RSSFormer config (hrnetw32.py:12)")
+
+    def _make_transition_layer(self, pre, cur):
+        layers = []
+        for i in range(len(cur)):
+            if i < len(pre):
+                if cur[i] != pre[i]:
+                    layers.append(nn.Sequential(_conv(pre[i], cur[i], 3, 1, 1), FusedBNAct(cur[i], _lib.ACT_RELU), nn.Identity()))
+                else:
+                    layers.append(None)
+            else:
+                chain = []
+                for j in range(i + 1 - len(pre)):
+                    cin = pre[-1]
+                    cout = cur[i] if j == i - len(pre) else cin
+                    chain.append(nn.Sequential(_conv(cin, cout, 3, 2, 1), FusedBNAct(cout, _lib.ACT_RELU), nn.Identity()))
+                layers.append(nn.Sequential(*chain))
+        return nn.ModuleList(layers)
+
+    def _make_layer(self, block, inplanes, planes, blocks, stride=1):
+        downsample = None
+        if stride != 1 or inplanes != planes * block.expansion:
+            downsample = _downsample(inplanes, planes * block.expansion, stride)
+        layers = [block(inplanes, planes, stride, downsample)]
+        layers += [block(planes * block.expansion, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*layers)
+
+    def _make_stage(self, cfg, num_inchannels, multi_scale_output=True):
+        modules = []
+        for i in range(cfg["num_modules"]):
+            reset = not (not multi_scale_output and i == cfg["num_modules"] - 1)
+            modules.append(HighResolutionModule(cfg["num_branches"], blocks_dict[cfg["block"]], cfg["num_blocks"],
+                                                num_inchannels, list(cfg["num_channels"]), cfg["fuse_method"], reset))
+            num_inchannels = modules[-1].get_num_inchannels()
+        return nn.Sequential(*modules), num_inchannels
+
+    @staticmethod
+    def _transition(layer, x):
+        if layer[0].__class__ is nn.Sequential:        # chain of stride-2 conv+BN+ReLU
+            for seq in layer:
+                x = _run(seq[0], seq[1], x)
+            return x
+        return _run(layer[0], layer[1], x)
+
+    def forward(self, x):
+        x = _run(self.conv1, self.bn1, x)
+        x = _run(self.conv2, self.bn2, x)
+        x = self.layer1(x)
+        x_list = [x if self.transition1[i] is None else self._transition(self.transition1[i], x)
+                  for i in range(self.stage2_cfg["num_branches"])]
+        y_list = self.stage2(x_list)
+        x_list = [y_list[i] if self.transition2[i] is None else self._transition(self.transition2[i], y_list[-1])
+                  for i in range(self.stage3_cfg["num_branches"])]
+        y_list = self.stage3(x_list)
+        x_list = [y_list[i] if self.transition3[i] is None else self._transition(self.transition3[i], y_list[-1])
+                  for i in range(self.stage4_cfg["num_branches"])]
+        return self.stage4(x_list)
+
+    def train(self, mode=True):
+        super().train(mode)
+        if mode and self.norm_eval:
+            for m in self.modules():
+                if isinstance(m, FusedBNAct) and not m.sync:
+                    m.eval()
+        return self
+
+
+def _factory(name):
+    def build(pretrained=False, weight_path=None, norm_eval=False, frozen_stages=-1):
+        model = HighResolutionNet(MODEL_EXTRA[name], norm_eval, zero_init_residual=False, frozen_stages=frozen_stages)
+        if pretrained:
+            if weight_path is None:
+                raise FileNotFoundError("no network here: pass weight_path for pretrained=True (_hrnet_rssformer.py:669-675)")
+            model.load_state_dict(torch.load(weight_path, map_location="cpu"), strict=False)
+        return model
+    build.__name__ = name
+    return build
+
+
+hrnetv2_w32 = _factory("hrnetv2_w32")

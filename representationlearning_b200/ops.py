@@ -1,0 +1,393 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels (include/rss_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams and records the tape; every forward and
+backward below is a call into librss_b200.so on `torch.cuda.current_stream()`.  Tensors cross the
+boundary as raw NHWC device pointers (channels_last memory format on the torch side).
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import AttnGrads, AttnParams
+from ._lib import check as _check
+
+CL = torch.channels_last
+# kernels launched per C-ABI call (for bench.py's `gpu_launches`; counted from the csrc/*.cu launch sites)
+KERNELS_PER_CALL = {
+    "rss_layernorm_fwd": 1, "rss_layernorm_bwd": 1, "rss_attn_fwd": 5, "rss_attn_bwd": 7, "rss_bn_stats": 1, "rss_bn_combine": 1,
+    "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1,
+    "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 4, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
+    "rss_headaux_fwd": 2, "rss_seg_loss_fwd": 2, "rss_seg_loss_bwd": 1, "rss_grad_sumsq": 1, "rss_sgd_step": 1,
+    "rss_conv_fwd": 1, "rss_conv_dgrad": 1, "rss_conv_wgrad": 1,
+}
+COUNTERS = {"launches": 0, "calls": 0}
+TIMED = {}            # op name -> list of (start_event, end_event), filled only while bench.py enables it
+TIMED_OPS = set()
+
+
+def check(rc, what):
+    COUNTERS["launches"] += KERNELS_PER_CALL.get(what, 1)
+    COUNTERS["calls"] += 1
+    _check(rc, what)
+
+
+class timed:
+    """records CUDA events around a C-ABI call on the launching stream when bench.py asks for `name`"""
+
+    def __init__(self, name):
+        self.on = name in TIMED_OPS
+        self.name = name
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e1.record()
+            TIMED.setdefault(self.name, []).append((self.e0, self.e1))
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return _lib.RSS_F32
+    if t.dtype == torch.bfloat16:
+        return _lib.RSS_BF16
+    raise _lib.RssError("unsupported activation dtype %s (float32 or bfloat16)" % t.dtype)
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t):
+    """fp32 contiguous view of a parameter (parameters are fp32 masters; a cast is a bug upstream)."""
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.detach().float().contiguous()
+    return t
+
+
+def nhwc(t):
+    """Return `t` (logical NCHW) laid out NHWC in memory."""
+    return t.contiguous(memory_format=CL)
+
+
+def _world(group):
+    if group is None or not dist.is_available() or not dist.is_initialized():
+        return 1
+    return dist.get_world_size(group if group is not True else None)
+
+
+# ----------------------------------------------------------------------------------------------
+# LayerNorm over channels of NHWC tokens
+# ----------------------------------------------------------------------------------------------
+class LayerNormNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        _lib.require_device()
+        lib = _lib.load()
+        x = nhwc(x)
+        B, C, H, W = x.shape
+        rows = B * H * W
+        y = torch.empty_like(x, memory_format=CL)
+        stats = torch.empty(2, rows, device=x.device, dtype=torch.float32)
+        g, b = _f32(gamma), _f32(beta)
+        check(lib.rss_layernorm_fwd(_p(x), _p(y), _p(stats[0]), _p(stats[1]), _p(g), _p(b), eps, rows, C, _dt(x), _st()),
+              "rss_layernorm_fwd")
+        ctx.save_for_backward(x, stats, g)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, stats, g = ctx.saved_tensors
+        dy = nhwc(dy)
+        B, C, H, W = x.shape
+        rows = B * H * W
+        dx = torch.empty_like(x, memory_format=CL)
+        dgb = torch.zeros(2, C, device=x.device, dtype=torch.float32)
+        check(lib.rss_layernorm_bwd(_p(dy), _p(x), _p(stats[0]), _p(stats[1]), _p(g), None, _p(dx), _p(dgb[0]), _p(dgb[1]),
+                                    rows, C, _dt(x), _st()), "rss_layernorm_bwd")
+        return dx, dgb[0], dgb[1], None
+
+
+# ----------------------------------------------------------------------------------------------
+# gate + window attention region
+# ----------------------------------------------------------------------------------------------
+_ATTN_NAMES = ("ln_w", "ln_b", "sa1_w", "sa2_w", "lvl_w", "lvl_b", "q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w", "o_b")
+
+
+class WindowAttention(torch.autograd.Function):
+    """out = [x +] Attn([LN1](x), [LN1](y)); tensors are (B,C,H,W) channels_last.
+    params: 14 tensors in _ATTN_NAMES order; ln_w/ln_b may be None (no norm1)."""
+
+    @staticmethod
+    def forward(ctx, x, y, eps, residual, *params):
+        _lib.require_device()
+        lib = _lib.load()
+        x, y = nhwc(x), nhwc(y)
+        B, C, H, W = x.shape
+        HW = H * W
+        has_ln = params[0] is not None
+        ps = [None if p is None else _f32(p) for p in params]
+        ap = AttnParams()
+        for n, p in zip(_ATTN_NAMES, ps):
+            setattr(ap, n, _p(p))
+        ap.ln_eps, ap.C, ap.num_heads, ap.window = float(eps), C, 2, 7
+        dev = x.device
+        xn = torch.empty_like(x, memory_format=CL) if has_ln else None
+        yn = torch.empty_like(x, memory_format=CL) if has_ln else None
+        ln_stats = torch.empty(4, B * HW, device=dev, dtype=torch.float32) if has_ln else None
+        pooled = torch.empty(B, 4, HW, device=dev, dtype=torch.float32)
+        amax = torch.empty(B, 2, HW, device=dev, dtype=torch.uint8)
+        smap = torch.empty(B, 2, HW, device=dev, dtype=torch.float32)
+        gmap = torch.empty(B, 2, HW, device=dev, dtype=torch.float32)
+        out = torch.empty_like(x, memory_format=CL)
+        flags = 0 if residual else 1
+        with timed("rss_attn_fwd"):
+            check(lib.rss_attn_fwd(_p(x), _p(y), ctypes.byref(ap), B, H, W, _dt(x), flags, _p(xn), _p(yn), _p(ln_stats),
+                                   _p(pooled), _p(amax), _p(smap), _p(gmap), _p(out), _st()), "rss_attn_fwd")
+        ctx.save_for_backward(x, y, xn, yn, ln_stats, pooled, amax, smap, gmap, *ps)
+        ctx.eps, ctx.flags = float(eps), flags
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x, y, xn, yn, ln_stats, pooled, amax, smap, gmap = ctx.saved_tensors[:9]
+        ps = ctx.saved_tensors[9:]
+        dout = nhwc(dout)
+        B, C, H, W = x.shape
+        ap = AttnParams()
+        for n, p in zip(_ATTN_NAMES, ps):
+            setattr(ap, n, _p(p))
+        ap.ln_eps, ap.C, ap.num_heads, ap.window = ctx.eps, C, 2, 7
+        grads = [None if p is None else torch.zeros_like(p) for p in ps]
+        ag = AttnGrads()
+        for n, g in zip(_ATTN_NAMES, grads):
+            setattr(ag, n, _p(g))
+        wsb = lib.rss_attn_bwd_workspace_bytes(B, H, W, _dt(x))
+        ws = torch.empty(wsb, device=x.device, dtype=torch.uint8)
+        dx = torch.empty_like(x, memory_format=CL)
+        dy = torch.empty_like(x, memory_format=CL)
+        with timed("rss_attn_bwd"):
+            check(lib.rss_attn_bwd(_p(dout), _p(x), _p(y), ctypes.byref(ap), B, H, W, _dt(x), ctx.flags, _p(xn), _p(yn),
+                                   _p(ln_stats), _p(pooled), _p(amax), _p(smap), _p(gmap), _p(ws), wsb, _p(dx), _p(dy),
+                                   ctypes.byref(ag), _st()), "rss_attn_bwd")
+        return (dx, dy, None, None) + tuple(grads)
+
+
+# ----------------------------------------------------------------------------------------------
+# BatchNorm(+SyncBN) + activation (+ residual)
+# ----------------------------------------------------------------------------------------------
+class BNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, training, momentum, eps, act, group):
+        _lib.require_device()
+        lib = _lib.load()
+        x = nhwc(x)
+        if residual is not None:
+            residual = nhwc(residual)
+            if residual.dtype != x.dtype:
+                residual = residual.to(x.dtype)
+        B, C, H, W = x.shape
+        rows = B * H * W
+        dev, dt, st = x.device, _dt(x), _st()
+        g, b = _f32(gamma), _f32(beta)
+        aff = torch.empty(4, C, device=dev, dtype=torch.float32)      # mean, invstd, scale, shift
+        world = _world(group) if training else 1
+        if training:
+            nparts = lib.rss_bn_stats_nparts(rows, C)
+            part = torch.empty(nparts * C * 2 + nparts, device=dev, dtype=torch.float32)
+            cnt = part[nparts * C * 2:]
+            check(lib.rss_bn_stats(_p(x), _p(part), _p(cnt), rows, C, dt, st), "rss_bn_stats")
+            stat = torch.empty(C * 2 + 1, device=dev, dtype=torch.float32)
+            check(lib.rss_bn_combine(_p(part), _p(cnt), nparts, C, _p(stat), _p(stat[C * 2:]), st), "rss_bn_combine")
+            if world > 1:     # SyncBN: exchange (mean, M2, count) per rank, Chan-combine again
+                gathered = torch.empty(world, C * 2 + 1, device=dev, dtype=torch.float32)
+                dist.all_gather_into_tensor(gathered, stat, group=None if group is True else group)
+                parts = gathered[:, :C * 2].contiguous()
+                cnts = gathered[:, C * 2].contiguous()
+                check(lib.rss_bn_combine(_p(parts), _p(cnts), world, C, _p(stat), _p(stat[C * 2:]), st), "rss_bn_combine")
+            check(lib.rss_bn_finalize(_p(stat), _p(stat[C * 2:]), _p(g), _p(b), _p(running_mean), _p(running_var),
+                                      momentum, eps, C, _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), st), "rss_bn_finalize")
+        else:
+            check(lib.rss_bn_eval_affine(_p(g), _p(b), _p(running_mean), _p(running_var), eps, C,
+                                         _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), st), "rss_bn_eval_affine")
+        y = torch.empty_like(x, memory_format=CL)
+        check(lib.rss_bn_act_fwd(_p(x), _p(residual), _p(y), _p(aff[2]), _p(aff[3]), rows, C, act, dt, st), "rss_bn_act_fwd")
+        ctx.save_for_backward(x, y if act == _lib.ACT_RELU else None, aff)
+        ctx.act, ctx.training, ctx.group, ctx.world, ctx.has_res = act, training, group, world, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, y, aff = ctx.saved_tensors
+        dy = nhwc(dy)
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        B, C, H, W = x.shape
+        rows = B * H * W
+        dt, st = _dt(x), _st()
+        sums = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+        check(lib.rss_bn_bwd_reduce(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(sums),
+                                    rows, C, ctx.act, dt, st), "rss_bn_bwd_reduce")
+        dbeta, dgamma = sums[:C], sums[C:]
+        if ctx.training:
+            red = sums
+            if ctx.world > 1:
+                dbeta, dgamma = dbeta.clone(), dgamma.clone()
+                dist.all_reduce(red, group=None if ctx.group is True else ctx.group)
+            inv_count = 1.0 / (rows * ctx.world)
+        else:                       # eval-mode BN is a fixed affine map: no batch-statistic terms
+            red = torch.zeros_like(sums)
+            inv_count = 0.0
+        dx = torch.empty_like(x, memory_format=CL)
+        dres = torch.empty_like(x, memory_format=CL) if ctx.has_res else None
+        check(lib.rss_bn_bwd_apply(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(red), inv_count,
+                                   _p(dx), _p(dres), rows, C, ctx.act, dt, st), "rss_bn_bwd_apply")
+        return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# neck gather (3x bilinear up + concat), head, headaux, loss
+# ----------------------------------------------------------------------------------------------
+def _geom(feats):
+    n = len(feats)
+    C = (ctypes.c_int * 4)(*[f.shape[1] for f in feats])
+    h = (ctypes.c_int * 4)(*[f.shape[2] for f in feats])
+    w = (ctypes.c_int * 4)(*[f.shape[3] for f in feats])
+    assert n == 4
+    return C, h, w
+
+
+class NeckGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f0, f1, f2, f3):
+        _lib.require_device()
+        lib = _lib.load()
+        feats = [nhwc(f) for f in (f0, f1, f2, f3)]
+        feats = [f if f.dtype == feats[0].dtype else f.to(feats[0].dtype) for f in feats]
+        B = feats[0].shape[0]
+        C, h, w = _geom(feats)
+        out = torch.empty((B, sum(f.shape[1] for f in feats), feats[0].shape[2], feats[0].shape[3]),
+                          device=f0.device, dtype=feats[0].dtype, memory_format=CL)
+        check(lib.rss_neck_gather_fwd(*[_p(f) for f in feats], _p(out), B, C, h, w, _dt(out), _st()), "rss_neck_gather_fwd")
+        ctx.shapes = [tuple(f.shape) for f in feats]
+        return out
+
+    @staticmethod
+    def backward(ctx, dcat):
+        lib = _lib.load()
+        dcat = nhwc(dcat)
+        ds = [torch.empty(s, device=dcat.device, dtype=dcat.dtype, memory_format=CL) for s in ctx.shapes]
+        C, h, w = _geom(ds)
+        check(lib.rss_neck_gather_bwd(_p(dcat), *[_p(d) for d in ds], ctx.shapes[0][0], C, h, w, _dt(dcat), _st()),
+              "rss_neck_gather_bwd")
+        return tuple(ds)
+
+
+class HeadConv(torch.autograd.Function):
+    """(B,C,h,w) channels_last -> low-resolution logits (B,h,w,8) fp32 (class 7 = padding)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _lib.require_device()
+        lib = _lib.load()
+        x = nhwc(x)
+        B, C, h, w = x.shape
+        wt = _f32(weight).reshape(7, C)
+        logits = torch.empty(B, h, w, 8, device=x.device, dtype=torch.float32)
+        check(lib.rss_head_fwd(_p(x), _p(wt), _p(_f32(bias)), _p(logits), B * h * w, C, _dt(x), _st()), "rss_head_fwd")
+        ctx.save_for_backward(x, wt)
+        ctx.wshape = tuple(weight.shape)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = _lib.load()
+        x, wt = ctx.saved_tensors
+        B, C, h, w = x.shape
+        dlogits = dlogits.contiguous()
+        dx = torch.empty_like(x, memory_format=CL)
+        dw = torch.zeros(7, C, device=x.device, dtype=torch.float32)
+        db = torch.zeros(7, device=x.device, dtype=torch.float32)
+        check(lib.rss_head_bwd(_p(x), _p(dlogits), _p(wt), _p(dx), _p(dw), _p(db), B * h * w, C, _dt(x), _st()), "rss_head_bwd")
+        return dx, dw.reshape(ctx.wshape), db
+
+
+def head_probs(logits_lr, scale, want_argmax=False):
+    """eval output: softmax over classes of the x`scale` bilinear (align_corners=True) up-sampling; NCHW fp32."""
+    lib = _lib.load()
+    B, h, w, _ = logits_lr.shape
+    probs = torch.empty(B, 7, h * scale, w * scale, device=logits_lr.device, dtype=torch.float32)
+    am = torch.empty(B, h * scale, w * scale, device=logits_lr.device, dtype=torch.uint8) if want_argmax else None
+    check(lib.rss_head_probs(_p(logits_lr), _p(probs), _p(am), B, h, w, scale, _st()), "rss_head_probs")
+    return (probs, am) if want_argmax else probs
+
+
+def headaux(f0, weight, bias):
+    """AdaptiveAvgPool2d(1) + Linear(C,7); no gradient (the reference consumes it under no_grad)."""
+    _lib.require_device()
+    lib = _lib.load()
+    f0 = nhwc(f0.detach())
+    B, C, H, W = f0.shape
+    ws = torch.empty(B * C, device=f0.device, dtype=torch.float32)
+    scores = torch.empty(B, 7, device=f0.device, dtype=torch.float32)
+    check(lib.rss_headaux_fwd(_p(f0), _p(_f32(weight)), _p(_f32(bias)), _p(ws), _p(scores), B, H * W, C, _dt(f0), _st()),
+          "rss_headaux_fwd")
+    return scores
+
+
+class SegLoss(torch.autograd.Function):
+    """fc_loss of SegmentationLossaux on LOW-resolution logits (the x`scale` up-sampling is fused)."""
+
+    @staticmethod
+    def forward(ctx, logits_lr, labels, aux_scores, scale, ignore_index):
+        lib = _lib.load()
+        B, h, w, _ = logits_lr.shape
+        logits_lr = logits_lr.contiguous()
+        labels = labels.contiguous()
+        if labels.dtype != torch.int64:
+            labels = labels.long()
+        assert labels.shape == (B, h * scale, w * scale), (labels.shape, (B, h * scale, w * scale))
+        dev = logits_lr.device
+        acc = torch.empty(lib.rss_seg_loss_acc_floats(B), device=dev, dtype=torch.float32)
+        gdir = torch.empty(B, h, w, 8, device=dev, dtype=torch.float32)
+        out4 = torch.empty(4, device=dev, dtype=torch.float32)
+        check(lib.rss_seg_loss_fwd(_p(logits_lr), _p(labels), _p(aux_scores.contiguous()), _p(acc), _p(gdir), _p(out4),
+                                   B, h, w, scale, ignore_index, _st()), "rss_seg_loss_fwd")
+        ctx.save_for_backward(gdir, out4)
+        return out4[0].clone()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        lib = _lib.load()
+        gdir, out4 = ctx.saved_tensors
+        B, h, w, _ = gdir.shape
+        up = dloss.detach().float().reshape(1).contiguous()
+        dl = torch.empty_like(gdir)
+        check(lib.rss_seg_loss_bwd(_p(gdir), _p(out4), _p(up), _p(dl), B, h, w, _st()), "rss_seg_loss_bwd")
+        return dl, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# optimiser
+# ----------------------------------------------------------------------------------------------
+def grad_sumsq(flat_grad, grad_scale, out):
+    check(_lib.load().rss_grad_sumsq(_p(flat_grad), flat_grad.numel(), grad_scale, _p(out), _st()), "rss_grad_sumsq")
+
+
+def sgd_step(flat_p, flat_g, flat_m, sumsq, grad_scale, max_norm, lr, momentum, weight_decay, first_step, zero_grad,
+             shadow=None):
+    check(_lib.load().rss_sgd_step(_p(flat_p), _p(flat_g), _p(flat_m), flat_p.numel(), _p(sumsq), grad_scale, max_norm, lr,
+                                   momentum, weight_decay, int(first_step), int(zero_grad), _p(shadow), _st()), "rss_sgd_step")

@@ -1,0 +1,403 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C ABI, against
+  (1) the oracle on the same seeded inputs, (2) the committed golden vectors the REFERENCE produced,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Tolerance: BASELINE.json north_star states 1e-3 relative for floating point -> TOL_F32 (fp32 activations,
+error measured against the tensor's max magnitude); bf16 activations are held to TOL_BF16 (the reference's
+own bf16 autocast differs from its fp32 forward by 5.9e-3 relative)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import rssformer_ref as R
+
+pytestmark = pytest.mark.gpu
+TOL_F32 = 1e-3
+TOL_BF16 = 4e-2
+BLK = "backbone.hrnet.stage2.0.transformer."
+DEV = "cuda"
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def nchw_from(t):
+    return t.to(DEV).contiguous(memory_format=torch.channels_last)
+
+
+@pytest.fixture(scope="module")
+def P():
+    import representationlearning_b200 as P
+    P._lib.require_device()
+    return P
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 32, 15, 15), (1, 32, 128, 128), (3, 64, 7, 9)])
+def test_layernorm(P, report, dtype, shape):
+    from representationlearning_b200 import ops
+    torch.manual_seed(1)
+    B, C, H, W = shape
+    x = torch.randn(shape).to(dtype).float()
+    g, b, dy = torch.randn(C), torch.randn(C), torch.randn(shape).to(dtype).float()
+    xr = x.clone().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    yr = R.layer_norm(xr.permute(0, 2, 3, 1), gr, br).permute(0, 3, 1, 2)
+    yr.backward(dy)
+    xc = nchw_from(x.to(dtype)).requires_grad_(True)
+    gc, bc = g.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    yc = ops.LayerNormNHWC.apply(xc, gc, bc, 1e-6)
+    yc.backward(nchw_from(dy.to(dtype)))
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    errs = dict(y=rel(yc.float(), yr), dx=rel(xc.grad.float(), xr.grad), dg=rel(gc.grad, gr.grad), db=rel(bc.grad, br.grad))
+    report["layernorm_%s_%s" % (str(dtype)[6:], "x".join(map(str, shape)))] = errs
+    assert max(errs.values()) < tol, errs
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("shape,res", [((2, 32, 16, 16), False), ((2, 64, 9, 11), True), ((1, 480, 8, 8), False), ((4, 128, 32, 32), True)])
+def test_bn_act(P, report, dtype, act, shape, res):
+    from representationlearning_b200 import ops
+    torch.manual_seed(2)
+    B, C, H, W = shape
+    x = (torch.randn(shape) * 2 + 0.5).to(dtype).float()
+    r = torch.randn(shape).to(dtype).float() if res else None
+    g, b = torch.rand(C) + 0.5, torch.randn(C) * 0.2
+    rm, rv = torch.randn(C) * 0.1, torch.rand(C) + 0.5
+    dy = torch.randn(shape).to(dtype).float()
+    sd = {"bn.weight": g.clone().requires_grad_(True), "bn.bias": b.clone().requires_grad_(True), "bn.running_mean": rm.clone(),
+          "bn.running_var": rv.clone(), "bn.num_batches_tracked": torch.tensor(0)}
+    ctx = R.Ctx(sd, True)
+    xr = x.clone().requires_grad_(True)
+    rr = r.clone().requires_grad_(True) if res else None
+    z = R._bn(ctx, xr, "bn")
+    if res:
+        z = z + rr
+    yr = [lambda t: t, torch.relu, R.gelu][act](z)
+    yr.backward(dy)
+    xc = nchw_from(x.to(dtype)).requires_grad_(True)
+    rc = nchw_from(r.to(dtype)).requires_grad_(True) if res else None
+    gc, bc = g.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    rmc, rvc = rm.to(DEV), rv.to(DEV)
+    yc = ops.BNAct.apply(xc, rc, gc, bc, rmc, rvc, True, 0.1, 1e-5, act, None)
+    yc.backward(nchw_from(dy.to(dtype)))
+    errs = dict(y=rel(yc.float(), yr), dx=rel(xc.grad.float(), xr.grad), dg=rel(gc.grad, sd["bn.weight"].grad),
+                db=rel(bc.grad, sd["bn.bias"].grad), rm=rel(rmc, ctx.new_stats["bn.running_mean"]),
+                rv=rel(rvc, ctx.new_stats["bn.running_var"]))
+    if res:
+        errs["dres"] = rel(rc.grad.float(), rr.grad)
+    report["bn_act%d_%s_%s" % (act, str(dtype)[6:], "x".join(map(str, shape)))] = errs
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    assert max(errs.values()) < tol, errs
+
+
+def _block_product(P, dtype):
+    blk = P.GeneralTransformerBlock(32, 32, 2).to(DEV)
+    sd = {k[len(BLK):]: v for k, v in R.synth_state_dict(2333).items() if k.startswith(BLK)}
+    blk.load_state_dict(sd)
+    blk.train()
+    return blk
+
+
+@pytest.mark.parametrize("name", ["block_B2_H15_W15_seed11", "block_B2_H16_W16_seed12", "block_B1_H14_W21_seed13",
+                                  "block_B1_H28_W28_seed14"])
+def test_transformer_block_vs_reference_golden_fp32(P, report, name):
+    """whole GeneralTransformerBlock (a1-a5) forward + backward against vectors produced by the reference itself"""
+    from oracle.gen_golden import block_inputs
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    B, H, W, seed = [int(x) for x in re.match(r"block_B(\d+)_H(\d+)_W(\d+)_seed(\d+)", name).groups()]
+    blk = _block_product(P, torch.float32)
+    x, y, dout = [t.float() for t in block_inputs(B, 32, H, W, seed)]
+    xc, yc = nchw_from(x).requires_grad_(True), nchw_from(y).requires_grad_(True)
+    out = blk(xc, yc)
+    out.backward(nchw_from(dout))
+    errs = dict(out=rel(out, g["out"]), dx=rel(xc.grad, g["dx"]), dy=rel(yc.grad, g["dy"]))
+    gmax = max(np.abs(g[k]).max() for k in g.files if k.startswith("grad."))
+    worst = ("", 0.0)
+    for k, p in blk.named_parameters():
+        d = (p.grad.detach().double().cpu() - torch.as_tensor(g["grad." + k]).double()).abs().max().item() / gmax
+        errs["grad." + k] = d
+    for k, v in blk.state_dict().items():
+        if "running" in k:
+            errs["stat." + k] = rel(v, g["stat." + k])
+    report[name] = errs
+    bad = {k: v for k, v in errs.items() if not v < TOL_F32}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("shape", [(2, 15, 15), (1, 16, 16), (2, 14, 21), (1, 128, 128)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_window_attention_region_vs_oracle(P, report, shape, dtype):
+    """attention half only (LN1 x2 + gate + pad/window + Mhca + residual) vs the oracle restatement"""
+    from representationlearning_b200 import ops
+    B, H, W = shape
+    torch.manual_seed(3)
+    sd = {k: v for k, v in R.synth_state_dict(2333).items() if k.startswith(BLK)}
+    x = torch.randn(B, 32, H, W).to(dtype).float(); y = torch.randn(B, 32, H, W).to(dtype).float()
+    dout = torch.randn(B, 32, H, W).to(dtype).float()
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    ctx = R.Ctx(sdg, True)
+    xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    t = xr.reshape(B, 32, H * W).permute(0, 2, 1); u = yr.reshape(B, 32, H * W).permute(0, 2, 1)
+    xn = R.layer_norm(t, sdg[BLK + "norm1.weight"], sdg[BLK + "norm1.bias"]).contiguous()
+    yn = R.layer_norm(u, sdg[BLK + "norm1.weight"], sdg[BLK + "norm1.bias"]).contiguous()
+    o = (t + R.window_attention(ctx, BLK + "attn.", xn, yn, H, W)).permute(0, 2, 1).reshape(B, 32, H, W)
+    o.backward(dout)
+    blk = _block_product(P, dtype)
+    xc, yc = nchw_from(x.to(dtype)).requires_grad_(True), nchw_from(y.to(dtype)).requires_grad_(True)
+    oc = ops.WindowAttention.apply(xc, yc, 1e-6, True, blk.norm1.weight, blk.norm1.bias, *blk.attn.gate_params(),
+                                   *blk.attn.attn.proj_params())
+    oc.backward(nchw_from(dout.to(dtype)))
+    errs = dict(out=rel(oc.float(), o), dx=rel(xc.grad.float(), xr.grad), dy=rel(yc.grad.float(), yr.grad))
+    names = {"norm1.weight": blk.norm1.weight, "norm1.bias": blk.norm1.bias,
+             "attn.atrous_block1.conv1.weight": blk.attn.atrous_block1.conv1.weight,
+             "attn.atrous_block2.conv1.weight": blk.attn.atrous_block2.conv1.weight,
+             "attn.weight_levels.weight": blk.attn.weight_levels.weight, "attn.weight_levels.bias": blk.attn.weight_levels.bias}
+    for n in ("q", "k", "v", "out"):
+        names["attn.attn.%s_proj.weight" % n] = getattr(blk.attn.attn, n + "_proj").weight
+        names["attn.attn.%s_proj.bias" % n] = getattr(blk.attn.attn, n + "_proj").bias
+    gmax = max(sdg[BLK + k].grad.abs().max().item() for k in names)
+    for k, p in names.items():
+        errs["grad." + k] = (p.grad.detach().double().cpu() - sdg[BLK + k].grad.double()).abs().max().item() / gmax
+    report["winattn_%s_%s" % (str(dtype)[6:], "x".join(map(str, shape)))] = errs
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, bad
+
+
+def test_interlaced_pool_attention_module_interface(P, report):
+    """InterlacedPoolAttention2.forward(x,y,H,W) on (B,N,C) tokens, as the reference calls it (MTFM.py:107)"""
+    B, H, W = 2, 15, 17
+    torch.manual_seed(4)
+    sd = {k: v for k, v in R.synth_state_dict(2333).items() if k.startswith(BLK)}
+    x, y = torch.randn(B, H * W, 32), torch.randn(B, H * W, 32)
+    ref = R.window_attention(R.Ctx(sd, True), BLK + "attn.", x, y, H, W)
+    blk = _block_product(P, torch.float32)
+    out = blk.attn(x.to(DEV), y.to(DEV), H, W)
+    report["ipa2_module"] = dict(out=rel(out, ref))
+    assert rel(out, ref) < TOL_F32
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_neck_gather(P, report, dtype):
+    from representationlearning_b200 import ops
+    torch.manual_seed(5)
+    B = 2
+    feats = [torch.randn(B, c, s, s).to(dtype).float() for c, s in ((32, 24), (64, 12), (128, 6), (256, 3))]
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    ups = [fr[0]] + [torch.nn.functional.interpolate(f, size=(24, 24), mode="bilinear", align_corners=True) for f in fr[1:]]
+    cat = torch.cat(ups, 1)
+    dcat = torch.randn_like(cat).to(dtype).float()
+    cat.backward(dcat)
+    fc = [nchw_from(f.to(dtype)).requires_grad_(True) for f in feats]
+    oc = ops.NeckGather.apply(*fc)
+    oc.backward(nchw_from(dcat.to(dtype)))
+    errs = dict(out=rel(oc.float(), cat))
+    for i in range(4):
+        errs["d%d" % i] = rel(fc[i].grad.float(), fr[i].grad)
+    report["neck_gather_%s" % str(dtype)[6:]] = errs
+    assert max(errs.values()) < (TOL_F32 if dtype == torch.float32 else TOL_BF16), errs
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_head_conv(P, report, dtype):
+    from representationlearning_b200 import ops
+    torch.manual_seed(6)
+    x = torch.randn(2, 480, 9, 13).to(dtype).float()
+    w, b = torch.randn(7, 480, 1, 1) * 0.05, torch.randn(7)
+    dl = torch.randn(2, 9, 13, 8); dl[..., 7] = 0
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    lr = torch.nn.functional.conv2d(xr, wr, br)
+    lr.backward(dl[..., :7].permute(0, 3, 1, 2))
+    xc = nchw_from(x.to(dtype)).requires_grad_(True)
+    wc, bc = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    lc = ops.HeadConv.apply(xc, wc, bc)
+    lc.backward(dl.to(DEV))
+    errs = dict(logits=rel(lc[..., :7].permute(0, 3, 1, 2), lr), pad=float(lc[..., 7].abs().max()),
+                dx=rel(xc.grad.float(), xr.grad), dw=rel(wc.grad, wr.grad), db=rel(bc.grad, br.grad))
+    report["head_conv_%s" % str(dtype)[6:]] = errs
+    assert max(errs.values()) < (TOL_F32 if dtype == torch.float32 else TOL_BF16), errs
+
+
+@pytest.mark.parametrize("name", ["headloss_rand_B2_h16_seed31", "headloss_edge_B4_h8_seed32"])
+def test_head_upsample_loss_vs_reference_golden(P, report, name):
+    """UpsamplingBilinear2d(x4) + SegmentationLossaux from low-res logits: loss and d/dlogits vs the reference's own
+    output, incl. the all-background / all-ignored / single-class images"""
+    from representationlearning_b200 import ops
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    case, B, h, seed = re.match(r"headloss_(\w+)_B(\d+)_h(\d+)_seed(\d+)", name).groups()
+    B, h, seed = int(B), int(h), int(seed)
+    gen = torch.Generator().manual_seed(seed)
+    lr = 2.0 * torch.randn(B, 7, h, h, generator=gen, dtype=torch.float64)
+    labels = torch.randint(-1, 7, (B, 4 * h, 4 * h), generator=gen, dtype=torch.int64)
+    aux = torch.randn(B, 7, generator=gen, dtype=torch.float64)
+    if case == "edge":
+        labels[0] = 0; labels[1] = -1; labels[2] = 3
+    lr8 = torch.zeros(B, h, h, 8)
+    lr8[..., :7] = lr.float().permute(0, 2, 3, 1)
+    lrc = lr8.to(DEV).requires_grad_(True)
+    loss = ops.SegLoss.apply(lrc, labels.to(DEV), aux.float().to(DEV), 4, -1)
+    (loss * 1.0).backward()
+    errs = dict(loss=abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])),
+                dlogits=rel(lrc.grad[..., :7].permute(0, 3, 1, 2), g["dlogits_lr"]))
+    report[name] = errs
+    assert max(errs.values()) < TOL_F32, errs
+
+
+def test_head_probs_and_argmax(P, report):
+    from representationlearning_b200 import ops
+    torch.manual_seed(7)
+    lr = torch.randn(2, 7, 16, 20) * 3
+    ref = torch.softmax(torch.nn.functional.interpolate(lr, scale_factor=4, mode="bilinear", align_corners=True), 1)
+    lr8 = torch.zeros(2, 16, 20, 8); lr8[..., :7] = lr.permute(0, 2, 3, 1)
+    probs, am = ops.head_probs(lr8.to(DEV), 4, want_argmax=True)
+    errs = dict(probs=rel(probs, ref), sum=float((probs.sum(1) - 1).abs().max()),
+                argmax_mismatch=float((am.cpu().long() != ref.argmax(1)).float().mean()))
+    report["head_probs"] = errs
+    assert errs["probs"] < TOL_F32 and errs["sum"] < 1e-5 and errs["argmax_mismatch"] == 0.0, errs
+
+
+def test_headaux(P, report):
+    from representationlearning_b200 import ops
+    torch.manual_seed(8)
+    f0 = torch.randn(3, 32, 20, 24); w = torch.randn(7, 32); b = torch.randn(7)
+    ref = f0.mean((2, 3)) @ w.t() + b
+    out = ops.headaux(nchw_from(f0), w.to(DEV), b.to(DEV))
+    report["headaux"] = dict(out=rel(out, ref))
+    assert rel(out, ref) < TOL_F32
+
+
+# ------------------------------------------------------------------------------------------------
+def _model(P, dtype):
+    m = P.build_rssformer(compute_dtype=dtype)
+    m.load_state_dict(R.synth_state_dict(2333))
+    return m
+
+
+def test_model_S64_vs_reference_golden_fp32(P, report):
+    g = np.load(os.path.join(GOLDEN, "model_S64_B2.npz"))
+    gn = json.load(open(os.path.join(GOLDEN, "model_S64_B2_gradnorms.json")))
+    img, lbl = R.synth_batch(2, 64)
+    m = _model(P, torch.float32)
+    m.eval()
+    with torch.no_grad():
+        probs = m(img.to(DEV))
+    errs = dict(probs=rel(probs, g["probs"]),
+                argmax_mismatch=float((probs.argmax(1).cpu() != torch.as_tensor(g["probs"]).argmax(1)).float().mean()))
+    m.train()
+    loss = sum(m(img.to(DEV), {"cls": lbl.to(DEV)}).values())
+    loss.backward()
+    errs["loss"] = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
+    named = dict(m.named_parameters())
+    for k in g.files:
+        if k.startswith("grad."):
+            errs[k] = rel(named[k[5:]].grad, g[k])
+        if k.startswith("stat."):
+            errs[k] = rel(m.state_dict()[k[5:]], g[k])
+    worst = 0.0
+    for k, n in gn.items():
+        if n > 1e-12:
+            worst = max(worst, abs(named[k].grad.norm().item() - n) / max(n, 1e-3 * max(gn.values())))
+    errs["gradnorm_worst"] = worst
+    assert named["headaux.0.weight"].grad is None
+    report["model_S64_fp32"] = errs
+    bad = {k: v for k, v in errs.items() if not v < (5 * TOL_F32 if k.startswith("grad") else TOL_F32) and k != "argmax_mismatch"}
+    assert not bad and errs["argmax_mismatch"] < 1e-3, (bad, errs["argmax_mismatch"])
+
+
+def test_model_S64_bf16_agreement(P, report):
+    g = np.load(os.path.join(GOLDEN, "model_S64_B2.npz"))
+    img, lbl = R.synth_batch(2, 64)
+    m = _model(P, torch.bfloat16)
+    m.eval()
+    with torch.no_grad():
+        probs = m(img.to(DEV))
+    ref = torch.as_tensor(g["probs"])
+    m.train()
+    loss = sum(m(img.to(DEV), {"cls": lbl.to(DEV)}).values())
+    loss.backward()
+    errs = dict(probs=rel(probs, ref), argmax_agree=float((probs.argmax(1).cpu() == ref.argmax(1)).float().mean()),
+                loss=abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])))
+    report["model_S64_bf16"] = errs
+    assert errs["probs"] < TOL_BF16 and errs["argmax_agree"] > 0.97 and errs["loss"] < TOL_BF16, errs
+
+
+def test_model_S512_cfg1_argmax_vs_reference_golden(P, report):
+    """BASELINE config #1 tile (B=1, 512x512): per-pixel class argmax vs the reference's fp32 forward."""
+    g = np.load(os.path.join(GOLDEN, "model_S512_B1.npz"))
+    img, lbl = R.synth_batch(1, 512)
+    m = _model(P, torch.float32)
+    m.eval()
+    with torch.no_grad():
+        probs = m(img.to(DEV))
+    am = probs.argmax(1).cpu().numpy().astype(np.uint8)
+    gap = g["top2gap"].astype(np.float32)
+    decided = gap > 2e-3                       # pixels whose oracle top-2 gap exceeds the fp tolerance
+    errs = dict(probs_strided=rel(probs[:, :, ::8, ::8], g["probs_strided"]),
+                argmax_mismatch_all=float((am != g["argmax"]).mean()),
+                argmax_mismatch_decided=float((am != g["argmax"])[decided].mean()), tie_fraction=float(1 - decided.mean()))
+    m.train()
+    loss = sum(m(img.to(DEV), {"cls": lbl.to(DEV)}).values())
+    errs["loss"] = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
+    report["model_S512_fp32"] = errs
+    assert errs["probs_strided"] < TOL_F32 and errs["argmax_mismatch_decided"] == 0.0 and errs["loss"] < TOL_F32, errs
+
+
+def test_flat_sgd_vs_oracle(P, report):
+    torch.manual_seed(9)
+    lin = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 5)).to(DEV)
+    ref_p = [p.detach().cpu().clone() for p in lin.parameters()]
+    mom = [None] * len(ref_p)
+    opt = P.FlatSGD(lin, bf16_shadow=True)
+    worst = 0.0
+    for it in range(3):
+        gs = [torch.randn_like(p) * 40 for p in ref_p]
+        for p, g_ in zip(lin.parameters(), gs):
+            p.grad.copy_(g_.to(DEV))
+        lr = opt.lr()
+        opt.step(1.0)
+        R.sgd_step(ref_p, gs, mom, lr)
+        for p, r in zip(lin.parameters(), ref_p):
+            worst = max(worst, rel(p, r))
+        assert float(opt.flat_g.abs().max()) == 0.0           # zero_grad folded into the step
+    report["flat_sgd"] = dict(worst=worst)
+    assert worst < 1e-5
+    assert rel(opt.shadow.float(), opt.flat_p) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# properties at BASELINE.json full size (cfg2: B=16, 512x512 -> branch-0 tokens (16,128,128,32))
+# ------------------------------------------------------------------------------------------------
+def test_full_size_block_properties(P, report):
+    from representationlearning_b200 import ops
+    torch.manual_seed(10)
+    B, H, W = 16, 128, 128
+    blk = _block_product(P, torch.bfloat16)
+    x = torch.randn(B, 32, H, W, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = torch.randn(B, 32, H, W, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    args = (1e-6, True, blk.norm1.weight, blk.norm1.bias, *blk.attn.gate_params(), *blk.attn.attn.proj_params())
+    with torch.no_grad():
+        full = ops.WindowAttention.apply(x, y, *args)
+        one = ops.WindowAttention.apply(x[5:6].contiguous(memory_format=torch.channels_last),
+                                        y[5:6].contiguous(memory_format=torch.channels_last), *args)
+    # images are independent (windows never cross images): bit-exact batch independence
+    assert torch.equal(full[5:6], one)
+    assert torch.isfinite(full.float()).all()
+    # backward is linear in the incoming gradient
+    xg = x.clone().requires_grad_(True); yg = y.clone().requires_grad_(True)
+    out = ops.WindowAttention.apply(xg, yg, *args)
+    d = torch.randn_like(out)
+    g1 = torch.autograd.grad(out, (xg, yg), d, retain_graph=True)
+    g2 = torch.autograd.grad(out, (xg, yg), 2 * d)
+    lin = max(rel(g2[0].float(), 2 * g1[0].float()), rel(g2[1].float(), 2 * g1[1].float()))
+    report["full_size_block"] = dict(bwd_linearity=lin)
+    assert lin < 2e-2
