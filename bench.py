@@ -104,6 +104,8 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--cpu-baseline-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--profile", action="store_true", help="profiling run (under ncu): skip the e2e and cpu legs; numbers are not bench values")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,47 +166,73 @@ def main():
 
     last = {}
 
-    def step_resident():
+    def step_eager():
         last["loss"] = P.train_step(model, opt, img_d, lbl_d)
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    # ---- device-resident throughput, with live timing of the dominant hand-written region --------------------
+    # ---- eager warm-up with live CUDA-event timing of the hand-written regions (same shapes, same process) ----
+    for _ in range(2):
+        step_eager()
     dom = "rss_attn_bwd"
-    ops.TIMED_OPS.add(dom); ops.TIMED_OPS.add("rss_attn_fwd"); ops.TIMED.clear()
+    ops.TIMED_OPS.update(["rss_attn_bwd", "rss_attn_fwd", "rss_conv_igemm"]); ops.TIMED.clear()
     c0 = ops.COUNTERS["launches"]
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ms = timed(step_resident, args.steps)
-    clocks = sampler.finish() if sampler else None
-    launches = ops.COUNTERS["launches"] - c0
+    ms_eager = timed(step_eager, 2) / 2
+    launches_per_step = (ops.COUNTERS["launches"] - c0) // 2
     ops.TIMED_OPS.clear()
     torch.cuda.synchronize()
     kt = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in ops.TIMED.items() if v}
-    value = world * B * args.steps / (ms / 1e3)
+    kn = {k: len(v) for k, v in ops.TIMED.items() if v}
 
-    # ---- end to end: pinned host -> device every step (double-buffered on a copy stream), loss read back -----
+    # ---- the timed region: the whole step captured once as a CUDA graph, replayed K times -------------------
+    if args.no_graph:
+        run_step = step_eager
+    else:
+        graphed = P.GraphedTrainStep(model, opt, img_d, lbl_d, warmup=max(1, args.warmup - 2))
+
+        def run_step():
+            last["loss"] = graphed()
+    for _ in range(max(args.warmup, 3)):
+        run_step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = timed(run_step, args.steps)
+    clocks = sampler.finish() if sampler else None
+    launches = launches_per_step * args.steps
+    value = world * B * args.steps / (ms / 1e3)
+    if args.profile:
+        print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "region_ms": kt, "gpu_launches": launches}))
+        return 0
+
+    # ---- end to end: pinned host -> device every step (staged on a copy stream, overlapped), loss read back ---
     copy_stream = torch.cuda.Stream(dev)
     bufs = [(torch.empty_like(img_d), torch.empty_like(lbl_d)) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
     state = {"i": 0, "sink": 0.0}
 
     def stage(slot):
         with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
             bufs[slot][0].copy_(img_h, non_blocking=True)
             bufs[slot][1].copy_(lbl_h, non_blocking=True)
             ready[slot].record(copy_stream)
 
     def step_e2e():
         slot = state["i"] & 1
-        torch.cuda.current_stream().wait_event(ready[slot])
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[slot])
         stage(slot ^ 1)                                   # prefetch the next step's batch while this one computes
-        loss = P.train_step(model, opt, bufs[slot][0], bufs[slot][1])
+        if args.no_graph:
+            loss = P.train_step(model, opt, bufs[slot][0], bufs[slot][1])
+        else:
+            graphed.load(bufs[slot][0], bufs[slot][1])    # device-to-device into the graph's static inputs
+            loss = graphed()
+        consumed[slot].record(cur)
         state["sink"] += float(loss.item())              # device -> host read of the step's result
-        copy_stream.wait_stream(torch.cuda.current_stream())
         state["i"] += 1
 
+    for e in consumed:
+        e.record(torch.cuda.current_stream())
     stage(0)
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -222,7 +250,8 @@ def main():
         ach = alg[dom] / (kt[dom] / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                 "traffic": None, "peak_source": pk["src"] + " (burst copy)", "ms_per_launch": kt[dom],
-                "launches_timed": len(ops.TIMED[dom]), "algorithmic_bytes_per_launch": alg[dom]}
+                "launches_timed": kn[dom], "algorithmic_bytes_per_launch": alg[dom],
+                "timing": "CUDA events around the C-ABI call on the launching stream, eager pass of the same step in this process"}
     step_tf = per_gpu * FLOP_PER_IMG_TRAIN / 1e12
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -230,6 +259,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload, "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "per-step activations (GBs) far exceed the 126 MB L2; no explicit flush",
+                   "launch": "eager" if args.no_graph else "whole step replayed as one CUDA graph", "ms_per_step_eager": ms_eager,
                    "weights": "synthetic, seed 2333 (oracle.synth_state_dict)"},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,

@@ -45,7 +45,7 @@ int rss_last_cuda_error(void);
 int rss_check_device(void);
 
 /* ---- LayerNorm over channels of (rows, C) tokens: base_hrnet/modules/MTFM.py:64,78-79,107,109 ---- */
-int rss_layernorm_fwd(const void* x, void* y, float* mean /*[rows] or NULL*/, float* rstd /*[rows]*/,
+int rss_layernorm_fwd(const void* x, void* y /*NULL: statistics only*/, float* mean /*[rows] or NULL*/, float* rstd /*[rows]*/,
                       const float* gamma, const float* beta, float eps, int64_t rows, int C, int dtype, cudaStream_t stream);
 /* dx = LN'(dy) (+ dx_add if not NULL); dgamma_acc/dbeta_acc accumulate */
 int rss_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
@@ -67,16 +67,17 @@ typedef struct {
     float *ln_w, *ln_b, *sa1_w, *sa2_w, *lvl_w, *lvl_b, *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b;
 } rss_attn_grads;
 
-/* out = x + Attn(LN1(x), LN1(y)).  Saved for backward (caller-owned): xn, yn (B,HW,C) dtype;
- * ln_stats [4][B*HW] f32; pooled [B][4][HW] f32; amax [B][2][HW] u8; smap, gmap [B][2][HW] f32. */
+/* out = x + Attn(LN1(x), LN1(y)).  Saved for backward (caller-owned): ln_stats [4][B*HW] f32 (mean/rstd of x, of y);
+ * pooled [B][4][HW] f32; amax [B][2][HW] u8; smap, gmap [B][2][HW] f32.  The normalised tokens are never materialised:
+ * every consumer recomputes (x-mean)*rstd*gamma+beta in fp32 from x and ln_stats. */
 #define RSS_ATTN_NO_RESIDUAL 1   /* flags bit 0: out = Attn(...) without "+ x" (InterlacedPoolAttention2.forward alone) */
-/* p->ln_w == NULL skips norm1 (x, y are then the already-normalised tokens; xn, yn, ln_stats unused). */
+/* p->ln_w == NULL skips norm1 (x, y are then the already-normalised tokens; ln_stats unused). */
 int rss_attn_fwd(const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int dtype, int flags,
-                 void* xn, void* yn, float* ln_stats, float* pooled, uint8_t* amax, float* smap, float* gmap,
+                 float* ln_stats, float* pooled, uint8_t* amax, float* smap, float* gmap,
                  void* out, cudaStream_t stream);
 size_t rss_attn_bwd_workspace_bytes(int B, int H, int W, int dtype);
 int rss_attn_bwd(const void* dout, const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int dtype, int flags,
-                 const void* xn, const void* yn, const float* ln_stats, const float* pooled, const uint8_t* amax,
+                 const float* ln_stats, const float* pooled, const uint8_t* amax,
                  const float* smap, const float* gmap, void* workspace, size_t workspace_bytes,
                  void* dx, void* dy, const rss_attn_grads* grads_acc, cudaStream_t stream);
 
@@ -101,7 +102,22 @@ int rss_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float*
 int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
                      const float* mean, const float* invstd, const float* sums, float inv_count,
                      void* dx, void* dresidual /*may be NULL: receives dz*/, int64_t rows, int C, int act, int dtype,
-                     cudaStream_t stream);
+                     const float* local_sums /*this rank's sums (== sums without SyncBN)*/,
+                     float* dgamma_acc /*may be NULL*/, float* dbeta_acc, cudaStream_t stream);
+
+/* ---- tcgen05/TMA implicit-GEMM convolution (stride 1, "same" padding, NHWC bf16, fp32 TMEM accumulation):
+ *      the FFN's dw(1x1)+dw6(3x3,d6)+dw12(3x3,d12) summed convs as ONE 17-tap GEMM (ffn_block.py:226-228,250-257),
+ *      fc1/fc2 (ffn_block.py:219,232), the neck 1x1 (hrnet_aux.py:46), HRNet stride-1 3x3/1x1 convs
+ *      (_hrnet_rssformer.py:209-213,253-259) and their data gradients (transposed pack, negated taps). ---- */
+int rss_conv_igemm_supported(int B, int H, int W, int Cin, int Cout);
+size_t rss_conv_packed_bytes(int n_srcs, const int* ksizes, int Cout, int Cin);
+/* packs 1..3 parallel convs (fp32 (Cout,Cin,k,k), k in {1,3}, summed outputs) into bf16 [tap][N][K]; coinciding taps are
+ * merged; bias_sum[Cout] = sum of the biases (forward pack only); taps_*_out sized 32.  transpose=1: data-gradient operand. */
+int rss_conv_pack_weights(const float* const* weights, const float* const* biases, const int* ksizes, const int* dilations,
+                          int n_srcs, int Cout, int Cin, int transpose, void* packed, float* bias_sum,
+                          int* n_taps_out, int* taps_dy_out, int* taps_dx_out, cudaStream_t stream);
+int rss_conv_igemm(const void* x, const void* w_packed, const float* bias /*may be NULL*/, void* y, int B, int H, int W,
+                   int Cin, int Cout, int n_taps, const int* taps_dy, const int* taps_dx, cudaStream_t stream);
 
 /* ---- neck: hrnet_aux.py:51-68 (SimpleFusion8: 3x bilinear align_corners=True + concat), NHWC ---- */
 int rss_neck_gather_fwd(const void* f0, const void* f1, const void* f2, const void* f3, void* out_cat,
@@ -131,8 +147,10 @@ int rss_seg_loss_bwd(const float* gdir, const float* out4, const float* upstream
 
 /* ---- optimiser step: configs/base/loveda.py:68-99 (clip_grad_norm_(35,L2) + SGD(m=.9, wd=1e-4)) on ONE flat buffer ---- */
 int rss_grad_sumsq(const float* grads, int64_t n, float grad_scale, double* sumsq, cudaStream_t stream);
+/* momentum_buf must start zeroed (then m = g on the first step, as torch.optim.SGD); lr is a DEVICE scalar (poly schedule
+ * written by the host between steps, so a captured CUDA graph of the step stays valid). */
 int rss_sgd_step(float* params, float* grads, float* momentum_buf, int64_t n, const double* sumsq, float grad_scale,
-                 float max_norm, float lr, float momentum, float weight_decay, int first_step, int zero_grad,
+                 float max_norm, const float* lr, float momentum, float weight_decay, int zero_grad,
                  void* bf16_shadow /*may be NULL*/, cudaStream_t stream);
 
 #ifdef __cplusplus

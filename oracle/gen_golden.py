@@ -163,6 +163,19 @@ def main():
     named = dict(model.named_parameters())
     for k in keep:
         arrs["grad." + k] = _np(named[k].grad)
+    # rounding envelope of the reference itself: its fp32 run vs its fp64 run on the same inputs
+    m32 = build_reference_model()
+    m32.load_state_dict(R.synth_state_dict(2333, torch.float32))
+    m32.train()
+    sum(m32(img.float(), {"cls": lbl}).values()).backward()
+    n32 = dict(m32.named_parameters())
+    for k in keep:
+        arrs["fp32dev." + k] = np.float64(((n32[k].grad.double() - named[k].grad).abs().max() / named[k].grad.abs().max()).item())
+    gmx = max(grad_norms.values())
+    arrs["fp32dev_gradnorm_worst"] = np.float64(max(abs(n32[k].grad.norm().item() - n) / max(n, 1e-3 * gmx)
+                                                    for k, n in grad_norms.items() if n > 1e-12))
+    report["model_S64_fp32_reference_envelope"] = {k: float(arrs["fp32dev." + k]) for k in keep}
+    report["model_S64_fp32_reference_envelope"]["gradnorm_worst"] = float(arrs["fp32dev_gradnorm_worst"])
     arrs["stat.backbone.hrnet.bn1.running_mean"] = _np(new_sd["backbone.hrnet.bn1.running_mean"])
     arrs["stat." + BLK + "mlp.norm2.running_var"] = _np(new_sd[BLK + "mlp.norm2.running_var"])
     np.savez_compressed(os.path.join(OUT, "model_S64_B2.npz"), **arrs)

@@ -15,8 +15,8 @@ torch.backends.cuda.matmul.allow_tf32 = False
 from .model import HRNetFusion, MODEL, RSSFORMER_CONFIG, build_rssformer  # noqa: F401
 from .modules import (FusedBNAct, GeneralTransformerBlock, InterlacedPoolAttention2, Mhca, MlpDWBN,  # noqa: F401
                       SimpleFusion8, SpatialAttention)
-from .trainer import FlatSGD, poly_lr, train_step  # noqa: F401
+from .trainer import FlatSGD, GraphedTrainStep, poly_lr, train_step  # noqa: F401
 
 __all__ = ["HRNetFusion", "MODEL", "RSSFORMER_CONFIG", "build_rssformer", "GeneralTransformerBlock",
            "InterlacedPoolAttention2", "Mhca", "MlpDWBN", "SimpleFusion8", "SpatialAttention", "FusedBNAct",
-           "FlatSGD", "poly_lr", "train_step"]
+           "FlatSGD", "GraphedTrainStep", "poly_lr", "train_step"]

@@ -39,9 +39,9 @@ SIGNATURES = {
     "rss_check_device": (c_int, []),
     "rss_layernorm_fwd": (c_int, [P, P, P, P, P, P, c_float, c_int64, c_int, c_int, P]),
     "rss_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, P]),
-    "rss_attn_fwd": (c_int, [P, P, POINTER(AttnParams), c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
+    "rss_attn_fwd": (c_int, [P, P, POINTER(AttnParams), c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "rss_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "rss_attn_bwd": (c_int, [P, P, P, POINTER(AttnParams), c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_size_t,
+    "rss_attn_bwd": (c_int, [P, P, P, POINTER(AttnParams), c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_size_t,
                              P, P, POINTER(AttnGrads), P]),
     "rss_bn_stats_nparts": (c_int, [c_int64, c_int]),
     "rss_bn_stats": (c_int, [P, P, P, c_int64, c_int, c_int, P]),
@@ -50,7 +50,12 @@ SIGNATURES = {
     "rss_bn_eval_affine": (c_int, [P, P, P, P, c_float, c_int, P, P, P, P, P]),
     "rss_bn_act_fwd": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
     "rss_bn_bwd_reduce": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
-    "rss_bn_bwd_apply": (c_int, [P, P, P, P, P, P, P, P, c_float, P, P, c_int64, c_int, c_int, c_int, P]),
+    "rss_bn_bwd_apply": (c_int, [P, P, P, P, P, P, P, P, c_float, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
+    "rss_conv_igemm_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "rss_conv_packed_bytes": (c_size_t, [c_int, POINTER(c_int), c_int, c_int]),
+    "rss_conv_pack_weights": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int,
+                                      P, P, POINTER(c_int), POINTER(c_int), POINTER(c_int), P]),
+    "rss_conv_igemm": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P]),
     "rss_neck_gather_fwd": (c_int, [P, P, P, P, P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, P]),
     "rss_neck_gather_bwd": (c_int, [P, P, P, P, P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, P]),
     "rss_head_fwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, P]),
@@ -61,7 +66,7 @@ SIGNATURES = {
     "rss_seg_loss_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "rss_seg_loss_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     "rss_grad_sumsq": (c_int, [P, c_int64, c_float, P, P]),
-    "rss_sgd_step": (c_int, [P, P, P, c_int64, P, c_float, c_float, c_float, c_float, c_float, c_int, c_int, P, P]),
+    "rss_sgd_step": (c_int, [P, P, P, c_int64, P, c_float, c_float, P, c_float, c_float, c_int, P, P]),
 }
 
 _lib = None

@@ -7,9 +7,11 @@ Two engines, chosen per layer shape (DESIGN.md lists which layer uses which):
 Both take the low-precision copy of the weight from the optimiser's bf16 shadow buffer when one is
 registered (no per-call cast kernels), and return fp32 weight gradients to the master parameter.
 """
+import ctypes
+
 import torch
 
-from . import ops
+from . import _lib, ops
 
 CL = torch.channels_last
 _SHADOW = {}          # id(param) -> bf16 view kept fresh by the fused optimiser step (trainer.py)
@@ -35,13 +37,14 @@ def _lowp(w, dtype):
 
 class _ConvLib(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, dilation):
+    def forward(ctx, x, weight, bias, stride, padding, dilation, bias_grad):
         x = ops.nhwc(x)
         w = _lowp(weight, x.dtype).contiguous(memory_format=CL)
         b = _lowp(bias, x.dtype)
         y = torch.ops.aten.convolution(x, w, b, [stride, stride], [padding, padding], [dilation, dilation], False, [0, 0], 1)
         ctx.save_for_backward(x, w)
-        ctx.cfg = (stride, padding, dilation, bias is not None, weight.dtype)
+        ctx.cfg = (stride, padding, dilation, bias is not None and bias_grad, weight.dtype)
+        ctx.refs = (weight, bias)
         return y
 
     @staticmethod
@@ -54,12 +57,133 @@ class _ConvLib(torch.autograd.Function):
         mask = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]]
         dx, dw, db = torch.ops.aten.convolution_backward(dy, x, w, [w.shape[0]] if has_bias else None, [stride, stride],
                                                          [padding, padding], [dilation, dilation], False, [0, 0], 1, mask)
-        if dw is not None:
+        sw = ops.grad_sink(ctx.refs[0])
+        if dw is not None and sw is not None:        # accumulate straight into the flat fp32 grad buffer (cast fused into the add)
+            sw.add_(dw)
+            dw = None
+        elif dw is not None:
             dw = dw.to(wdtype)
         if db is not None:
-            db = db.to(wdtype)
-        return dx, dw, db, None, None, None
+            sb = ops.grad_sink(ctx.refs[1])
+            if sb is not None:
+                sb.add_(db)
+                db = None
+            else:
+                db = db.to(wdtype)
+        return dx, dw, db, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1):
-    return _ConvLib.apply(x, weight, bias, stride, padding, dilation)
+def _igemm_ok(x, Cout):
+    if not ENGINE["igemm"] or x.dtype != torch.bfloat16 or not x.is_cuda:
+        return False
+    B, Cin, H, W = x.shape
+    return bool(_lib.load().rss_conv_igemm_supported(B, H, W, Cin, Cout))
+
+
+def _pack(weights, biases, ksizes, dils, Cout, Cin, transpose, dev):
+    """-> (packed bf16 buffer, bias_sum or None, n_taps, dy[], dx[]) through rss_conv_pack_weights"""
+    lib = _lib.load()
+    n = len(weights)
+    ws = [ops._f32(w) for w in weights]
+    bs = [None if b is None else ops._f32(b) for b in biases]
+    wptr = (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws])
+    has_b = any(b is not None for b in bs) and not transpose
+    bptr = (ctypes.c_void_p * n)(*[None if b is None else b.data_ptr() for b in bs]) if has_b else None
+    ks = (ctypes.c_int * n)(*ksizes)
+    ds = (ctypes.c_int * n)(*dils)
+    packed = torch.empty(lib.rss_conv_packed_bytes(n, ks, Cout, Cin) // 2, device=dev, dtype=torch.bfloat16)
+    bias_sum = torch.empty(Cout, device=dev, dtype=torch.float32) if has_b else None
+    nt = ctypes.c_int(0)
+    dy = (ctypes.c_int * 32)()
+    dx = (ctypes.c_int * 32)()
+    ops.check(lib.rss_conv_pack_weights(wptr, bptr, ks, ds, n, Cout, Cin, int(transpose), packed.data_ptr(),
+                                        None if bias_sum is None else bias_sum.data_ptr(), ctypes.byref(nt), dy, dx, ops._st()),
+              "rss_conv_pack_weights")
+    return packed, bias_sum, nt.value, dy, dx, (ws, bs)
+
+
+class _ConvIgemm(torch.autograd.Function):
+    """sum_s conv2d(x, w_s, b_s, stride 1, padding = dil_s*(k_s//2), dilation dil_s) as ONE tcgen05 implicit GEMM.
+    Data gradient: same kernel on the transposed pack.  Weight gradient: library kernel per source (for now)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, *wb):
+        ksizes, dils, bias_grad = cfg
+        n = len(ksizes)
+        weights, biases = wb[:n], wb[n:]
+        lib = _lib.load()
+        x = ops.nhwc(x)
+        B, Cin, H, W = x.shape
+        Cout = weights[0].shape[0]
+        packed, bias_sum, nt, dy, dx, keep = _pack(weights, biases, ksizes, dils, Cout, Cin, False, x.device)
+        y = torch.empty((B, Cout, H, W), device=x.device, dtype=x.dtype, memory_format=CL)
+        with ops.timed("rss_conv_igemm"):
+            ops.check(lib.rss_conv_igemm(x.data_ptr(), packed.data_ptr(), None if bias_sum is None else bias_sum.data_ptr(),
+                                         y.data_ptr(), B, H, W, Cin, Cout, nt, dy, dx, ops._st()), "rss_conv_igemm")
+        ctx.save_for_backward(x)
+        ctx.cfg, ctx.refs, ctx.n = cfg, wb, n
+        return y
+
+    @staticmethod
+    def backward(ctx, dy_):
+        (x,) = ctx.saved_tensors
+        ksizes, dils, bias_grad = ctx.cfg
+        n = ctx.n
+        weights, biases = ctx.refs[:n], ctx.refs[n:]
+        lib = _lib.load()
+        dy_ = ops.nhwc(dy_)
+        if dy_.dtype != x.dtype:
+            dy_ = dy_.to(x.dtype)
+        B, Cin, H, W = x.shape
+        Cout = weights[0].shape[0]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            packed, _, nt, tdy, tdx, keep = _pack(weights, [None] * n, ksizes, dils, Cout, Cin, True, x.device)
+            dx = torch.empty_like(x, memory_format=CL)
+            with ops.timed("rss_conv_igemm"):
+                ops.check(lib.rss_conv_igemm(dy_.data_ptr(), packed.data_ptr(), None, dx.data_ptr(), B, H, W, Cout, Cin, nt, tdy, tdx,
+                                             ops._st()), "rss_conv_igemm")
+        gw, gb = [], []
+        for s in range(n):
+            k, d = ksizes[s], dils[s]
+            w_lp = _lowp(weights[s], x.dtype).contiguous(memory_format=CL)
+            want_b = biases[s] is not None and bias_grad
+            _, dw, db = torch.ops.aten.convolution_backward(dy_, x, w_lp, [Cout] if want_b else None, [1, 1], [d * (k // 2)] * 2, [d, d],
+                                                            False, [0, 0], 1, [False, True, want_b])
+            sw = ops.grad_sink(weights[s])
+            if sw is not None:
+                sw.add_(dw); dw = None
+            else:
+                dw = dw.to(weights[s].dtype)
+            if db is not None:
+                sb = ops.grad_sink(biases[s])
+                if sb is not None:
+                    sb.add_(db); db = None
+                else:
+                    db = db.to(biases[s].dtype)
+            gw.append(dw); gb.append(db)
+        return (dx, None) + tuple(gw) + tuple(gb)
+
+
+def conv_sum(x, convs, bias_grad=True):
+    """sum of parallel stride-1 'same' convolutions of the same input (the FFN's dw + dw6 + dw12): one igemm launch when the
+    geometry is supported, else the library convs added up.  convs: list of (weight, bias, ksize, dilation)."""
+    Cout = convs[0][0].shape[0]
+    if _igemm_ok(x, Cout):
+        cfg = (tuple(c[2] for c in convs), tuple(c[3] for c in convs), bias_grad)
+        return _ConvIgemm.apply(x, cfg, *[c[0] for c in convs], *[c[1] for c in convs])
+    out = None
+    for w, b, k, d in convs:
+        t = _ConvLib.apply(x, w, b, 1, d * (k // 2), d, bias_grad)
+        out = t if out is None else out + t
+    return out
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, bias_grad=True):
+    """bias_grad=False: the caller guarantees d loss/d bias == 0 (conv feeding a training-mode BatchNorm: the batch-mean
+    subtraction cancels any per-channel shift; the reference computes ~1e-18 round-off there), so the (B*H*W)-long
+    reduction is skipped."""
+    k = weight.shape[2]
+    if stride == 1 and padding == dilation * (k // 2) and k in (1, 3) and _igemm_ok(x, weight.shape[0]):
+        return _ConvIgemm.apply(x, ((k,), (dilation,), bias_grad), weight, bias)
+    return _ConvLib.apply(x, weight, bias, stride, padding, dilation, bias_grad)

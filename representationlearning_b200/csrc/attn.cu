@@ -23,6 +23,10 @@ constexpr int kThreads = 128;
 
 struct WinGeom { int B, H, W, HW, ph, pw, qh, qw, nWin; };
 
+int layernorm_bwd_f32dy(const float* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                        const void* dx_add, void* dx, float* dgamma_acc, float* dbeta_acc, int64_t rows, int C, int dtype,
+                        cudaStream_t stream);
+
 static inline WinGeom make_geom(int B, int H, int W) {
     WinGeom g; g.B = B; g.H = H; g.W = W; g.HW = H * W;
     const int Hp = (H + kWS - 1) / kWS * kWS, Wp = (W + kWS - 1) / kWS * kWS;
@@ -33,18 +37,34 @@ static inline WinGeom make_geom(int B, int H, int W) {
 // ------------------------------------------------------------------------------------------
 // gate: pooled maps over the flat view, 7x7 conv + sigmoid, 1x1 conv + softmax
 // ------------------------------------------------------------------------------------------
+// LayerNorm applied on the fly: the normalised tokens are never written to HBM, and every consumer sees the
+// fp32 value (x - mean)*rstd*gamma + beta whatever the storage dtype of x (ln == NULL: x is used as is).
+struct LnRef { const float* mean; const float* rstd; const float* gamma; const float* beta; };
+
 template <typename T>
-__global__ void gate_pool_kernel(const T* __restrict__ xn, const T* __restrict__ yn, float* __restrict__ pooled,
+__device__ __forceinline__ float normed_at(const T* __restrict__ base, const LnRef& ln, size_t img_row0, size_t f) {
+    float v = to_f(base[f]);
+    if (ln.mean) {
+        const size_t n = img_row0 + f / kC;
+        const int c = (int)(f % kC);
+        v = (v - ln.mean[n]) * ln.rstd[n] * ln.gamma[c] + ln.beta[c];
+    }
+    return v;
+}
+
+template <typename T>
+__global__ void gate_pool_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef lx, LnRef ly, float* __restrict__ pooled,
                                  uint8_t* __restrict__ amax, int HW) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= HW) return;
     const int b = blockIdx.y, z = blockIdx.z;
-    const T* base = (z == 0 ? xn : yn) + (size_t)b * HW * kC;
+    const T* base = (z == 0 ? x : y) + (size_t)b * HW * kC;
+    const LnRef ln = z == 0 ? lx : ly;
     float s = 0.f, mx = -INFINITY;
     int am = 0;
 #pragma unroll 8
     for (int k = 0; k < kC; ++k) {
-        const float v = to_f(base[(size_t)k * HW + j]);
+        const float v = normed_at(base, ln, (size_t)b * HW, (size_t)k * HW + j);
         s += v;
         if (v > mx) { mx = v; am = k; }
     }
@@ -100,7 +120,7 @@ __device__ __forceinline__ int token_pixel(const WinGeom& g, int wi, int wj, int
 
 // gated tokens of one window -> dst[49][36]; pad tokens are zeros
 template <typename T>
-__device__ __forceinline__ void load_window(const T* __restrict__ src, const float* __restrict__ gate_b, float* dst,
+__device__ __forceinline__ void load_window(const T* __restrict__ src, const LnRef& ln, const float* __restrict__ gate_b, float* dst,
                                             const WinGeom& g, int b, int wi, int wj) {
     for (int idx = threadIdx.x; idx < kL * 4; idx += kThreads) {
         const int t = idx >> 2, part = idx & 3;
@@ -110,6 +130,11 @@ __device__ __forceinline__ void load_window(const T* __restrict__ src, const flo
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
         if (n >= 0) {
             load8(src + ((size_t)b * g.HW + n) * kC + part * 8, v);
+            if (ln.mean) {
+                const float mu = ln.mean[(size_t)b * g.HW + n], rs = ln.rstd[(size_t)b * g.HW + n];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = (v[i] - mu) * rs * ln.gamma[part * 8 + i] + ln.beta[part * 8 + i];
+            }
             if (gate_b) {
                 int gi = (int)(((int64_t)n * kC + part * 8) % g.HW);
 #pragma unroll
@@ -217,7 +242,7 @@ constexpr int kFwdSmemFloats = 5 * kTok + 4 * kC * kLD + 4 * kC + 32;
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 4)
-win_attn_fwd_kernel(const T* __restrict__ xn, const T* __restrict__ yn, const float* __restrict__ gmap,
+win_attn_fwd_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef lx, LnRef ly, const float* __restrict__ gmap,
                     const T* __restrict__ xres, T* __restrict__ out, rss_attn_params p, WinGeom g) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;
@@ -233,8 +258,8 @@ win_attn_fwd_kernel(const T* __restrict__ xn, const T* __restrict__ yn, const fl
 
     for (int win = blockIdx.x; win < g.nWin; win += gridDim.x) {
         const int b = win / (g.qh * g.qw), wi = (win / g.qw) % g.qh, wj = win % g.qw;
-        load_window(xn, gmap + ((size_t)b * 2 + 0) * g.HW, xs, g, b, wi, wj);
-        load_window(yn, gmap + ((size_t)b * 2 + 1) * g.HW, ys, g, b, wi, wj);
+        load_window(x, lx, gmap + ((size_t)b * 2 + 0) * g.HW, xs, g, b, wi, wj);
+        load_window(y, ly, gmap + ((size_t)b * 2 + 1) * g.HW, ys, g, b, wi, wj);
         __syncthreads();
         for (int task = warp; task < 21; task += 4) {      // q,k,v projections (DAL.py:873-875)
             const int m = task / 7, tg = task % 7;
@@ -306,8 +331,8 @@ constexpr int kBwdSmemFloats = 7 * kTok + 2 * 2 * kL * kPS + 4 * kC * kLD + 4 * 
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
-win_attn_bwd_kernel(const T* __restrict__ xn, const T* __restrict__ yn, const float* __restrict__ gmap,
-                    const T* __restrict__ dout, T* __restrict__ dxg, T* __restrict__ dyg,
+win_attn_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef lx, LnRef ly, const float* __restrict__ gmap,
+                    const T* __restrict__ dout, float* __restrict__ dxg, float* __restrict__ dyg,
                     rss_attn_params p, rss_attn_grads gr, WinGeom g) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;
@@ -332,9 +357,9 @@ win_attn_bwd_kernel(const T* __restrict__ xn, const T* __restrict__ yn, const fl
 
     for (int win = blockIdx.x; win < g.nWin; win += gridDim.x) {
         const int b = win / (g.qh * g.qw), wi = (win / g.qw) % g.qh, wj = win % g.qw;
-        load_window(xn, gmap + ((size_t)b * 2 + 0) * g.HW, xs, g, b, wi, wj);
-        load_window(yn, gmap + ((size_t)b * 2 + 1) * g.HW, ys, g, b, wi, wj);
-        load_window(dout, (const float*)nullptr, Pb, g, b, wi, wj);     // cropped grad: pad queries get 0
+        load_window(x, lx, gmap + ((size_t)b * 2 + 0) * g.HW, xs, g, b, wi, wj);
+        load_window(y, ly, gmap + ((size_t)b * 2 + 1) * g.HW, ys, g, b, wi, wj);
+        load_window(dout, LnRef{nullptr, nullptr, nullptr, nullptr}, (const float*)nullptr, Pb, g, b, wi, wj);   // cropped grad: pad queries get 0
         __syncthreads();
         for (int task = warp; task < 28; task += 4) {
             const int m = task / 7, tg = task % 7;
@@ -468,11 +493,11 @@ win_attn_bwd_kernel(const T* __restrict__ xn, const T* __restrict__ yn, const fl
             float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (side == 0) projT7(q, Wsm + 0 * kC * kLD, acc, tg, lane);
             else { projT7(k, Wsm + 1 * kC * kLD, acc, tg, lane); projT7(v, Wsm + 2 * kC * kLD, acc, tg, lane); }
-            T* dst = side == 0 ? dxg : dyg;
+            float* dst = side == 0 ? dxg : dyg;
 #pragma unroll
             for (int tt = 0; tt < 7; ++tt) {
                 const int n = token_pixel(g, wi, wj, tg * 7 + tt);
-                if (n >= 0) dst[((size_t)b * g.HW + n) * kC + lane] = from_f<T>(acc[tt]);
+                if (n >= 0) dst[((size_t)b * g.HW + n) * kC + lane] = acc[tt];
             }
         }
         {   // weight / bias gradients: thread (m=warp, c=lane) accumulates dW_m[c][:] += sum_t G_m[t][c] * X_m[t][:]
@@ -508,16 +533,17 @@ win_attn_bwd_kernel(const T* __restrict__ xn, const T* __restrict__ yn, const fl
 // ------------------------------------------------------------------------------------------
 // dgmap[b][z][j] = sum_k dgated_flat[k*HW+j] * normed_flat[k*HW+j]
 template <typename T>
-__global__ void gate_bwd_reduce_kernel(const T* __restrict__ dxg, const T* __restrict__ dyg, const T* __restrict__ xn,
-                                       const T* __restrict__ yn, float* __restrict__ dgmap, int HW) {
+__global__ void gate_bwd_reduce_kernel(const float* __restrict__ dxg, const float* __restrict__ dyg, const T* __restrict__ x,
+                                       const T* __restrict__ y, LnRef lx, LnRef ly, float* __restrict__ dgmap, int HW) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= HW) return;
     const int b = blockIdx.y, z = blockIdx.z;
-    const T* d = (z == 0 ? dxg : dyg) + (size_t)b * HW * kC;
-    const T* n = (z == 0 ? xn : yn) + (size_t)b * HW * kC;
+    const float* d = (z == 0 ? dxg : dyg) + (size_t)b * HW * kC;
+    const T* n = (z == 0 ? x : y) + (size_t)b * HW * kC;
+    const LnRef ln = z == 0 ? lx : ly;
     float s = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < kC; ++k) s += to_f(d[(size_t)k * HW + j]) * to_f(n[(size_t)k * HW + j]);
+    for (int k = 0; k < kC; ++k) s += d[(size_t)k * HW + j] * normed_at(n, ln, (size_t)b * HW, (size_t)k * HW + j);
     dgmap[((size_t)b * 2 + z) * HW + j] = s;
 }
 
@@ -597,14 +623,14 @@ __global__ void __launch_bounds__(256) gate_bwd_conv_kernel(const float* __restr
 }
 
 // d(normed)[f] = d(gated)[f]*g[f mod HW] + dpooled_avg[j]/C + dpooled_max[j]*[k == argmax[j]],  f = k*HW + j
-template <typename T>
-__global__ void gate_bwd_apply_kernel(const T* __restrict__ dxg, const T* __restrict__ dyg, const float* __restrict__ gmap,
+template <typename T, typename TOUT>
+__global__ void gate_bwd_apply_kernel(const float* __restrict__ dxg, const float* __restrict__ dyg, const float* __restrict__ gmap,
                                       const float* __restrict__ dpooled, const uint8_t* __restrict__ amax,
-                                      const T* __restrict__ x_add, T* __restrict__ dxn, T* __restrict__ dyn, int HW) {
+                                      const T* __restrict__ x_add, TOUT* __restrict__ dxn, TOUT* __restrict__ dyn, int HW) {
     const int b = blockIdx.y, z = blockIdx.z;
     const size_t img = (size_t)b * HW * kC;
-    const T* src = (z == 0 ? dxg : dyg) + img;
-    T* dst = (z == 0 ? dxn : dyn) + img;
+    const float* src = (z == 0 ? dxg : dyg) + img;
+    TOUT* dst = (z == 0 ? dxn : dyn) + img;
     const T* add = (z == 0 && x_add) ? x_add + img : nullptr;
     const float* gm = gmap + ((size_t)b * 2 + z) * HW;
     const float* da = dpooled + ((size_t)b * 4 + z * 2 + 0) * HW;
@@ -631,22 +657,25 @@ __global__ void gate_bwd_apply_kernel(const T* __restrict__ dxg, const T* __rest
     }
 }
 
+static inline LnRef ln_ref(const rss_attn_params* p, const float* ln_stats, int64_t rows, int which) {
+    if (!p->ln_w) return LnRef{nullptr, nullptr, nullptr, nullptr};
+    return LnRef{ln_stats + (2 * which) * rows, ln_stats + (2 * which + 1) * rows, p->ln_w, p->ln_b};
+}
+
 template <typename T>
 static int attn_fwd_impl(const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int flags,
-                         void* xn_, void* yn_, float* ln_stats, float* pooled, uint8_t* amax, float* smap, float* gmap,
-                         void* out, cudaStream_t st) {
+                         float* ln_stats, float* pooled, uint8_t* amax, float* smap, float* gmap, void* out, cudaStream_t st) {
     const WinGeom g = make_geom(B, H, W);
     const int64_t rows = (int64_t)B * g.HW;
+    const int dt = sizeof(T) == 4 ? RSS_F32 : RSS_BF16;
     int rc;
-    const void* xn = xn_; const void* yn = yn_;
-    if (p->ln_w) {
-        if ((rc = rss_layernorm_fwd(x, xn_, ln_stats, ln_stats + rows, p->ln_w, p->ln_b, p->ln_eps, rows, kC,
-                                    sizeof(T) == 4 ? RSS_F32 : RSS_BF16, st)) != RSS_OK) return rc;
-        if ((rc = rss_layernorm_fwd(y, yn_, ln_stats + 2 * rows, ln_stats + 3 * rows, p->ln_w, p->ln_b, p->ln_eps, rows, kC,
-                                    sizeof(T) == 4 ? RSS_F32 : RSS_BF16, st)) != RSS_OK) return rc;
-    } else { xn = x; yn = y; }                 // no norm1: the inputs ARE the normalised tokens
+    if (p->ln_w) {      // norm1 statistics only; the normalised tokens are recomputed where they are consumed
+        if ((rc = rss_layernorm_fwd(x, nullptr, ln_stats, ln_stats + rows, p->ln_w, p->ln_b, p->ln_eps, rows, kC, dt, st)) != RSS_OK) return rc;
+        if ((rc = rss_layernorm_fwd(y, nullptr, ln_stats + 2 * rows, ln_stats + 3 * rows, p->ln_w, p->ln_b, p->ln_eps, rows, kC, dt, st)) != RSS_OK) return rc;
+    }
+    const LnRef lx = ln_ref(p, ln_stats, rows, 0), ly = ln_ref(p, ln_stats, rows, 1);
     dim3 pg((g.HW + 255) / 256, B, 2);
-    gate_pool_kernel<T><<<pg, 256, 0, st>>>((const T*)xn, (const T*)yn, pooled, amax, g.HW);
+    gate_pool_kernel<T><<<pg, 256, 0, st>>>((const T*)x, (const T*)y, lx, ly, pooled, amax, g.HW);
     dim3 mg((g.HW + 127) / 128, B);
     gate_map_kernel<<<mg, 128, 0, st>>>(pooled, p->sa1_w, p->sa2_w, p->lvl_w, p->lvl_b, smap, gmap, H, W);
     const size_t smem = kFwdSmemFloats * sizeof(float);
@@ -658,29 +687,27 @@ static int attn_fwd_impl(const void* x, const void* y, const rss_attn_params* p,
     }
     int grid = num_sms() * 4;
     if (grid > g.nWin) grid = g.nWin;
-    win_attn_fwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)xn, (const T*)yn, gmap,
+    win_attn_fwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)y, lx, ly, gmap,
                                                          (flags & RSS_ATTN_NO_RESIDUAL) ? (const T*)nullptr : (const T*)x, (T*)out, *p, g);
     return check_launch();
 }
 
 template <typename T>
 static int attn_bwd_impl(const void* dout, const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int flags,
-                         const void* xn, const void* yn, const float* ln_stats, const float* pooled, const uint8_t* amax,
+                         const float* ln_stats, const float* pooled, const uint8_t* amax,
                          const float* smap, const float* gmap, void* workspace, void* dx, void* dy, const rss_attn_grads* gr,
                          cudaStream_t st) {
     const WinGeom g = make_geom(B, H, W);
     const int64_t rows = (int64_t)B * g.HW;
-    const size_t tok_bytes = (size_t)rows * kC * sizeof(T);
+    const size_t tok_bytes = (size_t)rows * kC * sizeof(float);   // gradient intermediates stay fp32 (LN backward cancels)
     char* ws = (char*)workspace;
-    T* dxg = (T*)ws;  ws += tok_bytes;
-    T* dyg = (T*)ws;  ws += tok_bytes;
+    float* dxg = (float*)ws;  ws += tok_bytes;
+    float* dyg = (float*)ws;  ws += tok_bytes;
     float* dgmap = (float*)ws;  ws += (size_t)B * 2 * g.HW * sizeof(float);
     float* dpre = (float*)ws;   ws += (size_t)B * 2 * g.HW * sizeof(float);
     float* dpooled = (float*)ws;
     const bool has_ln = p->ln_w != nullptr, has_res = !(flags & RSS_ATTN_NO_RESIDUAL);
-    if (!has_ln) { xn = x; yn = y; }
-    // the apply kernel is elementwise: in place when LayerNorm backward follows, else straight into dx/dy
-    T* dxn = has_ln ? dxg : (T*)dx; T* dyn = has_ln ? dyg : (T*)dy;
+    const LnRef lx = ln_ref(p, ln_stats, rows, 0), ly = ln_ref(p, ln_stats, rows, 1);
     const int dt = sizeof(T) == 4 ? RSS_F32 : RSS_BF16;
 
     const size_t smem = kBwdSmemFloats * sizeof(float);
@@ -692,9 +719,9 @@ static int attn_bwd_impl(const void* dout, const void* x, const void* y, const r
     }
     int grid = num_sms() * 2;
     if (grid > g.nWin) grid = g.nWin;
-    win_attn_bwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)xn, (const T*)yn, gmap, (const T*)dout, dxg, dyg, *p, *gr, g);
+    win_attn_bwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)y, lx, ly, gmap, (const T*)dout, dxg, dyg, *p, *gr, g);
     dim3 pg((g.HW + 255) / 256, B, 2);
-    gate_bwd_reduce_kernel<T><<<pg, 256, 0, st>>>(dxg, dyg, (const T*)xn, (const T*)yn, dgmap, g.HW);
+    gate_bwd_reduce_kernel<T><<<pg, 256, 0, st>>>(dxg, dyg, (const T*)x, (const T*)y, lx, ly, dgmap, g.HW);
     dim3 mg((g.HW + 255) / 256, B);
     gate_bwd_map_kernel<<<mg, 256, 0, st>>>(dgmap, gmap, smap, p->lvl_w, dpre, gr->lvl_w, gr->lvl_b, g.HW);
     dim3 cg(((H + 31) / 32) * ((W + 31) / 32), B, 2);
@@ -702,13 +729,15 @@ static int attn_bwd_impl(const void* dout, const void* x, const void* y, const r
     int ag = (int)(((int64_t)g.HW * kC / 8 + 255) / 256);
     if (ag > 1024) ag = 1024;
     dim3 apg(ag, B, 2);
-    gate_bwd_apply_kernel<T><<<apg, 256, 0, st>>>(dxg, dyg, gmap, dpooled, amax,
-                                                  (!has_ln && has_res) ? (const T*)dout : (const T*)nullptr, dxn, dyn, g.HW);
+    // the apply kernel is elementwise: in place (fp32) when LayerNorm backward follows, else straight into dx/dy
+    if (has_ln) gate_bwd_apply_kernel<T, float><<<apg, 256, 0, st>>>(dxg, dyg, gmap, dpooled, amax, (const T*)nullptr, dxg, dyg, g.HW);
+    else gate_bwd_apply_kernel<T, T><<<apg, 256, 0, st>>>(dxg, dyg, gmap, dpooled, amax, has_res ? (const T*)dout : (const T*)nullptr,
+                                                          (T*)dx, (T*)dy, g.HW);
     int rc = check_launch();
     if (rc != RSS_OK || !has_ln) return rc;
     // LayerNorm1 backward for both streams (shared gamma/beta grads); dx also takes the residual path (MTFM:107)
-    if ((rc = rss_layernorm_bwd(dxn, x, ln_stats, ln_stats + rows, p->ln_w, has_res ? dout : nullptr, dx, gr->ln_w, gr->ln_b, rows, kC, dt, st)) != RSS_OK) return rc;
-    return rss_layernorm_bwd(dyn, y, ln_stats + 2 * rows, ln_stats + 3 * rows, p->ln_w, nullptr, dy, gr->ln_w, gr->ln_b, rows, kC, dt, st);
+    if ((rc = layernorm_bwd_f32dy(dxg, x, ln_stats, ln_stats + rows, p->ln_w, has_res ? dout : nullptr, dx, gr->ln_w, gr->ln_b, rows, kC, dt, st)) != RSS_OK) return rc;
+    return layernorm_bwd_f32dy(dyg, y, ln_stats + 2 * rows, ln_stats + 3 * rows, p->ln_w, nullptr, dy, gr->ln_w, gr->ln_b, rows, kC, dt, st);
 }
 
 }  // namespace rss
@@ -716,27 +745,27 @@ static int attn_bwd_impl(const void* dout, const void* x, const void* y, const r
 using namespace rss;
 
 extern "C" size_t rss_attn_bwd_workspace_bytes(int B, int H, int W, int dtype) {
-    const size_t esz = dtype == RSS_F32 ? 4 : 2;
+    (void)dtype;
     const size_t HW = (size_t)H * W;
-    return 2 * (size_t)B * HW * kC * esz + (size_t)B * HW * (2 + 2 + 4) * sizeof(float) + 256;
+    return 2 * (size_t)B * HW * kC * sizeof(float) + (size_t)B * HW * (2 + 2 + 4) * sizeof(float) + 256;
 }
 
 extern "C" int rss_attn_fwd(const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int dtype, int flags,
-                            void* xn, void* yn, float* ln_stats, float* pooled, uint8_t* amax, float* smap, float* gmap,
+                            float* ln_stats, float* pooled, uint8_t* amax, float* smap, float* gmap,
                             void* out, cudaStream_t stream) {
     if (B <= 0 || H <= 0 || W <= 0 || !p) return RSS_ERR_SHAPE;
     if (p->C != kC || p->num_heads != 2 || p->window != kWS) return RSS_ERR_SHAPE;
     if (((int64_t)H * W * kC) % 8) return RSS_ERR_SHAPE;
-    RSS_DISPATCH_DTYPE(dtype, return attn_fwd_impl<T>(x, y, p, B, H, W, flags, xn, yn, ln_stats, pooled, amax, smap, gmap, out, stream));
+    RSS_DISPATCH_DTYPE(dtype, return attn_fwd_impl<T>(x, y, p, B, H, W, flags, ln_stats, pooled, amax, smap, gmap, out, stream));
 }
 
 extern "C" int rss_attn_bwd(const void* dout, const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int dtype, int flags,
-                            const void* xn, const void* yn, const float* ln_stats, const float* pooled, const uint8_t* amax,
+                            const float* ln_stats, const float* pooled, const uint8_t* amax,
                             const float* smap, const float* gmap, void* workspace, size_t workspace_bytes,
                             void* dx, void* dy, const rss_attn_grads* grads, cudaStream_t stream) {
     if (B <= 0 || H <= 0 || W <= 0 || !p || !grads) return RSS_ERR_SHAPE;
     if (p->C != kC || p->num_heads != 2 || p->window != kWS) return RSS_ERR_SHAPE;
     if (workspace_bytes < rss_attn_bwd_workspace_bytes(B, H, W, dtype)) return RSS_ERR_WORKSPACE;
-    RSS_DISPATCH_DTYPE(dtype, return attn_bwd_impl<T>(dout, x, y, p, B, H, W, flags, xn, yn, ln_stats, pooled, amax, smap, gmap,
+    RSS_DISPATCH_DTYPE(dtype, return attn_bwd_impl<T>(dout, x, y, p, B, H, W, flags, ln_stats, pooled, amax, smap, gmap,
                                                         workspace, dx, dy, grads, stream));
 }

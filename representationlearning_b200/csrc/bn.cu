@@ -76,25 +76,42 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, float* __restrict__ par
     }
 }
 
-// Chan-combine nparts partials -> stat[C][2] = (mean, M2), total[0] = count.  One thread per channel.
+// Chan-combine nparts partials -> stat[C][2] = (mean, M2), total[0] = count.  One WARP per channel: lanes take
+// partials p = lane, lane+32, ... and the 32 running (n, mean, M2) triples are merged with a shuffle tree.
 __global__ void bn_combine_kernel(const float* __restrict__ part, const float* __restrict__ cnt, int nparts, int C,
                                   float* __restrict__ stat, float* __restrict__ total) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
-    double na = 0.0, ma = 0.0, qa = 0.0;
-    for (int p = 0; p < nparts; ++p) {
-        const double nb = cnt[p];
-        if (nb > 0.0) {
-            const double mb = part[((size_t)p * C + c) * 2], qb = part[((size_t)p * C + c) * 2 + 1];
-            const double nn = na + nb, d = mb - ma;
+    float na = 0.f, ma = 0.f, qa = 0.f;
+    for (int p = lane; p < nparts; p += 32) {
+        const float nb = cnt[p];
+        if (nb > 0.f) {
+            const float mb = part[((size_t)p * C + c) * 2], qb = part[((size_t)p * C + c) * 2 + 1];
+            const float nn = na + nb, d = mb - ma;
             ma += d * (nb / nn);
             qa += qb + d * d * (na * nb / nn);
             na = nn;
         }
     }
-    stat[c * 2] = (float)ma;
-    stat[c * 2 + 1] = (float)qa;
-    if (c == 0) total[0] = (float)na;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float nb = __shfl_xor_sync(0xffffffffu, na, o), mb = __shfl_xor_sync(0xffffffffu, ma, o),
+                    qb = __shfl_xor_sync(0xffffffffu, qa, o);
+        const float nn = na + nb;
+        if (nn > 0.f) {
+            const float d = mb - ma;
+            // symmetric form: both lanes of a pair compute the same merged triple
+            const float m = (na * ma + nb * mb) / nn;
+            qa = qa + qb + d * d * (na * nb / nn);
+            ma = m;
+            na = nn;
+        }
+    }
+    if (lane == 0) {
+        stat[c * 2] = ma;
+        stat[c * 2 + 1] = qa;
+        if (c == 0) total[0] = na;
+    }
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ stat, const float* __restrict__ total,
@@ -222,8 +239,12 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ sums, float inv_count,
-                                    T* __restrict__ dx, T* __restrict__ dres, int64_t rows, int C, int cg, int rpb) {
+                                    T* __restrict__ dx, T* __restrict__ dres, int64_t rows, int C, int cg, int rpb,
+                                    const float* __restrict__ local_sums, float* __restrict__ dgamma_acc, float* __restrict__ dbeta_acc) {
     const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
+    if (dgamma_acc && blockIdx.x == 0) {      // parameter gradients straight into the caller's (flat) grad buffer
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta_acc[c] += local_sums[c]; dgamma_acc[c] += local_sums[C + c]; }
+    }
     float sc[8], sh[8], mu[8], is[8], m0[8], m1[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -248,7 +269,7 @@ using namespace rss;
 extern "C" int rss_bn_stats_nparts(int64_t rows, int C) {
     if (C <= 0 || C % 8) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    return bn_grid(rows, g.rpb * 8, 4);
+    return bn_grid(rows, g.rpb * 8, 2);
 }
 
 extern "C" int rss_bn_stats(const void* x, float* partials, float* counts, int64_t rows, int C, int dtype, cudaStream_t st) {
@@ -263,7 +284,7 @@ extern "C" int rss_bn_stats(const void* x, float* partials, float* counts, int64
 extern "C" int rss_bn_combine(const float* partials, const float* counts, int nparts, int C, float* stat, float* total,
                               cudaStream_t st) {
     if (C <= 0 || nparts <= 0) return RSS_ERR_SHAPE;
-    bn_combine_kernel<<<(C + 127) / 128, 128, 0, st>>>(partials, counts, nparts, C, stat, total);
+    bn_combine_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(partials, counts, nparts, C, stat, total);
     return check_launch();
 }
 
@@ -294,6 +315,7 @@ extern "C" int rss_bn_eval_affine(const float* gamma, const float* beta, const f
 extern "C" int rss_bn_act_fwd(const void* x, const void* residual, void* y, const float* scale, const float* shift,
                               int64_t rows, int C, int act, int dtype, cudaStream_t st) {
     if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
+    if (residual && act == RSS_ACT_GELU) return RSS_ERR_SHAPE;   // not a pattern of the reference (backward would need the residual)
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 4, 8);
     RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_act_fwd_kernel, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, rows, C, g.cg, g.rpb)));
@@ -316,11 +338,13 @@ extern "C" int rss_bn_bwd_reduce(const void* x, const void* y, const void* dy, c
 
 extern "C" int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
                                 const float* mean, const float* invstd, const float* sums, float inv_count,
-                                void* dx, void* dres, int64_t rows, int C, int act, int dtype, cudaStream_t st) {
+                                void* dx, void* dres, int64_t rows, int C, int act, int dtype,
+                                const float* local_sums, float* dgamma_acc, float* dbeta_acc, cudaStream_t st) {
     if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
     if (act == RSS_ACT_RELU && !y) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 4, 8);
-    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb)));
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
+                                                                                                           local_sums, dgamma_acc, dbeta_acc)));
     return check_launch();
 }

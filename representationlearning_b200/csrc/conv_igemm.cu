@@ -1,0 +1,421 @@
+// tcgen05 / TMA implicit-GEMM convolution for NHWC bf16 activations (sm_100a only).
+//
+// Covers the dense convolutions of the RSSFormer hot path that are stride-1 "same" convolutions:
+//   * the FFN's three parallel convs dw(1x1) + dw6(3x3, dil 6) + dw12(3x3, dil 12) summed
+//     (modules/ffn_block.py:226-228,250-257) as ONE GEMM: 17 taps (the three centre taps coincide and are
+//     merged by adding their weights), K = 17 * 128;
+//   * fc1 / fc2 (1x1, ffn_block.py:219,232), the neck's 480x480 1x1 (hrnet_aux.py:46), HRNet's 3x3/1x1
+//     stride-1 convs (_hrnet_rssformer.py:209-213,253-259);
+//   * their data gradients (same kernel, transposed weights, negated taps).
+//
+// GEMM view: M = B*H*W output pixels (BLOCK_M = 128 = BH rows x BW pixels of one image), N = Cout (BLOCK_N <= 256),
+// K = taps x Cin in blocks of 64 channels.  Per k-block the A operand is ONE TMA tile load of the input at
+// the tap-shifted coordinates {c0, x0+dx, y0+dy, b}: TMA's out-of-bounds zero fill IS the conv padding, so no
+// im2col buffer and no boundary code exist.  Operands land in 128B-swizzled shared memory, tcgen05.mma
+// (cta_group::1, M=128, kind::f16, bf16 x bf16 -> fp32) accumulates in TMEM, and a 4-warp epilogue drains
+// TMEM with tcgen05.ld (+bias, ->bf16) while the MMA warp already works on the next tile (2 TMEM stages).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.  Persistent: one CTA per SM.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace rss {
+
+constexpr int kBlockM = 128, kBlockK = 64, kUmmaK = 16;
+constexpr int kConvThreads = 192;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;          // 16 KB
+constexpr int kMaxTaps = 32;
+constexpr uint32_t kSpinLimit = 1u << 28;
+
+struct ConvTaps { int n; int dy[kMaxTaps]; int dx[kMaxTaps]; };
+
+struct ConvGeom {
+    int B, H, W, Cin, Cout;
+    int BW, BH;                  // spatial tile: BW*BH == 128
+    int tiles_x, tiles_y, m_tiles, n_tiles, block_n;
+    int kchunks;                 // ceil(Cin / 64)
+    int stages;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must trap (error returned to the caller), never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) { __trap(); }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {     // arrives on `bar` when all prior MMAs of this thread are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B; 8-row groups of 1024 B): cute::UMMA::SmemDescriptor
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);           // start address      bits [0,14)
+    d |= (uint64_t)1 << 16;                                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                       // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                                 // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                                 // layout: SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ inline uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, ConvGeom g, ConvTaps taps) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t b_tile_bytes = (uint32_t)g.block_n * kBlockK * 2;
+    const uint32_t stage_bytes = kATileBytes + b_tile_bytes;               // multiple of 1024 (block_n % 16 == 0 -> N*128 B % 2048)
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
+    // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty ; then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * g.stages + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tmem_cols = (2 * g.block_n <= 32) ? 32 : (2 * g.block_n <= 64) ? 64 : (2 * g.block_n <= 128) ? 128
+                               : (2 * g.block_n <= 256) ? 256 : 512;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + g.stages + s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(bars + 2 * g.stages + s), 1); mbar_init(smem_u32(bars + 2 * g.stages + 2 + s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = g.m_tiles * g.n_tiles;
+    const int kblocks = taps.n * g.kchunks;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
+                const int tx = mt % g.tiles_x, ty = (mt / g.tiles_x) % g.tiles_y, b = mt / (g.tiles_x * g.tiles_y);
+                const int x0 = tx * g.BW, y0 = ty * g.BH, n0 = nt * g.block_n;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const int tap = kb / g.kchunks, kc = kb % g.kchunks;
+                    mbar_wait(smem_u32(bars + g.stages + stage), phase ^ 1);           // slot free?
+                    const uint32_t full = smem_u32(bars + stage);
+                    const uint32_t a_dst = smem_u32(smem + (size_t)stage * stage_bytes);
+                    mbar_expect_tx(full, stage_bytes);
+                    tma_load_4d(a_dst, &tmap_a, full, kc * kBlockK, x0 + taps.dx[tap], y0 + taps.dy[tap], b);
+                    tma_load_2d(a_dst + kATileBytes, &tmap_b, full, kc * kBlockK, tap * g.Cout + n0);
+                    if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(g.block_n);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(smem_u32(bars + 2 * g.stages + 2 + acc), acc_phase ^ 1);       // epilogue drained this TMEM stage?
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * g.block_n;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const int kc = kb % g.kchunks;
+                    int ksteps = (g.Cin - kc * kBlockK + kUmmaK - 1) / kUmmaK;            // skip zero-filled tail channels
+                    if (ksteps > kBlockK / kUmmaK) ksteps = kBlockK / kUmmaK;
+                    mbar_wait(smem_u32(bars + stage), phase);                             // TMA landed?
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(a_addr + kATileBytes);
+                    for (int k = 0; k < ksteps; ++k)     // +32 B per K=16 step inside the 128 B swizzle atom
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(smem_u32(bars + g.stages + stage));                      // frees the smem slot when MMAs finish
+                    if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(smem_u32(bars + 2 * g.stages + acc));                        // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue: TMEM -> registers -> (+bias, bf16) -> global =================
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;                   // tile row == TMEM lane
+        uint32_t acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
+            const int tx = mt % g.tiles_x, ty = (mt / g.tiles_x) % g.tiles_y, b = mt / (g.tiles_x * g.tiles_y);
+            const int x = tx * g.BW + row % g.BW, y = ty * g.BH + row / g.BW, n0 = nt * g.block_n;
+            const bool live = x < g.W && y < g.H;
+            __nv_bfloat16* dst = out + (((size_t)b * g.H + y) * g.W + x) * g.Cout + n0;
+            mbar_wait(smem_u32(bars + 2 * g.stages + acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * g.block_n;
+            for (int c0 = 0; c0 < g.block_n; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(t_row + c0, r);
+                tmem_ld_wait();
+                if (live) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (bias ? bias[n0 + c0 + i] : 0.f);
+                    store8(dst + c0, v);
+                    store8(dst + c0 + 8, v + 8);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(bars + 2 * g.stages + 2 + acc));           // 4 warps -> count 4
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---- weight packing: fp32 (Cout,Cin,k,k) sources -> bf16 [tap][N][K] (K contiguous) ------------------------
+struct PackSrc { const float* w; const float* b; int k; int dil; };
+struct PackPlan {
+    int n_src;
+    PackSrc src[3];
+    int n_taps;
+    int tap_src[kMaxTaps][3];        // per tap: up to 3 contributing (source, ky*k+kx); -1 = none
+    int tap_pos[kMaxTaps][3];
+};
+
+// transpose == 0: packed[tap][co][ci] = sum_s w_s[co][ci][pos]      (forward:  N=Cout, K=Cin)
+// transpose == 1: packed[tap][ci][co] = sum_s w_s[co][ci][pos]      (dgrad:    N=Cin,  K=Cout)
+__global__ void conv_pack_kernel(PackPlan plan, int Cout, int Cin, int transpose, __nv_bfloat16* __restrict__ packed,
+                                 float* __restrict__ bias_sum) {
+    const int64_t per_tap = (int64_t)Cout * Cin;
+    const int64_t total = per_tap * plan.n_taps;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(idx / per_tap);
+        const int64_t r = idx % per_tap;
+        const int n = (int)(r / (transpose ? Cout : Cin)), k = (int)(r % (transpose ? Cout : Cin));
+        const int co = transpose ? k : n, ci = transpose ? n : k;
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int s = plan.tap_src[tap][e];
+            if (s >= 0) {
+                const int kk = plan.src[s].k * plan.src[s].k;
+                acc += plan.src[s].w[((int64_t)co * Cin + ci) * kk + plan.tap_pos[tap][e]];
+            }
+        }
+        packed[idx] = __float2bfloat16_rn(acc);
+    }
+    if (bias_sum && blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
+            float s = 0.f;
+            bool any = false;
+            for (int e = 0; e < plan.n_src; ++e) if (plan.src[e].b) { s += plan.src[e].b[c]; any = true; }
+            bias_sum[c] = any ? s : 0.f;
+        }
+    }
+}
+
+static int build_plan(const float* const* w, const float* const* b, const int* ks, const int* dils, int n_src, int negate,
+                      PackPlan* plan, ConvTaps* taps) {
+    if (n_src < 1 || n_src > 3) return RSS_ERR_SHAPE;
+    plan->n_src = n_src;
+    taps->n = 0;
+    for (int t = 0; t < kMaxTaps; ++t) for (int e = 0; e < 3; ++e) { plan->tap_src[t][e] = -1; plan->tap_pos[t][e] = 0; }
+    for (int s = 0; s < n_src; ++s) {
+        const int k = ks[s], d = dils[s];
+        if (k != 1 && k != 3) return RSS_ERR_SHAPE;
+        plan->src[s].w = w[s]; plan->src[s].b = b ? b[s] : nullptr; plan->src[s].k = k; plan->src[s].dil = d;
+        for (int ky = 0; ky < k; ++ky)
+            for (int kx = 0; kx < k; ++kx) {
+                int dy = (ky - k / 2) * d, dx = (kx - k / 2) * d;
+                if (negate) { dy = -dy; dx = -dx; }
+                int t = 0;
+                for (; t < taps->n; ++t) if (taps->dy[t] == dy && taps->dx[t] == dx) break;
+                if (t == taps->n) {
+                    if (taps->n == kMaxTaps) return RSS_ERR_SHAPE;
+                    taps->dy[t] = dy; taps->dx[t] = dx; ++taps->n;
+                }
+                int e = 0;
+                while (e < 3 && plan->tap_src[t][e] >= 0) ++e;
+                if (e == 3) return RSS_ERR_SHAPE;
+                plan->tap_src[t][e] = s; plan->tap_pos[t][e] = ky * k + kx;
+            }
+    }
+    plan->n_taps = taps->n;
+    return RSS_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// the driver entry point is resolved through the runtime (no link-time dependency on libcuda.so)
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int make_maps(const void* x, const void* wp, const ConvGeom& g, int n_taps, CUtensorMap* ma, CUtensorMap* mb) {
+    EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled();
+    if (!cuTensorMapEncodeTiled) return RSS_ERR_CUDA;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+        cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.W * g.Cin * 2, (cuuint64_t)g.H * g.W * g.Cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)g.BW, (cuuint32_t)g.BH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = cuTensorMapEncodeTiled(ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return RSS_ERR_CUDA; }
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)n_taps * g.Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)g.block_n};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = cuTensorMapEncodeTiled(mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, es,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return RSS_ERR_CUDA; }
+    }
+    return RSS_OK;
+}
+
+}  // namespace rss
+
+using namespace rss;
+
+// geometry the igemm path accepts: stride 1, "same" padding, Cin % 8 == 0, Cout % 16 == 0, W a power of two <= 128 or a
+// multiple of 128; returns 1 if supported
+extern "C" int rss_conv_igemm_supported(int B, int H, int W, int Cin, int Cout) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin < 16 || Cin % 8 || Cout < 16 || Cout % 16) return 0;
+    if (W >= 128) return W % 128 == 0;
+    return (W & (W - 1)) == 0 && W >= 8;
+}
+
+extern "C" size_t rss_conv_packed_bytes(int n_srcs, const int* ksizes, int Cout, int Cin) {
+    size_t taps = 0;
+    for (int s = 0; s < n_srcs; ++s) taps += (size_t)ksizes[s] * ksizes[s];
+    return taps * Cout * Cin * 2;     // upper bound (merged centre taps make it smaller)
+}
+
+// Pack 1..3 parallel convolutions (same Cout/Cin, summed outputs) into the igemm weight layout.
+// transpose=0: forward operand; transpose=1: data-gradient operand (taps negated, Cout/Cin swapped).
+extern "C" int rss_conv_pack_weights(const float* const* weights, const float* const* biases, const int* ksizes, const int* dilations,
+                                     int n_srcs, int Cout, int Cin, int transpose, void* packed, float* bias_sum,
+                                     int* n_taps_out, int* taps_dy_out, int* taps_dx_out, cudaStream_t st) {
+    PackPlan plan; ConvTaps taps;
+    int rc = build_plan(weights, biases, ksizes, dilations, n_srcs, transpose, &plan, &taps);
+    if (rc != RSS_OK) return rc;
+    const int64_t total = (int64_t)plan.n_taps * Cout * Cin;
+    int grid = (int)((total + 255) / 256);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    conv_pack_kernel<<<grid, 256, 0, st>>>(plan, Cout, Cin, transpose, (__nv_bfloat16*)packed, transpose ? nullptr : bias_sum);
+    *n_taps_out = taps.n;
+    for (int t = 0; t < taps.n; ++t) { taps_dy_out[t] = taps.dy[t]; taps_dx_out[t] = taps.dx[t]; }
+    return check_launch();
+}
+
+// y[b,y,x,:] = bias + sum_tap W_tap . x[b, y+dy_tap, x+dx_tap, :]   (zero outside the image); bf16 in/out, fp32 accumulate.
+// w_packed: bf16 [n_taps][Cout][Cin].  For a data gradient call it with (x=dY, Cin<->Cout swapped, transposed pack).
+extern "C" int rss_conv_igemm(const void* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int Cin, int Cout,
+                              int n_taps, const int* taps_dy, const int* taps_dx, cudaStream_t st) {
+    if (!rss_conv_igemm_supported(B, H, W, Cin, Cout) || n_taps < 1 || n_taps > kMaxTaps) return RSS_ERR_SHAPE;
+    ConvGeom g;
+    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
+    g.BW = W >= 128 ? 128 : W; g.BH = kBlockM / g.BW;
+    g.tiles_x = (W + g.BW - 1) / g.BW; g.tiles_y = (H + g.BH - 1) / g.BH;
+    g.m_tiles = B * g.tiles_x * g.tiles_y;
+    g.n_tiles = (Cout + 255) / 256;
+    if (Cout % g.n_tiles || (Cout / g.n_tiles) % 16) return RSS_ERR_SHAPE;
+    g.block_n = Cout / g.n_tiles;
+    g.kchunks = (Cin + kBlockK - 1) / kBlockK;
+    const size_t stage_bytes = kATileBytes + (size_t)g.block_n * kBlockK * 2;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return RSS_ERR_SHAPE;
+    g.stages = stages;
+    const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 4) * 8 + 16;
+    ConvTaps taps; taps.n = n_taps;
+    for (int t = 0; t < n_taps; ++t) { taps.dy[t] = taps_dy[t]; taps.dx[t] = taps_dx[t]; }
+    CUtensorMap ma, mb;
+    int rc = make_maps(x, w_packed, g, n_taps, &ma, &mb);
+    if (rc != RSS_OK) return rc;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e != cudaSuccess) { g_last_cuda_error = (int)e; return RSS_ERR_CUDA; }
+        attr_smem = 227 * 1024;
+    }
+    int grid = num_sms();
+    const int total_tiles = g.m_tiles * g.n_tiles;
+    if (grid > total_tiles) grid = total_tiles;
+    conv_igemm_kernel<<<grid, kConvThreads, smem, st>>>(ma, mb, bias, (__nv_bfloat16*)y, g, taps);
+    return check_launch();
+}

@@ -46,15 +46,15 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, T*
             float o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = (v[i] - mu) * rstd * g[i] + b[i];
-            store8(y + row * C + sub * 8, o);
+            if (y) store8(y + row * C + sub * 8, o);      // y == NULL: statistics only (consumers re-normalise on the fly)
             if (sub == 0 && mean_out) { mean_out[row] = mu; rstd_out[row] = rstd; }
         }
     }
 }
 
 // dx = rstd * (dy*g - mean_c(dy*g) - xhat * mean_c(dy*g*xhat)) [+ dx_add];  dgamma += sum_rows dy*xhat; dbeta += sum_rows dy
-template <typename T, int TPT>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename T, typename TDY, int TPT>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, const T* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const T* __restrict__ dx_add,
                                                      T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -132,7 +132,7 @@ static int ln_fwd_launch(const void* x, void* y, float* mean, float* rstd, const
     return check_launch();
 }
 
-template <typename T>
+template <typename T, typename TDY>
 static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                          const void* dx_add, void* dx, float* dgamma, float* dbeta, int64_t rows, int C, cudaStream_t st) {
     const int tpt = C / 8;
@@ -141,7 +141,7 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const
     const int cap = num_sms() * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-#define LN_CASE(TPT) case TPT: ln_bwd_kernel<T, TPT><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dx_add, (T*)dx, dgamma, dbeta, rows); break;
+#define LN_CASE(TPT) case TPT: ln_bwd_kernel<T, TDY, TPT><<<grid, 256, 0, st>>>((const TDY*)dy, (const T*)x, mean, rstd, gamma, (const T*)dx_add, (T*)dx, dgamma, dbeta, rows); break;
     switch (tpt) { LN_CASE(1) LN_CASE(2) LN_CASE(4) LN_CASE(8) LN_CASE(16) LN_CASE(32) default: return RSS_ERR_SHAPE; }
 #undef LN_CASE
     return check_launch();
@@ -161,5 +161,15 @@ extern "C" int rss_layernorm_bwd(const void* dy, const void* x, const float* mea
                                  int64_t rows, int C, int dtype, cudaStream_t stream) {
     if (rows < 0 || C <= 0 || C % 8 != 0 || C > 256 || ((C / 8) & (C / 8 - 1))) return RSS_ERR_SHAPE;
     if (rows == 0) return RSS_OK;
-    RSS_DISPATCH_DTYPE(dtype, return rss::ln_bwd_launch<T>(dy, x, mean, rstd, gamma, dx_add, dx, dgamma_acc, dbeta_acc, rows, C, stream));
+    RSS_DISPATCH_DTYPE(dtype, return rss::ln_bwd_launch<T, T>(dy, x, mean, rstd, gamma, dx_add, dx, dgamma_acc, dbeta_acc, rows, C, stream));
+}
+
+// internal variant used by the attention region: the incoming gradient is fp32 whatever the activation dtype
+namespace rss {
+int layernorm_bwd_f32dy(const float* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                        const void* dx_add, void* dx, float* dgamma_acc, float* dbeta_acc, int64_t rows, int C, int dtype,
+                        cudaStream_t stream) {
+    if (rows <= 0) return RSS_OK;
+    RSS_DISPATCH_DTYPE(dtype, return ln_bwd_launch<T, float>(dy, x, mean, rstd, gamma, dx_add, dx, dgamma_acc, dbeta_acc, rows, C, stream));
+}
 }

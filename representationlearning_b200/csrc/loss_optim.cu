@@ -167,17 +167,20 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float gscal
     }
 }
 
-// g' = g*gscale*clip + wd*p ; m = first ? g' : mu*m + g' ; p -= lr*m ; optionally g = 0 and bf16 shadow copy
+// g' = g*gscale*clip + wd*p ; m = mu*m + g' (m starts at 0, i.e. m = g' on the first step like torch.optim.SGD) ;
+// p -= lr*m ; optionally g = 0 and bf16 shadow copy.  lr is read from device memory so that a captured CUDA graph
+// of the step follows the poly schedule without re-capture.
 __global__ void sgd_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, int64_t n,
-                                const double* __restrict__ sumsq, float gscale, float max_norm, float lr, float mu, float wd,
-                                int first_step, int zero_grad, __nv_bfloat16* __restrict__ shadow) {
+                                const double* __restrict__ sumsq, float gscale, float max_norm, const float* __restrict__ lr_dev,
+                                float mu, float wd, int zero_grad, __nv_bfloat16* __restrict__ shadow) {
+    const float lr = *lr_dev;
     const float total = (float)sqrt(*sumsq);
     float clip = max_norm > 0.f ? max_norm / (total + 1e-6f) : 1.f;
     clip = fminf(clip, 1.f) * gscale;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float pv = p[i];
         const float gv = g[i] * clip + wd * pv;
-        const float mv = first_step ? gv : mu * m[i] + gv;
+        const float mv = mu * m[i] + gv;
         const float np = pv - lr * mv;
         m[i] = mv;
         p[i] = np;
@@ -225,10 +228,10 @@ extern "C" int rss_grad_sumsq(const float* grads, int64_t n, float grad_scale, d
 }
 
 extern "C" int rss_sgd_step(float* params, float* grads, float* momentum_buf, int64_t n, const double* sumsq, float grad_scale,
-                            float max_norm, float lr, float momentum, float weight_decay, int first_step, int zero_grad,
+                            float max_norm, const float* lr, float momentum, float weight_decay, int zero_grad,
                             void* bf16_shadow, cudaStream_t st) {
-    if (n <= 0) return RSS_ERR_SHAPE;
+    if (n <= 0 || !lr) return RSS_ERR_SHAPE;
     sgd_step_kernel<<<num_sms() * 8, 256, 0, st>>>(params, grads, momentum_buf, n, sumsq, grad_scale, max_norm, lr, momentum,
-                                                   weight_decay, first_step, zero_grad, (__nv_bfloat16*)bf16_shadow);
+                                                   weight_decay, zero_grad, (__nv_bfloat16*)bf16_shadow);
     return check_launch();
 }

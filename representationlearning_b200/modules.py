@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .conv import conv2d
+from .conv import conv2d, conv_sum
 
 BN_MOMENTUM = 0.1        # _hrnet_rssformer.py:27
 CL = torch.channels_last
@@ -33,8 +33,10 @@ class FusedBNAct(nn.Module):
         self.register_buffer("running_var", torch.ones(num_features))
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
 
+    defer_counter = False      # trainer.FlatSGD bumps every num_batches_tracked with one foreach op per step instead
+
     def forward(self, x, residual=None):
-        if self.training:
+        if self.training and not FusedBNAct.defer_counter:
             self.num_batches_tracked += 1
         return ops.BNAct.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
                                self.training, self.momentum, self.eps, self.act, True if self.sync else None)
@@ -121,11 +123,12 @@ class MlpDWBN(nn.Module):
         self.norm3 = FusedBNAct(out_features, _lib.ACT_GELU, sync=True)
 
     def forward_nchw(self, x):
-        x = self.norm1(conv2d(x, self.fc1.weight, self.fc1.bias))
-        c = conv2d(x, self.dw.weight, self.dw.bias) + conv2d(x, self.dw6.weight, self.dw6.bias, 1, 6, 6) \
-            + conv2d(x, self.dw12.weight, self.dw12.bias, 1, 12, 12)
+        bg = not self.training       # every bias here feeds a training-mode BN: its gradient is identically zero
+        x = self.norm1(conv2d(x, self.fc1.weight, self.fc1.bias, bias_grad=bg))
+        c = conv_sum(x, [(self.dw.weight, self.dw.bias, 1, 1), (self.dw6.weight, self.dw6.bias, 3, 6),
+                         (self.dw12.weight, self.dw12.bias, 3, 12)], bias_grad=bg)
         x = self.norm2(c)
-        return self.norm3(conv2d(x, self.fc2.weight, self.fc2.bias))
+        return self.norm3(conv2d(x, self.fc2.weight, self.fc2.bias, bias_grad=bg))
 
     def forward(self, x, H, W):
         if x.dim() != 3:
@@ -176,5 +179,5 @@ class SimpleFusion8(nn.Module):
     def forward(self, feat_list):
         x0 = feat_list[0]
         cat = ops.NeckGather.apply(*feat_list)
-        x = self.fuse_conv[1](conv2d(cat, self.fuse_conv[0].weight, self.fuse_conv[0].bias))
+        x = self.fuse_conv[1](conv2d(cat, self.fuse_conv[0].weight, self.fuse_conv[0].bias, bias_grad=not self.training))
         return x, x0

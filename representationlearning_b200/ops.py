@@ -20,7 +20,7 @@ KERNELS_PER_CALL = {
     "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1,
     "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 4, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
     "rss_headaux_fwd": 2, "rss_seg_loss_fwd": 2, "rss_seg_loss_bwd": 1, "rss_grad_sumsq": 1, "rss_sgd_step": 1,
-    "rss_conv_fwd": 1, "rss_conv_dgrad": 1, "rss_conv_wgrad": 1,
+    "rss_conv_igemm": 1, "rss_conv_pack_weights": 1,
 }
 COUNTERS = {"launches": 0, "calls": 0}
 TIMED = {}            # op name -> list of (start_event, end_event), filled only while bench.py enables it
@@ -80,6 +80,17 @@ def nhwc(t):
     return t.contiguous(memory_format=CL)
 
 
+def grad_sink(p):
+    """fp32 gradient buffer of a parameter that kernels may accumulate into directly (bypassing one AccumulateGrad
+    add kernel per parameter per step: ~1.4 k launches).  None -> return the gradient through autograd as usual."""
+    if p is None or not isinstance(p, torch.nn.Parameter):
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous():
+        return None
+    return g
+
+
 def _world(group):
     if group is None or not dist.is_available() or not dist.is_initialized():
         return 1
@@ -103,6 +114,7 @@ class LayerNormNHWC(torch.autograd.Function):
         check(lib.rss_layernorm_fwd(_p(x), _p(y), _p(stats[0]), _p(stats[1]), _p(g), _p(b), eps, rows, C, _dt(x), _st()),
               "rss_layernorm_fwd")
         ctx.save_for_backward(x, stats, g)
+        ctx.refs = (gamma, beta)
         return y
 
     @staticmethod
@@ -113,10 +125,13 @@ class LayerNormNHWC(torch.autograd.Function):
         B, C, H, W = x.shape
         rows = B * H * W
         dx = torch.empty_like(x, memory_format=CL)
-        dgb = torch.zeros(2, C, device=x.device, dtype=torch.float32)
-        check(lib.rss_layernorm_bwd(_p(dy), _p(x), _p(stats[0]), _p(stats[1]), _p(g), None, _p(dx), _p(dgb[0]), _p(dgb[1]),
-                                    rows, C, _dt(x), _st()), "rss_layernorm_bwd")
-        return dx, dgb[0], dgb[1], None
+        sg, sb = grad_sink(ctx.refs[0]), grad_sink(ctx.refs[1])
+        direct = sg is not None and sb is not None
+        dgb = None if direct else torch.zeros(2, C, device=x.device, dtype=torch.float32)
+        check(lib.rss_layernorm_bwd(_p(dy), _p(x), _p(stats[0]), _p(stats[1]), _p(g), None, _p(dx),
+                                    _p(sg if direct else dgb[0]), _p(sb if direct else dgb[1]), rows, C, _dt(x), _st()),
+              "rss_layernorm_bwd")
+        return (dx, None, None, None) if direct else (dx, dgb[0], dgb[1], None)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -143,8 +158,6 @@ class WindowAttention(torch.autograd.Function):
             setattr(ap, n, _p(p))
         ap.ln_eps, ap.C, ap.num_heads, ap.window = float(eps), C, 2, 7
         dev = x.device
-        xn = torch.empty_like(x, memory_format=CL) if has_ln else None
-        yn = torch.empty_like(x, memory_format=CL) if has_ln else None
         ln_stats = torch.empty(4, B * HW, device=dev, dtype=torch.float32) if has_ln else None
         pooled = torch.empty(B, 4, HW, device=dev, dtype=torch.float32)
         amax = torch.empty(B, 2, HW, device=dev, dtype=torch.uint8)
@@ -153,24 +166,26 @@ class WindowAttention(torch.autograd.Function):
         out = torch.empty_like(x, memory_format=CL)
         flags = 0 if residual else 1
         with timed("rss_attn_fwd"):
-            check(lib.rss_attn_fwd(_p(x), _p(y), ctypes.byref(ap), B, H, W, _dt(x), flags, _p(xn), _p(yn), _p(ln_stats),
+            check(lib.rss_attn_fwd(_p(x), _p(y), ctypes.byref(ap), B, H, W, _dt(x), flags, _p(ln_stats),
                                    _p(pooled), _p(amax), _p(smap), _p(gmap), _p(out), _st()), "rss_attn_fwd")
-        ctx.save_for_backward(x, y, xn, yn, ln_stats, pooled, amax, smap, gmap, *ps)
-        ctx.eps, ctx.flags = float(eps), flags
+        ctx.save_for_backward(x, y, ln_stats, pooled, amax, smap, gmap, *ps)
+        ctx.eps, ctx.flags, ctx.refs = float(eps), flags, params
         return out
 
     @staticmethod
     def backward(ctx, dout):
         lib = _lib.load()
-        x, y, xn, yn, ln_stats, pooled, amax, smap, gmap = ctx.saved_tensors[:9]
-        ps = ctx.saved_tensors[9:]
+        x, y, ln_stats, pooled, amax, smap, gmap = ctx.saved_tensors[:7]
+        ps = ctx.saved_tensors[7:]
         dout = nhwc(dout)
         B, C, H, W = x.shape
         ap = AttnParams()
         for n, p in zip(_ATTN_NAMES, ps):
             setattr(ap, n, _p(p))
         ap.ln_eps, ap.C, ap.num_heads, ap.window = ctx.eps, C, 2, 7
-        grads = [None if p is None else torch.zeros_like(p) for p in ps]
+        sinks = [grad_sink(r) for r in ctx.refs]
+        direct = all(s is not None or p is None for s, p in zip(sinks, ps))
+        grads = sinks if direct else [None if p is None else torch.zeros_like(p) for p in ps]
         ag = AttnGrads()
         for n, g in zip(_ATTN_NAMES, grads):
             setattr(ag, n, _p(g))
@@ -179,10 +194,10 @@ class WindowAttention(torch.autograd.Function):
         dx = torch.empty_like(x, memory_format=CL)
         dy = torch.empty_like(x, memory_format=CL)
         with timed("rss_attn_bwd"):
-            check(lib.rss_attn_bwd(_p(dout), _p(x), _p(y), ctypes.byref(ap), B, H, W, _dt(x), ctx.flags, _p(xn), _p(yn),
+            check(lib.rss_attn_bwd(_p(dout), _p(x), _p(y), ctypes.byref(ap), B, H, W, _dt(x), ctx.flags,
                                    _p(ln_stats), _p(pooled), _p(amax), _p(smap), _p(gmap), _p(ws), wsb, _p(dx), _p(dy),
                                    ctypes.byref(ag), _st()), "rss_attn_bwd")
-        return (dx, dy, None, None) + tuple(grads)
+        return (dx, dy, None, None) + ((None,) * len(ps) if direct else tuple(grads))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -226,6 +241,7 @@ class BNAct(torch.autograd.Function):
         check(lib.rss_bn_act_fwd(_p(x), _p(residual), _p(y), _p(aff[2]), _p(aff[3]), rows, C, act, dt, st), "rss_bn_act_fwd")
         ctx.save_for_backward(x, y if act == _lib.ACT_RELU else None, aff)
         ctx.act, ctx.training, ctx.group, ctx.world, ctx.has_res = act, training, group, world, residual is not None
+        ctx.refs = (gamma, beta)
         return y
 
     @staticmethod
@@ -241,11 +257,11 @@ class BNAct(torch.autograd.Function):
         sums = torch.empty(2 * C, device=x.device, dtype=torch.float32)
         check(lib.rss_bn_bwd_reduce(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(sums),
                                     rows, C, ctx.act, dt, st), "rss_bn_bwd_reduce")
-        dbeta, dgamma = sums[:C], sums[C:]
+        local = sums
         if ctx.training:
             red = sums
-            if ctx.world > 1:
-                dbeta, dgamma = dbeta.clone(), dgamma.clone()
+            if ctx.world > 1:       # SyncBN: dx needs the global sums, the parameter gradients the local ones (DDP averages them)
+                local = sums.clone()
                 dist.all_reduce(red, group=None if ctx.group is True else ctx.group)
             inv_count = 1.0 / (rows * ctx.world)
         else:                       # eval-mode BN is a fixed affine map: no batch-statistic terms
@@ -253,9 +269,14 @@ class BNAct(torch.autograd.Function):
             inv_count = 0.0
         dx = torch.empty_like(x, memory_format=CL)
         dres = torch.empty_like(x, memory_format=CL) if ctx.has_res else None
+        sg, sb = grad_sink(ctx.refs[0]), grad_sink(ctx.refs[1])
+        direct = sg is not None and sb is not None
         check(lib.rss_bn_bwd_apply(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(red), inv_count,
-                                   _p(dx), _p(dres), rows, C, ctx.act, dt, st), "rss_bn_bwd_apply")
-        return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None
+                                   _p(dx), _p(dres), rows, C, ctx.act, dt, _p(local), _p(sg) if direct else None,
+                                   _p(sb) if direct else None, st), "rss_bn_bwd_apply")
+        if direct:
+            return dx, dres, None, None, None, None, None, None, None, None, None
+        return dx, dres, local[C:], local[:C], None, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -310,6 +331,7 @@ class HeadConv(torch.autograd.Function):
         check(lib.rss_head_fwd(_p(x), _p(wt), _p(_f32(bias)), _p(logits), B * h * w, C, _dt(x), _st()), "rss_head_fwd")
         ctx.save_for_backward(x, wt)
         ctx.wshape = tuple(weight.shape)
+        ctx.refs = (weight, bias)
         return logits
 
     @staticmethod
@@ -319,10 +341,12 @@ class HeadConv(torch.autograd.Function):
         B, C, h, w = x.shape
         dlogits = dlogits.contiguous()
         dx = torch.empty_like(x, memory_format=CL)
-        dw = torch.zeros(7, C, device=x.device, dtype=torch.float32)
-        db = torch.zeros(7, device=x.device, dtype=torch.float32)
+        sw, sb = grad_sink(ctx.refs[0]), grad_sink(ctx.refs[1])
+        direct = sw is not None and sb is not None
+        dw = sw if direct else torch.zeros(7, C, device=x.device, dtype=torch.float32)
+        db = sb if direct else torch.zeros(7, device=x.device, dtype=torch.float32)
         check(lib.rss_head_bwd(_p(x), _p(dlogits), _p(wt), _p(dx), _p(dw), _p(db), B * h * w, C, _dt(x), _st()), "rss_head_bwd")
-        return dx, dw.reshape(ctx.wshape), db
+        return (dx, None, None) if direct else (dx, dw.reshape(ctx.wshape), db)
 
 
 def head_probs(logits_lr, scale, want_argmax=False):
@@ -387,7 +411,6 @@ def grad_sumsq(flat_grad, grad_scale, out):
     check(_lib.load().rss_grad_sumsq(_p(flat_grad), flat_grad.numel(), grad_scale, _p(out), _st()), "rss_grad_sumsq")
 
 
-def sgd_step(flat_p, flat_g, flat_m, sumsq, grad_scale, max_norm, lr, momentum, weight_decay, first_step, zero_grad,
-             shadow=None):
-    check(_lib.load().rss_sgd_step(_p(flat_p), _p(flat_g), _p(flat_m), flat_p.numel(), _p(sumsq), grad_scale, max_norm, lr,
-                                   momentum, weight_decay, int(first_step), int(zero_grad), _p(shadow), _st()), "rss_sgd_step")
+def sgd_step(flat_p, flat_g, flat_m, sumsq, grad_scale, max_norm, lr_dev, momentum, weight_decay, zero_grad, shadow=None):
+    check(_lib.load().rss_sgd_step(_p(flat_p), _p(flat_g), _p(flat_m), flat_p.numel(), _p(sumsq), grad_scale, max_norm, _p(lr_dev),
+                                   momentum, weight_decay, int(zero_grad), _p(shadow), _st()), "rss_sgd_step")

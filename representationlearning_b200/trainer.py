@@ -45,6 +45,8 @@ class FlatSGD:
         self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
         self.shadow = torch.zeros(total, device=dev, dtype=torch.bfloat16) if bf16_shadow else None
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.lr_dev = torch.zeros(1, device=dev, dtype=torch.float32)     # poly LR lives on the device (graph-replay safe)
+        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(1)
         for p, o in zip(self.params, offs):
             n = p.numel()
             self.flat_p[o:o + n].copy_(p.data.reshape(-1))
@@ -55,6 +57,9 @@ class FlatSGD:
         if self.shadow is not None:
             self.shadow.copy_(self.flat_p)
         self.iteration = 0
+        from .modules import FusedBNAct
+        self._bn_counters = [m.num_batches_tracked for m in model.modules() if isinstance(m, FusedBNAct)]
+        FusedBNAct.defer_counter = True
 
     def lr(self):
         return poly_lr(self.iteration, self.hp["base_lr"], self.hp["power"], self.hp["max_iters"])
@@ -74,22 +79,73 @@ class FlatSGD:
             return 1.0 / dist.get_world_size(group)
         return 1.0
 
-    def step(self, grad_scale=1.0):
+    def push_lr(self):
+        """host side of the schedule: write lr(iteration) into the device scalar (async, pinned)"""
+        self._lr_host[0] = self.lr()
+        self.lr_dev.copy_(self._lr_host, non_blocking=True)
+
+    def device_step(self, grad_scale=1.0):
+        """the two optimiser kernels only (capturable); the caller handles push_lr()/iteration"""
         hp = self.hp
         ops.grad_sumsq(self.flat_g, grad_scale, self.sumsq)
-        ops.sgd_step(self.flat_p, self.flat_g, self.flat_m, self.sumsq, grad_scale, hp["max_norm"], self.lr(), hp["momentum"],
-                     hp["weight_decay"], self.iteration == 0, True, self.shadow)
+        ops.sgd_step(self.flat_p, self.flat_g, self.flat_m, self.sumsq, grad_scale, hp["max_norm"], self.lr_dev, hp["momentum"],
+                     hp["weight_decay"], True, self.shadow)
+        if self._bn_counters and self.model.training:
+            torch._foreach_add_(self._bn_counters, 1)       # num_batches_tracked of all 330 BN layers in one multi-tensor op
+
+    def step(self, grad_scale=1.0):
+        self.push_lr()
+        self.device_step(grad_scale)
         self.iteration += 1
 
     def grad_norm(self):
         return float(self.sumsq.sqrt().item())
 
 
-def train_step(model, opt, img, labels, group=None):
-    """forward + loss + backward + gradient all-reduce + clip + SGD.  Returns the loss tensor (device, no sync)."""
+def _device_train_step(model, opt, img, labels, group=None):
     losses = model(img, {"cls": labels})
     loss = sum(losses.values())
     loss.backward()
     scale = opt.all_reduce_grads(group)
-    opt.step(scale)
+    opt.device_step(scale)
     return loss.detach()
+
+
+def train_step(model, opt, img, labels, group=None):
+    """forward + loss + backward + gradient all-reduce + clip + SGD.  Returns the loss tensor (device, no sync)."""
+    opt.push_lr()
+    loss = _device_train_step(model, opt, img, labels, group)
+    opt.iteration += 1
+    return loss
+
+
+class GraphedTrainStep:
+    """The whole training step captured ONCE in a CUDA graph and replayed: ~13 k kernel launches per step are
+    launch-latency bound when issued from Python, and every shape in the step is static.  Inputs are copied into
+    static device buffers; the poly LR is a device scalar refreshed by the host before each replay."""
+
+    def __init__(self, model, opt, img, labels, group=None, warmup=3):
+        self.model, self.opt, self.group = model, opt, group
+        self.img = img.clone()
+        self.labels = labels.clone()
+        side = torch.cuda.Stream(img.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                     # eager warm-up (also performs one-time kernel attribute setup)
+                train_step(model, opt, self.img, self.labels, group)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        opt.push_lr()
+        with torch.cuda.graph(self.graph):
+            self.loss = _device_train_step(model, opt, self.img, self.labels, group)   # capture records, does not run
+
+    def load(self, img, labels, non_blocking=True):
+        self.img.copy_(img, non_blocking=non_blocking)
+        self.labels.copy_(labels, non_blocking=non_blocking)
+
+    def __call__(self):
+        self.opt.push_lr()
+        self.graph.replay()
+        self.opt.iteration += 1
+        return self.loss

@@ -37,4 +37,4 @@ def pytest_sessionfinish(session, exitstatus):
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
     with open(os.path.join(out, "parity_report.json"), "w") as f:
-        json.dump(REPORT, f, indent=1, sort_keys=True)
+        json.dump(REPORT, f, indent=1, sort_keys=True, default=float)

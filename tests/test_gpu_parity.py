@@ -69,6 +69,12 @@ def test_bn_act(P, report, dtype, act, shape, res):
     from representationlearning_b200 import ops
     torch.manual_seed(2)
     B, C, H, W = shape
+    if act == 2 and res:      # not a pattern of the reference: the ABI must refuse it, loudly
+        z = torch.zeros(shape, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+        with pytest.raises(P._lib.RssError):
+            ops.BNAct.apply(z, z, torch.ones(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV),
+                            torch.ones(C, device=DEV), True, 0.1, 1e-5, act, None)
+        return
     x = (torch.randn(shape) * 2 + 0.5).to(dtype).float()
     r = torch.randn(shape).to(dtype).float() if res else None
     g, b = torch.rand(C) + 0.5, torch.randn(C) * 0.2
@@ -298,9 +304,14 @@ def test_model_S64_vs_reference_golden_fp32(P, report):
     loss.backward()
     errs["loss"] = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
     named = dict(m.named_parameters())
+    # gradients of a 140-layer net with training-mode BN over as few as 8 samples (B=2, 2x2 at the coarsest branch)
+    # are ill-conditioned in fp32: the REFERENCE's own fp32 run deviates from its fp64 run by `fp32dev.*` (recorded by
+    # gen_golden.py, up to 2e-2).  The CUDA path is held to 3x that envelope (and to TOL_F32 where the envelope is tighter).
+    env = {}
     for k in g.files:
         if k.startswith("grad."):
             errs[k] = rel(named[k[5:]].grad, g[k])
+            env[k] = max(TOL_F32, 3.0 * float(g["fp32dev." + k[5:]]))
         if k.startswith("stat."):
             errs[k] = rel(m.state_dict()[k[5:]], g[k])
     worst = 0.0
@@ -308,10 +319,11 @@ def test_model_S64_vs_reference_golden_fp32(P, report):
         if n > 1e-12:
             worst = max(worst, abs(named[k].grad.norm().item() - n) / max(n, 1e-3 * max(gn.values())))
     errs["gradnorm_worst"] = worst
+    env["gradnorm_worst"] = 3.0 * float(g["fp32dev_gradnorm_worst"])
     assert named["headaux.0.weight"].grad is None
     report["model_S64_fp32"] = errs
-    bad = {k: v for k, v in errs.items() if not v < (5 * TOL_F32 if k.startswith("grad") else TOL_F32) and k != "argmax_mismatch"}
-    assert not bad and errs["argmax_mismatch"] < 1e-3, (bad, errs["argmax_mismatch"])
+    bad = {k: (v, env.get(k, TOL_F32)) for k, v in errs.items() if not v < env.get(k, TOL_F32) and k != "argmax_mismatch"}
+    assert not bad and errs["argmax_mismatch"] == 0.0, (bad, errs["argmax_mismatch"])
 
 
 def test_model_S64_bf16_agreement(P, report):
@@ -401,3 +413,48 @@ def test_full_size_block_properties(P, report):
     lin = max(rel(g2[0].float(), 2 * g1[0].float()), rel(g2[1].float(), 2 * g1[1].float()))
     report["full_size_block"] = dict(bwd_linearity=lin)
     assert lin < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 / TMA implicit-GEMM convolution vs torch conv on the same bf16-representable inputs
+# (products exact, fp32 accumulation on both sides -> TOL_F32 applies; the bf16 output rounding adds 2^-9)
+# ------------------------------------------------------------------------------------------------
+IGEMM_CASES = [
+    # B, H, W, Cin, Cout, [(k, dil), ...]
+    (2, 16, 16, 128, 32, [(1, 1)]),
+    (1, 32, 32, 64, 64, [(3, 1)]),
+    (2, 128, 128, 128, 128, [(1, 1), (3, 6), (3, 12)]),
+    (1, 16, 16, 32, 128, [(1, 1)]),
+    (1, 16, 16, 480, 480, [(1, 1)]),
+    (3, 8, 8, 256, 256, [(3, 1)]),
+    (1, 128, 128, 32, 32, [(3, 1)]),
+    (2, 64, 64, 64, 64, [(3, 1)]),
+]
+
+
+@pytest.mark.parametrize("case", IGEMM_CASES)
+def test_conv_igemm_fwd_and_dgrad(P, report, case):
+    from representationlearning_b200 import conv
+    B, H, W, Cin, Cout, srcs = case
+    torch.manual_seed(11)
+    x = torch.randn(B, Cin, H, W).bfloat16().float()
+    ws = [(torch.randn(Cout, Cin, k, k) / (Cin * k * k) ** 0.5).bfloat16().float() for k, d in srcs]
+    bs = [torch.randn(Cout) for _ in srcs]
+    dy = torch.randn(B, Cout, H, W).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    ref = sum(torch.nn.functional.conv2d(xr, w, b, 1, d * (k // 2), d) for w, b, (k, d) in zip(ws, bs, srcs))
+    ref.backward(dy)
+    conv.ENGINE["igemm"] = True
+    try:
+        xc = nchw_from(x.bfloat16()).requires_grad_(True)
+        wc = [torch.nn.Parameter(w.to(DEV)) for w in ws]
+        bc = [torch.nn.Parameter(b.to(DEV)) for b in bs]
+        out = conv.conv_sum(xc, [(w, b, k, d) for w, b, (k, d) in zip(wc, bc, srcs)])
+        assert out.dtype == torch.bfloat16
+        out.backward(nchw_from(dy.bfloat16()))
+        torch.cuda.synchronize()
+    finally:
+        conv.ENGINE["igemm"] = False
+    errs = dict(out=rel(out.float(), ref), dx=rel(xc.grad.float(), xr.grad))
+    report["igemm_%s" % "_".join(map(str, case[:5])) + "_t%d" % sum(k * k for k, d in srcs)] = errs
+    assert max(errs.values()) < 6e-3, errs       # bf16 output rounding (2^-9 = 2e-3 of max) dominates
