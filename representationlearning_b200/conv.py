@@ -14,23 +14,19 @@ import torch
 from . import _lib, ops
 
 CL = torch.channels_last
-_SHADOW = {}          # id(param) -> bf16 view kept fresh by the fused optimiser step (trainer.py)
 ENGINE = {"igemm": False}
 
 
 def register_shadow(param, view):
-    _SHADOW[id(param)] = view
-
-
-def clear_shadows():
-    _SHADOW.clear()
+    """attach the bf16 view kept fresh by the fused optimiser step (trainer.py) to its fp32 master parameter"""
+    param._rss_shadow = view
 
 
 def _lowp(w, dtype):
     if w is None or w.dtype == dtype:
         return w
-    s = _SHADOW.get(id(w))
-    if s is not None and s.dtype == dtype:
+    s = getattr(w, "_rss_shadow", None)
+    if s is not None and s.dtype == dtype and s.numel() == w.numel():
         return s.view(w.shape)
     return w.detach().to(dtype)
 
