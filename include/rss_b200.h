@@ -86,6 +86,13 @@ int rss_attn_bwd(const void* dout, const void* x, const void* y, const rss_attn_
 int rss_bn_stats_nparts(int64_t rows, int C);          /* number of partials rss_bn_stats writes */
 int rss_bn_stats(const void* x, float* partials /*[nparts][C][2] (mean,M2)*/, float* counts /*[nparts]*/,
                  int64_t rows, int C, int dtype, cudaStream_t stream);
+/* single-GPU path: statistics + finalize in ONE launch.  accum_scratch: persistent float[2*C] (>= 4096 floats recommended),
+ * ticket: persistent uint; both zero before the first call and left zero by every call; calls sharing them must be
+ * stream-ordered.  The running mean (if given) is used as the shift of the one-pass variance. */
+int rss_bn_stats_fused(const void* x, float* accum_scratch, unsigned int* ticket, int64_t rows, int C, int dtype,
+                       const float* gamma, const float* beta, float* running_mean /*may be NULL*/, float* running_var,
+                       float momentum, float eps, float* mean_out, float* invstd_out, float* scale, float* shift,
+                       cudaStream_t stream);
 int rss_bn_combine(const float* partials, const float* counts, int nparts, int C, float* stat /*[C][2]*/, float* total /*[1]*/,
                    cudaStream_t stream);
 int rss_bn_finalize(const float* stat, const float* total, const float* gamma, const float* beta,

@@ -45,6 +45,7 @@ SIGNATURES = {
                              P, P, POINTER(AttnGrads), P]),
     "rss_bn_stats_nparts": (c_int, [c_int64, c_int]),
     "rss_bn_stats": (c_int, [P, P, P, c_int64, c_int, c_int, P]),
+    "rss_bn_stats_fused": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P, c_float, c_float, P, P, P, P, P]),
     "rss_bn_combine": (c_int, [P, P, c_int, c_int, P, P, P]),
     "rss_bn_finalize": (c_int, [P, P, P, P, P, P, c_float, c_float, c_int, P, P, P, P, P]),
     "rss_bn_eval_affine": (c_int, [P, P, P, P, c_float, c_int, P, P, P, P, P]),

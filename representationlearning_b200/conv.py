@@ -14,7 +14,9 @@ import torch
 from . import _lib, ops
 
 CL = torch.channels_last
-ENGINE = {"igemm": False}
+# per-shape engine policy from tools/conv_microbench.py (profiles/conv_microbench_r1.json): the igemm kernel runs the
+# FFN's fused 17-tap conv (forward + data gradient); single convs stay on the library until the halo-reuse version lands.
+ENGINE = {"igemm": True, "igemm_single": False}       # bf16 stride-1 convs go through csrc/conv_igemm.cu when the geometry is supported
 
 
 def register_shadow(param, view):
@@ -180,6 +182,7 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, bias_grad=True
     subtraction cancels any per-channel shift; the reference computes ~1e-18 round-off there), so the (B*H*W)-long
     reduction is skipped."""
     k = weight.shape[2]
-    if stride == 1 and padding == dilation * (k // 2) and k in (1, 3) and _igemm_ok(x, weight.shape[0]):
+    if ENGINE.get("igemm_single", False) and stride == 1 and padding == dilation * (k // 2) and k in (1, 3) \
+            and _igemm_ok(x, weight.shape[0]):
         return _ConvIgemm.apply(x, ((k,), (dilation,), bias_grad), weight, bias)
     return _ConvLib.apply(x, weight, bias, stride, padding, dilation, bias_grad)

@@ -27,9 +27,8 @@ static inline int bn_grid(int64_t rows, int rpb, int per_sm) {
 
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void bn_stats_kernel(const T* __restrict__ x, float* __restrict__ part /*[grid][C][2]*/,
-                                float* __restrict__ cnt /*[grid]*/, int64_t rows, int C, int cg, int rpb) {
-    extern __shared__ float sm[];           // [rpb][C][3]  (n, mean, M2)
+__device__ __forceinline__ void bn_block_partial(const T* __restrict__ x, float* __restrict__ part /*[grid][C][2]*/,
+                                                 float* __restrict__ cnt /*[grid]*/, int64_t rows, int C, int cg, int rpb, float* sm) {
     const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
     float K[8], s[8], q[8];
     int64_t n = 0;
@@ -76,13 +75,17 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, float* __restrict__ par
     }
 }
 
-// Chan-combine nparts partials -> stat[C][2] = (mean, M2), total[0] = count.  One WARP per channel: lanes take
-// partials p = lane, lane+32, ... and the 32 running (n, mean, M2) triples are merged with a shuffle tree.
-__global__ void bn_combine_kernel(const float* __restrict__ part, const float* __restrict__ cnt, int nparts, int C,
-                                  float* __restrict__ stat, float* __restrict__ total) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= C) return;
-    float na = 0.f, ma = 0.f, qa = 0.f;
+template <typename T>
+__global__ void bn_stats_kernel(const T* __restrict__ x, float* __restrict__ part, float* __restrict__ cnt,
+                                int64_t rows, int C, int cg, int rpb) {
+    extern __shared__ float sm[];           // [rpb][C][3]  (n, mean, M2)
+    bn_block_partial<T>(x, part, cnt, rows, C, cg, rpb, sm);
+}
+
+// Chan-merge of the partials of one channel by one warp (lanes stride over partials, shuffle tree at the end)
+__device__ __forceinline__ void bn_warp_combine(const float* __restrict__ part, const float* __restrict__ cnt, int nparts, int C,
+                                                int c, int lane, float& na, float& ma, float& qa) {
+    na = 0.f; ma = 0.f; qa = 0.f;
     for (int p = lane; p < nparts; p += 32) {
         const float nb = cnt[p];
         if (nb > 0.f) {
@@ -100,13 +103,103 @@ __global__ void bn_combine_kernel(const float* __restrict__ part, const float* _
         const float nn = na + nb;
         if (nn > 0.f) {
             const float d = mb - ma;
-            // symmetric form: both lanes of a pair compute the same merged triple
-            const float m = (na * ma + nb * mb) / nn;
+            const float m = (na * ma + nb * mb) / nn;       // symmetric: both lanes of a pair get the same triple
             qa = qa + qb + d * d * (na * nb / nn);
             ma = m;
             na = nn;
         }
     }
+}
+
+__device__ __forceinline__ void bn_finalize_channel(float n, float mean, float m2, int c, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, float* __restrict__ running_mean,
+                                                    float* __restrict__ running_var, float momentum, float eps,
+                                                    float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                                    float* __restrict__ scale, float* __restrict__ shift) {
+    const float invstd = rsqrtf(m2 / n + eps);                    // biased variance normalises
+    mean_out[c] = mean;
+    invstd_out[c] = invstd;
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    if (running_mean) {
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (m2 / fmaxf(n - 1.f, 1.f));   // unbiased estimate
+    }
+}
+
+// single-GPU training path: statistics and finalize in ONE launch.  Per-channel sums of d = x - K and d^2 (K = the running
+// mean: a shift close to the batch mean keeps E[d^2] - E[d]^2 well conditioned in fp32) are reduced per block and added
+// atomically to a persistent zeroed scratch; the last block to arrive (device-wide ticket) turns them into
+// scale/shift + running statistics and clears the scratch for the next launch on the stream.
+template <typename T>
+__global__ void bn_stats_fused_kernel(const T* __restrict__ x, float* __restrict__ accum /*[2][C] persistent, zero*/,
+                                      unsigned int* __restrict__ ticket, int64_t rows, int C, int cg, int rpb,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
+                                      float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+    extern __shared__ float sm[];               // [rpb][2][C]
+    __shared__ bool is_last;
+    const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
+    float K[8], a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { K[i] = running_mean ? running_mean[sub * 8 + i] : 0.f; a0[i] = 0.f; a1[i] = 0.f; }
+    const int64_t stride = (int64_t)gridDim.x * rpb;
+    int64_t row = (int64_t)blockIdx.x * rpb + r;
+    for (; row + 3 * stride < rows; row += 4 * stride) {          // 4 independent 16-byte loads in flight per thread
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8(x + (row + u * stride) * C + sub * 8, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = v[u][i] - K[i]; a0[i] += d; a1[i] += d * d; }
+    }
+    for (; row < rows; row += stride) {
+        float v[8];
+        load8(x + row * C + sub * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - K[i]; a0[i] += d; a1[i] += d * d; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sm[((size_t)r * 2 + 0) * C + sub * 8 + i] = a0[i];
+        sm[((size_t)r * 2 + 1) * C + sub * 8 + i] = a1[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+        const int which = c / C, ch = c % C;
+        float t = 0.f;
+        for (int rr = 0; rr < rpb; ++rr) t += sm[((size_t)rr * 2 + which) * C + ch];
+        atomicAdd(accum + which * C + ch, t);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const float n = (float)rows;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float S = __ldcg(accum + c), Q = __ldcg(accum + C + c);
+        const float md = S / n;
+        const float m2 = fmaxf(Q - S * md, 0.f);
+        const float k = running_mean ? running_mean[c] : 0.f;
+        bn_finalize_channel(n, k + md, m2, c, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out, scale, shift);
+        accum[c] = 0.f;
+        accum[C + c] = 0.f;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// Chan-combine nparts partials -> stat[C][2] = (mean, M2), total[0] = count.  One WARP per channel.
+__global__ void bn_combine_kernel(const float* __restrict__ part, const float* __restrict__ cnt, int nparts, int C,
+                                  float* __restrict__ stat, float* __restrict__ total) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= C) return;
+    float na, ma, qa;
+    bn_warp_combine(part, cnt, nparts, C, c, lane, na, ma, qa);
     if (lane == 0) {
         stat[c * 2] = ma;
         stat[c * 2 + 1] = qa;
@@ -278,6 +371,19 @@ extern "C" int rss_bn_stats(const void* x, float* partials, float* counts, int64
     const int grid = rss_bn_stats_nparts(rows, C);
     const size_t smem = (size_t)g.rpb * C * 3 * sizeof(float);
     RSS_DISPATCH_DTYPE(dtype, bn_stats_kernel<T><<<grid, g.threads, smem, st>>>((const T*)x, partials, counts, rows, C, g.cg, g.rpb));
+    return check_launch();
+}
+
+extern "C" int rss_bn_stats_fused(const void* x, float* accum_scratch, unsigned int* ticket, int64_t rows, int C, int dtype,
+                                  const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                  float momentum, float eps, float* mean_out, float* invstd_out, float* scale, float* shift,
+                                  cudaStream_t st) {
+    if (C <= 0 || C % 8 || C > 2048 || rows <= 0 || !ticket || !accum_scratch) return RSS_ERR_SHAPE;
+    const BnGeom g = bn_geom(C);
+    const int grid = bn_grid(rows, g.rpb * 8, 4);
+    const size_t smem = (size_t)g.rpb * C * 2 * sizeof(float);
+    RSS_DISPATCH_DTYPE(dtype, bn_stats_fused_kernel<T><<<grid, g.threads, smem, st>>>((const T*)x, accum_scratch, ticket, rows, C, g.cg, g.rpb,
+                       gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out, scale, shift));
     return check_launch();
 }
 

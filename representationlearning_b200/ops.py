@@ -203,6 +203,18 @@ class WindowAttention(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 # BatchNorm(+SyncBN) + activation (+ residual)
 # ----------------------------------------------------------------------------------------------
+_TICKETS = {}
+
+
+def _ticket(dev):
+    """persistent scratch of rss_bn_stats_fused: [0] = last-block ticket, [1:] = per-channel accumulators
+    (zero-initialised once; every call leaves it zero)"""
+    t = _TICKETS.get(dev)
+    if t is None:
+        t = _TICKETS[dev] = torch.zeros(1 + 4096, device=dev, dtype=torch.float32)
+    return t
+
+
 class BNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, residual, gamma, beta, running_mean, running_var, training, momentum, eps, act, group):
@@ -219,7 +231,12 @@ class BNAct(torch.autograd.Function):
         g, b = _f32(gamma), _f32(beta)
         aff = torch.empty(4, C, device=dev, dtype=torch.float32)      # mean, invstd, scale, shift
         world = _world(group) if training else 1
-        if training:
+        if training and world == 1:
+            scratch = _ticket(dev)
+            check(lib.rss_bn_stats_fused(_p(x), _p(scratch[1:]), _p(scratch), rows, C, dt, _p(g), _p(b),
+                                         _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
+                                         _p(aff[3]), st), "rss_bn_stats_fused")
+        elif training:
             nparts = lib.rss_bn_stats_nparts(rows, C)
             part = torch.empty(nparts * C * 2 + nparts, device=dev, dtype=torch.float32)
             cnt = part[nparts * C * 2:]

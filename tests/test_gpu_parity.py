@@ -447,7 +447,8 @@ def test_conv_igemm_fwd_and_dgrad(P, report, case):
     xr = x.clone().requires_grad_(True)
     ref = sum(torch.nn.functional.conv2d(xr, w, b, 1, d * (k // 2), d) for w, b, (k, d) in zip(ws, bs, srcs))
     ref.backward(dy)
-    conv.ENGINE["igemm"] = True
+    saved = dict(conv.ENGINE)
+    conv.ENGINE.update(igemm=True, igemm_single=True)
     try:
         xc = nchw_from(x.bfloat16()).requires_grad_(True)
         wc = [torch.nn.Parameter(w.to(DEV)) for w in ws]
@@ -457,7 +458,7 @@ def test_conv_igemm_fwd_and_dgrad(P, report, case):
         out.backward(nchw_from(dy.bfloat16()))
         torch.cuda.synchronize()
     finally:
-        conv.ENGINE["igemm"] = False
+        conv.ENGINE.update(saved)
     errs = dict(out=rel(out.float(), ref), dx=rel(xc.grad.float(), xr.grad))
     report["igemm_%s" % "_".join(map(str, case[:5])) + "_t%d" % sum(k * k for k, d in srcs)] = errs
     assert max(errs.values()) < 6e-3, errs       # bf16 output rounding (2^-9 = 2e-3 of max) dominates
