@@ -125,6 +125,12 @@ def main():
             "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
+    if os.environ.get("RSS_FAULTHANDLER"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["RSS_FAULTHANDLER"]), exit=True)
+    # keep stdout clean for the ONE JSON line (NCCL/torch may print banners): everything else goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import representationlearning_b200 as P
@@ -140,6 +146,10 @@ def main():
     model = P.build_rssformer(compute_dtype=torch.bfloat16, device=dev)
     model.load_state_dict(R.synth_state_dict(2333))
     model.train()
+    if os.environ.get("RSS_NO_SYNCBN"):
+        for mod in model.modules():
+            if isinstance(mod, P.FusedBNAct):
+                mod.sync = False
     opt = P.FlatSGD(model)
     B, S = args.batch, args.size
     img_h, lbl_h = R.synth_batch(B, S, seed_img=7 + rank, seed_lbl=1 + rank)
@@ -183,6 +193,8 @@ def main():
     kn = {k: len(v) for k, v in ops.TIMED.items() if v}
 
     # ---- the timed region: the whole step captured once as a CUDA graph, replayed K times -------------------
+    if world > 1 and os.environ.get("RSS_GRAPH_DDP", "1") == "0":
+        args.no_graph = True
     if args.no_graph:
         run_step = step_eager
     else:
@@ -200,7 +212,7 @@ def main():
     launches = launches_per_step * args.steps
     value = world * B * args.steps / (ms / 1e3)
     if args.profile:
-        print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "region_ms": kt, "gpu_launches": launches}))
+        os.write(json_fd, (json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "region_ms": kt, "gpu_launches": launches}) + "\n").encode())
         return 0
 
     # ---- end to end: pinned host -> device every step (staged on a copy stream, overlapped), loss read back ---
@@ -272,9 +284,13 @@ def main():
         r = cpu_reference_run(args.cpu_baseline_steps, 1, 1, S)
         out["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     if rank == 0:
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
-        dist.destroy_process_group()
+        # destroy_process_group() can block while captured graphs still reference the communicator: synchronise and leave
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

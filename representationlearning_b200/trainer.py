@@ -137,7 +137,8 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         opt.push_lr()
-        with torch.cuda.graph(self.graph):
+        # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures (DDP all-reduce / SyncBN inside the graph)
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.loss = _device_train_step(model, opt, self.img, self.labels, group)   # capture records, does not run
 
     def load(self, img, labels, non_blocking=True):
