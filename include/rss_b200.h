@@ -102,7 +102,8 @@ int rss_bn_eval_affine(const float* gamma, const float* beta, const float* runni
                        float eps, int C, float* mean_out, float* invstd_out, float* scale, float* shift, cudaStream_t stream);
 int rss_bn_act_fwd(const void* x, const void* residual /*may be NULL*/, void* y, const float* scale, const float* shift,
                    int64_t rows, int C, int act, int dtype, cudaStream_t stream);
-/* sums[0..C) = sum dz, sums[C..2C) = sum dz*xhat with dz = dy*act'(.) (== dbeta, dgamma). y is needed for RELU only. */
+/* sums[0..C) = sum dz, sums[C..2C) = sum dz*xhat with dz = dy*act'(.) (== dbeta, dgamma).  y (the saved output) is needed only
+ * for RELU layers that had a residual; with y == NULL the ReLU mask is recomputed from x*scale+shift. */
 int rss_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
                       const float* mean, const float* invstd, float* sums, int64_t rows, int C, int act, int dtype,
                       cudaStream_t stream);
@@ -111,6 +112,14 @@ int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, const float* 
                      void* dx, void* dresidual /*may be NULL: receives dz*/, int64_t rows, int C, int act, int dtype,
                      const float* local_sums /*this rank's sums (== sums without SyncBN)*/,
                      float* dgamma_acc /*may be NULL*/, float* dbeta_acc, cudaStream_t stream);
+
+/* ---- multi-resolution fuse sum of HighResolutionModule.forward (_hrnet_rssformer.py:418-435) and the residual+ReLU closing a
+ *      transformer block (MTFM.py:109, _hrnet_rssformer.py:435): out = [relu](sum_j nearest_up_{2^k_j}(term_j)), NHWC ---- */
+int rss_fuse_sum_fwd(const void* const* terms, const int* log2_up, int n_terms /*1..4*/, void* out, int B, int H, int W, int C,
+                     int relu, int dtype, cudaStream_t stream);
+/* gradient of ONE term: block-sum over its 2^k x 2^k footprint of dout * [out > 0 if relu] */
+int rss_fuse_sum_bwd(const void* dout, const void* out /*needed if relu*/, void* dterm, int log2_up, int B, int H, int W, int C,
+                     int relu, int dtype, cudaStream_t stream);
 
 /* ---- tcgen05/TMA implicit-GEMM convolution (stride 1, "same" padding, NHWC bf16, fp32 TMEM accumulation):
  *      the FFN's dw(1x1)+dw6(3x3,d6)+dw12(3x3,d12) summed convs as ONE 17-tap GEMM (ffn_block.py:226-228,250-257),

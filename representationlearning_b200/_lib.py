@@ -52,6 +52,8 @@ SIGNATURES = {
     "rss_bn_act_fwd": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
     "rss_bn_bwd_reduce": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
     "rss_bn_bwd_apply": (c_int, [P, P, P, P, P, P, P, P, c_float, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
+    "rss_fuse_sum_fwd": (c_int, [POINTER(c_void_p), POINTER(c_int), c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "rss_fuse_sum_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "rss_conv_igemm_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "rss_conv_packed_bytes": (c_size_t, [c_int, POINTER(c_int), c_int, c_int]),
     "rss_conv_pack_weights": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int,

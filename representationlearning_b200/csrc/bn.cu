@@ -282,10 +282,15 @@ __device__ __forceinline__ void bn_dz(const T* __restrict__ x, const T* __restri
 #pragma unroll
     for (int i = 0; i < 8; ++i) xh[i] = (v[i] - mu[i]) * is[i];
     if (ACT == 1) {
-        float o[8];
-        load8(y + off, o);
+        if (y) {                 // residual layers: the mask needs the saved output
+            float o[8];
+            load8(y + off, o);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dz[i] = o[i] > 0.f ? dz[i] : 0.f;
+            for (int i = 0; i < 8; ++i) dz[i] = o[i] > 0.f ? dz[i] : 0.f;
+        } else {                 // no residual: relu'(z) recomputed from x, one tensor read less
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dz[i] = (v[i] * sc[i] + sh[i]) > 0.f ? dz[i] : 0.f;
+        }
     }
     if (ACT == 2) {
 #pragma unroll
@@ -432,7 +437,6 @@ extern "C" int rss_bn_bwd_reduce(const void* x, const void* y, const void* dy, c
                                  const float* mean, const float* invstd, float* sums, int64_t rows, int C, int act, int dtype,
                                  cudaStream_t st) {
     if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
-    if (act == RSS_ACT_RELU && !y) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 8, 4);
     const size_t smem = (size_t)g.rpb * 2 * C * sizeof(float);
@@ -447,7 +451,7 @@ extern "C" int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, co
                                 void* dx, void* dres, int64_t rows, int C, int act, int dtype,
                                 const float* local_sums, float* dgamma_acc, float* dbeta_acc, cudaStream_t st) {
     if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
-    if (act == RSS_ACT_RELU && !y) return RSS_ERR_SHAPE;
+    if (act == RSS_ACT_RELU && dres && !y) return RSS_ERR_SHAPE;     // residual layers must pass the saved output
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 4, 8);
     RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,

@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib
+from . import _lib, ops
 from .conv import conv2d
 from .modules import FusedBNAct, GeneralTransformerBlock, BN_MOMENTUM
 
@@ -134,12 +134,13 @@ class HighResolutionModule(nn.Module):
         return self.num_inchannels
 
     def _fuse(self, i, j, x):
+        """fuse branch j into resolution i: returns (term, log2 of the nearest up-sampling still to apply)"""
         layer = self.fuse_layers[i][j]
         if j > i:
-            return layer[2](_run(layer[0], layer[1], x))
+            return _run(layer[0], layer[1], x), j - i          # the x2^(j-i) nearest up-sampling is fused into the sum kernel
         for seq in layer:
             x = _run(seq[0], seq[1], x)
-        return x
+        return x, 0
 
     def forward(self, x):
         if self.num_branches == 1:
@@ -147,15 +148,15 @@ class HighResolutionModule(nn.Module):
         x = [self.branches[i](x[i]) for i in range(self.num_branches)]
         x_fuse = []
         for i in range(len(self.fuse_layers)):
-            low = None
-            for j in range(1, self.num_branches):
-                term = x[j] if i == j else self._fuse(i, j, x[j])
-                low = term if low is None else low + term
+            terms, ks = [], []
+            for j in range(0 if i > 0 else 1, self.num_branches):
+                t, k = (x[j], 0) if i == j else self._fuse(i, j, x[j])
+                terms.append(t); ks.append(k)
             if i == 0:
-                y = self.transformer(low, x[0])              # (:430-431) x[0] enters only as keys/values
+                low = ops.fuse_sum(terms, ks, relu=False)
+                x_fuse.append(self.transformer(low, x[0], relu=True))   # (:430-431,435) x[0] enters only as keys/values
             else:
-                y = self._fuse(i, 0, x[0]) + low
-            x_fuse.append(F.relu(y))
+                x_fuse.append(ops.fuse_sum(terms, ks, relu=True))      # (:433,435)
         return x_fuse
 
 

@@ -156,13 +156,15 @@ class GeneralTransformerBlock(nn.Module):
         self.mlp = MlpDWBN(in_features=self.dim, hidden_features=int(self.dim * mlp_ratio), out_features=self.out_dim,
                            act_layer=act_layer, dw_act_layer=act_layer, drop=drop)
 
-    def forward(self, x, y, mask=None):
+    def forward(self, x, y, mask=None, relu=False):
+        """relu=True additionally applies the ReLU that HighResolutionModule puts on the block output
+        (_hrnet_rssformer.py:435), fused with the residual add."""
         # attention half: LN1(x), LN1(y), gate, window attention, + x  — one fused region
         t = ops.WindowAttention.apply(x, y, self.norm1.eps, True, self.norm1.weight, self.norm1.bias,
                                       *self.attn.gate_params(), *self.attn.attn.proj_params())
-        # FFN half: LN2 -> MlpDWBN -> + t
+        # FFN half: LN2 -> MlpDWBN -> + t (-> ReLU)
         u = ops.LayerNormNHWC.apply(t, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        return t + self.mlp.forward_nchw(u)
+        return ops.fuse_sum([t, self.mlp.forward_nchw(u)], [0, 0], relu)
 
     def extra_repr(self):
         return "num_heads={}, window_size={}, mlp_ratio={}".format(self.num_heads, self.window_size, self.mlp_ratio)

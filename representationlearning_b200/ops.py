@@ -20,7 +20,7 @@ KERNELS_PER_CALL = {
     "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1,
     "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 4, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
     "rss_headaux_fwd": 2, "rss_seg_loss_fwd": 2, "rss_seg_loss_bwd": 1, "rss_grad_sumsq": 1, "rss_sgd_step": 1,
-    "rss_conv_igemm": 1, "rss_conv_pack_weights": 1,
+    "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
 }
 COUNTERS = {"launches": 0, "calls": 0}
 TIMED = {}            # op name -> list of (start_event, end_event), filled only while bench.py enables it
@@ -256,7 +256,7 @@ class BNAct(torch.autograd.Function):
                                          _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), st), "rss_bn_eval_affine")
         y = torch.empty_like(x, memory_format=CL)
         check(lib.rss_bn_act_fwd(_p(x), _p(residual), _p(y), _p(aff[2]), _p(aff[3]), rows, C, act, dt, st), "rss_bn_act_fwd")
-        ctx.save_for_backward(x, y if act == _lib.ACT_RELU else None, aff)
+        ctx.save_for_backward(x, y if (act == _lib.ACT_RELU and residual is not None) else None, aff)
         ctx.act, ctx.training, ctx.group, ctx.world, ctx.has_res = act, training, group, world, residual is not None
         ctx.refs = (gamma, beta)
         return y
@@ -294,6 +294,61 @@ class BNAct(torch.autograd.Function):
         if direct:
             return dx, dres, None, None, None, None, None, None, None, None, None
         return dx, dres, local[C:], local[:C], None, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# multi-resolution fuse sum (+ReLU)
+# ----------------------------------------------------------------------------------------------
+class FuseSum(torch.autograd.Function):
+    """out = [relu](sum_j nearest_up_{2^k_j}(term_j)); term j has spatial size (H >> k_j, W >> k_j)."""
+
+    @staticmethod
+    def forward(ctx, relu, ks, *terms):
+        _lib.require_device()
+        lib = _lib.load()
+        terms = [nhwc(t) for t in terms]
+        dt0 = terms[0].dtype
+        terms = [t if t.dtype == dt0 else t.to(dt0) for t in terms]
+        n = len(terms)
+        B, C, h0, w0 = terms[0].shape
+        H, W = h0 << ks[0], w0 << ks[0]
+        out = torch.empty((B, C, H, W), device=terms[0].device, dtype=dt0, memory_format=CL)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in terms])
+        kk = (ctypes.c_int * n)(*ks)
+        check(lib.rss_fuse_sum_fwd(ptrs, kk, n, _p(out), B, H, W, C, int(relu), _dt(out), _st()), "rss_fuse_sum_fwd")
+        ctx.save_for_backward(out if relu else None)
+        ctx.cfg = (relu, ks, [tuple(t.shape) for t in terms])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        (out,) = ctx.saved_tensors
+        relu, ks, shapes = ctx.cfg
+        dout = nhwc(dout)
+        B, C, H, W = dout.shape
+        grads = []
+        shared = None
+        for j, (k, shp) in enumerate(zip(ks, shapes)):
+            if not ctx.needs_input_grad[2 + j]:
+                grads.append(None)
+                continue
+            if k == 0 and not relu:
+                grads.append(dout)               # identity term of an un-activated sum: the gradient passes through
+                continue
+            if k == 0 and shared is not None:
+                grads.append(shared)             # all full-resolution terms share the same masked gradient
+                continue
+            d = torch.empty(shp, device=dout.device, dtype=dout.dtype, memory_format=CL)
+            check(lib.rss_fuse_sum_bwd(_p(dout), _p(out), _p(d), k, B, H, W, C, int(relu), _dt(dout), _st()), "rss_fuse_sum_bwd")
+            if k == 0:
+                shared = d
+            grads.append(d)
+        return (None, None) + tuple(grads)
+
+
+def fuse_sum(terms, ks, relu):
+    return FuseSum.apply(bool(relu), tuple(int(k) for k in ks), *terms)
 
 
 # ----------------------------------------------------------------------------------------------
