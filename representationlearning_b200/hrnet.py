@@ -4,6 +4,8 @@ Mirror of RSSFormer-TIP2023/module/baseline/base_hrnet/_hrnet_rssformer.py (clas
 signatures and state_dict keys preserved; file:line cited per class).  Every conv -> BN -> ReLU
 (+ residual) chain runs as  conv kernel -> fused BN-statistics -> one fused apply pass.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -20,6 +22,17 @@ MODEL_EXTRA = {
         stage3=dict(num_modules=4, num_branches=3, block="BASIC", num_blocks=(4, 4, 4), num_channels=(32, 64, 128), fuse_method="SUM"),
         stage4=dict(num_modules=3, num_branches=4, block="BASIC", num_blocks=(4, 4, 4, 4), num_channels=(32, 64, 128, 256), fuse_method="SUM")),
 }
+
+
+BRANCH_STREAMS = {"on": os.environ.get("RSS_BRANCH_STREAMS", "1") != "0"}
+_SIDE = {}
+
+
+def _side_streams(dev, n):
+    lst = _SIDE.setdefault(dev, [])
+    while len(lst) < n:
+        lst.append(torch.cuda.Stream(dev))
+    return lst
 
 
 def _conv(cin, cout, k, stride=1, padding=0):
@@ -142,10 +155,33 @@ class HighResolutionModule(nn.Module):
             x = _run(seq[0], seq[1], x)
         return x, 0
 
+    def _run_branches(self, x):
+        """The branches of a module are independent until the fuse step: the low-resolution ones (few tiles, latency-bound
+        kernels) run on side streams next to the 128x128 branch, so that inside the captured CUDA graph they become
+        parallel sub-graphs that fill SMs the high-resolution kernels leave idle.  Autograd replays each branch's backward
+        on the stream of its forward, so the backward pass is overlapped the same way."""
+        if not BRANCH_STREAMS["on"] or not x[0].is_cuda:
+            return [self.branches[i](x[i]) for i in range(self.num_branches)]
+        dev = x[0].device
+        cur = torch.cuda.current_stream(dev)
+        side = _side_streams(dev, self.num_branches - 1)
+        out = [None] * self.num_branches
+        for i in range(1, self.num_branches):
+            s = side[i - 1]
+            s.wait_stream(cur)
+            x[i].record_stream(s)
+            with torch.cuda.stream(s):
+                out[i] = self.branches[i](x[i])
+        out[0] = self.branches[0](x[0])
+        for i in range(1, self.num_branches):
+            cur.wait_stream(side[i - 1])
+            out[i].record_stream(cur)
+        return out
+
     def forward(self, x):
         if self.num_branches == 1:
             return [self.branches[0](x[0])]
-        x = [self.branches[i](x[i]) for i in range(self.num_branches)]
+        x = self._run_branches(x)
         x_fuse = []
         for i in range(len(self.fuse_layers)):
             terms, ks = [], []

@@ -32,6 +32,9 @@ class FusedBNAct(nn.Module):
         self.register_buffer("running_mean", torch.zeros(num_features))
         self.register_buffer("running_var", torch.ones(num_features))
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        # private scratch of rss_bn_stats_fused ([0] ticket, [1:] per-channel accumulators; the kernel leaves it zeroed).
+        # One per layer: layers may run concurrently on different streams.  Not part of the state_dict.
+        self.register_buffer("_scratch", torch.zeros(1 + 2 * num_features), persistent=False)
 
     defer_counter = False      # trainer.FlatSGD bumps every num_batches_tracked with one foreach op per step instead
 
@@ -39,7 +42,7 @@ class FusedBNAct(nn.Module):
         if self.training and not FusedBNAct.defer_counter:
             self.num_batches_tracked += 1
         return ops.BNAct.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
-                               self.training, self.momentum, self.eps, self.act, True if self.sync else None)
+                               self.training, self.momentum, self.eps, self.act, True if self.sync else None, self._scratch)
 
     def extra_repr(self):
         return "%d, act=%d, sync=%s" % (self.num_features, self.act, self.sync)

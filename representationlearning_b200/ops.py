@@ -203,21 +203,9 @@ class WindowAttention(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 # BatchNorm(+SyncBN) + activation (+ residual)
 # ----------------------------------------------------------------------------------------------
-_TICKETS = {}
-
-
-def _ticket(dev):
-    """persistent scratch of rss_bn_stats_fused: [0] = last-block ticket, [1:] = per-channel accumulators
-    (zero-initialised once; every call leaves it zero)"""
-    t = _TICKETS.get(dev)
-    if t is None:
-        t = _TICKETS[dev] = torch.zeros(1 + 4096, device=dev, dtype=torch.float32)
-    return t
-
-
 class BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, training, momentum, eps, act, group):
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, training, momentum, eps, act, group, scratch=None):
         _lib.require_device()
         lib = _lib.load()
         x = nhwc(x)
@@ -232,7 +220,8 @@ class BNAct(torch.autograd.Function):
         aff = torch.empty(4, C, device=dev, dtype=torch.float32)      # mean, invstd, scale, shift
         world = _world(group) if training else 1
         if training and world == 1:
-            scratch = _ticket(dev)
+            if scratch is None or scratch.numel() < 1 + 2 * C:      # [0] last-block ticket, [1:] accumulators; kernel leaves zeros
+                scratch = torch.zeros(1 + 2 * C, device=dev, dtype=torch.float32)
             check(lib.rss_bn_stats_fused(_p(x), _p(scratch[1:]), _p(scratch), rows, C, dt, _p(g), _p(b),
                                          _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
                                          _p(aff[3]), st), "rss_bn_stats_fused")
@@ -292,8 +281,8 @@ class BNAct(torch.autograd.Function):
                                    _p(dx), _p(dres), rows, C, ctx.act, dt, _p(local), _p(sg) if direct else None,
                                    _p(sb) if direct else None, st), "rss_bn_bwd_apply")
         if direct:
-            return dx, dres, None, None, None, None, None, None, None, None, None
-        return dx, dres, local[C:], local[:C], None, None, None, None, None, None, None
+            return dx, dres, None, None, None, None, None, None, None, None, None, None
+        return dx, dres, local[C:], local[:C], None, None, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
