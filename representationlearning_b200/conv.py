@@ -8,6 +8,7 @@ Both take the low-precision copy of the weight from the optimiser's bf16 shadow 
 registered (no per-call cast kernels), and return fp32 weight gradients to the master parameter.
 """
 import ctypes
+import os
 
 import torch
 
@@ -16,7 +17,62 @@ from . import _lib, ops
 CL = torch.channels_last
 # per-shape engine policy from tools/conv_microbench.py (profiles/conv_microbench_r1.json): the igemm kernel runs the
 # FFN's fused 17-tap conv (forward + data gradient); single convs stay on the library until the halo-reuse version lands.
-ENGINE = {"igemm": True, "igemm_single": False}       # bf16 stride-1 convs go through csrc/conv_igemm.cu when the geometry is supported
+ENGINE = {"igemm": True, "igemm_single": False}
+
+# Weight gradients are needed only by the optimiser, data gradients by the next backward node: wgrad kernels go to a side
+# stream so they overlap the (latency-bound) rest of the backward chain; trainer joins the stream before the all-reduce.
+WGRAD = {"async": os.environ.get("RSS_WGRAD_STREAM", "1") != "0", "streams": {}, "used": set()}
+
+
+def wgrad_stream(dev):
+    s = WGRAD["streams"].get(dev)
+    if s is None:
+        s = WGRAD["streams"][dev] = torch.cuda.Stream(dev)
+    return s
+
+
+def join_wgrad(dev=None):
+    """make the current stream wait for every outstanding weight-gradient kernel (call before reading gradients)"""
+    for d, s in WGRAD["streams"].items():
+        if (dev is None or d == dev) and d in WGRAD["used"]:
+            torch.cuda.current_stream(d).wait_stream(s)
+    WGRAD["used"].clear()
+
+
+def _lib_wgrad(dy, x, w_lp, weight, bias, want_b, stride, padding, dilation, wdtype):
+    """cuDNN weight (+bias) gradient, accumulated into the flat fp32 grad buffer when there is one; returns (dw, db) to hand
+    back through autograd (None when already accumulated)."""
+    def run():
+        _, dw, db = torch.ops.aten.convolution_backward(dy, x, w_lp, [w_lp.shape[0]] if want_b else None, [stride, stride],
+                                                        [padding, padding], [dilation, dilation], False, [0, 0], 1,
+                                                        [False, True, want_b])
+        sw = ops.grad_sink(weight)
+        if sw is not None:
+            sw.add_(dw)
+            dw = None
+        else:
+            dw = dw.to(wdtype)
+        if db is not None:
+            sb = ops.grad_sink(bias)
+            if sb is not None:
+                sb.add_(db)
+                db = None
+            else:
+                db = db.to(wdtype)
+        return dw, db
+
+    direct = ops.grad_sink(weight) is not None and (not want_b or ops.grad_sink(bias) is not None)
+    # only parameters owned by trainer.FlatSGD go asynchronous (its step joins the stream); anyone else reads .grad right away
+    if not (WGRAD["async"] and direct and dy.is_cuda and getattr(weight, "_rss_flat", False)):
+        return run()
+    dev = dy.device
+    cur, side = torch.cuda.current_stream(dev), wgrad_stream(dev)
+    side.wait_stream(cur)
+    dy.record_stream(side); x.record_stream(side); w_lp.record_stream(side)
+    with torch.cuda.stream(side):
+        run()
+    WGRAD["used"].add(dev)
+    return None, None       # bf16 stride-1 convs go through csrc/conv_igemm.cu when the geometry is supported
 
 
 def register_shadow(param, view):
@@ -52,22 +108,12 @@ class _ConvLib(torch.autograd.Function):
         dy = ops.nhwc(dy)
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
-        mask = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]]
-        dx, dw, db = torch.ops.aten.convolution_backward(dy, x, w, [w.shape[0]] if has_bias else None, [stride, stride],
-                                                         [padding, padding], [dilation, dilation], False, [0, 0], 1, mask)
-        sw = ops.grad_sink(ctx.refs[0])
-        if dw is not None and sw is not None:        # accumulate straight into the flat fp32 grad buffer (cast fused into the add)
-            sw.add_(dw)
-            dw = None
-        elif dw is not None:
-            dw = dw.to(wdtype)
-        if db is not None:
-            sb = ops.grad_sink(ctx.refs[1])
-            if sb is not None:
-                sb.add_(db)
-                db = None
-            else:
-                db = db.to(wdtype)
+        dx = dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw, db = _lib_wgrad(dy, x, w, ctx.refs[0], ctx.refs[1], has_bias and ctx.needs_input_grad[2], stride, padding, dilation, wdtype)
+        if ctx.needs_input_grad[0]:
+            dx = torch.ops.aten.convolution_backward(dy, x, w, None, [stride, stride], [padding, padding], [dilation, dilation],
+                                                     False, [0, 0], 1, [True, False, False])[0]
         return dx, dw, db, None, None, None, None
 
 
@@ -134,6 +180,16 @@ class _ConvIgemm(torch.autograd.Function):
             dy_ = dy_.to(x.dtype)
         B, Cin, H, W = x.shape
         Cout = weights[0].shape[0]
+        gw, gb = [], []
+        for s in range(n):                         # weight gradients first: they start on the side stream while dgrad runs here
+            k, d = ksizes[s], dils[s]
+            if not ctx.needs_input_grad[2 + s]:
+                gw.append(None); gb.append(None)
+                continue
+            w_lp = _lowp(weights[s], x.dtype).contiguous(memory_format=CL)
+            want_b = biases[s] is not None and bias_grad
+            dw, db = _lib_wgrad(dy_, x, w_lp, weights[s], biases[s], want_b, 1, d * (k // 2), d, weights[s].dtype)
+            gw.append(dw); gb.append(db)
         dx = None
         if ctx.needs_input_grad[0]:
             packed, _, nt, tdy, tdx, keep = _pack(weights, [None] * n, ksizes, dils, Cout, Cin, True, x.device)
@@ -141,25 +197,6 @@ class _ConvIgemm(torch.autograd.Function):
             with ops.timed("rss_conv_igemm"):
                 ops.check(lib.rss_conv_igemm(dy_.data_ptr(), packed.data_ptr(), None, dx.data_ptr(), B, H, W, Cout, Cin, nt, tdy, tdx,
                                              ops._st()), "rss_conv_igemm")
-        gw, gb = [], []
-        for s in range(n):
-            k, d = ksizes[s], dils[s]
-            w_lp = _lowp(weights[s], x.dtype).contiguous(memory_format=CL)
-            want_b = biases[s] is not None and bias_grad
-            _, dw, db = torch.ops.aten.convolution_backward(dy_, x, w_lp, [Cout] if want_b else None, [1, 1], [d * (k // 2)] * 2, [d, d],
-                                                            False, [0, 0], 1, [False, True, want_b])
-            sw = ops.grad_sink(weights[s])
-            if sw is not None:
-                sw.add_(dw); dw = None
-            else:
-                dw = dw.to(weights[s].dtype)
-            if db is not None:
-                sb = ops.grad_sink(biases[s])
-                if sb is not None:
-                    sb.add_(db); db = None
-                else:
-                    db = db.to(biases[s].dtype)
-            gw.append(dw); gb.append(db)
         return (dx, None) + tuple(gw) + tuple(gb)
 
 

@@ -52,6 +52,7 @@ class FlatSGD:
             self.flat_p[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat_p[o:o + n].view(p.shape)
             p.grad = self.flat_g[o:o + n].view(p.shape)
+            p._rss_flat = True
             if self.shadow is not None:
                 conv.register_shadow(p, self.shadow[o:o + n].view(p.shape))
         if self.shadow is not None:
@@ -74,6 +75,7 @@ class FlatSGD:
                 p.grad = v
 
     def all_reduce_grads(self, group=None):
+        conv.join_wgrad()                      # weight-gradient kernels run on a side stream: join before touching flat_g
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat_g, group=group)          # sum; the 1/world mean is folded into the step kernels
             return 1.0 / dist.get_world_size(group)
