@@ -70,6 +70,7 @@ typedef struct {
 /* out = x + Attn(LN1(x), LN1(y)).  Saved for backward (caller-owned): ln_stats [4][B*HW] f32 (mean/rstd of x, of y);
  * pooled [B][4][HW] f32; amax [B][2][HW] u8; smap, gmap [B][2][HW] f32.  The normalised tokens are never materialised:
  * every consumer recomputes (x-mean)*rstd*gamma+beta in fp32 from x and ln_stats. */
+#define RSS_ATTN_SIMT 2          /* flags bit 1: force the fp32 SIMT kernels even for bf16 activations (A/B testing) */
 #define RSS_ATTN_NO_RESIDUAL 1   /* flags bit 0: out = Attn(...) without "+ x" (InterlacedPoolAttention2.forward alone) */
 /* p->ln_w == NULL skips norm1 (x, y are then the already-normalised tokens; ln_stats unused). */
 int rss_attn_fwd(const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int dtype, int flags,

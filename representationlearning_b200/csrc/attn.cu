@@ -325,6 +325,250 @@ win_attn_fwd_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef lx, 
 }
 
 // ------------------------------------------------------------------------------------------
+// forward, tensor-core version for bf16 activations: the window's tokens, q/k/v and the weights sit in shared memory as
+// bf16 (row stride 40 elements = 80 B: conflict-free ldmatrix), every product runs on mma.sync m16n8k16 (bf16 x bf16 -> fp32),
+// the softmax stays in the accumulator registers and P feeds the PV product straight from registers.  49 tokens are padded to
+// 64 rows (4 warps x 16 query rows); padded keys are masked out of the softmax.  ~10x fewer issued instructions than the
+// fp32 SIMT kernel above (which remains the strict-parity path for fp32 activations).
+// (49x16 tiles with K=16 cannot fill a 128-row tcgen05 tile: a UMMA per (window, head) would be >60 % padding and would need
+// a TMEM round trip per 49x49 score tile; warp-level MMA keeps the whole window in registers instead.  See DESIGN.md.)
+// ------------------------------------------------------------------------------------------
+constexpr int kTS = 40;                       // bf16 row stride of the token / weight tiles
+constexpr int kRows = 64;
+
+__device__ __forceinline__ void mma_bf16(float d[4], const uint32_t a[4], const uint32_t b[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t r[4], const __nv_bfloat16* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t r[4], const __nv_bfloat16* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t r[2], const __nv_bfloat16* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t r[2], const __nv_bfloat16* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// gated (and normalised) tokens of one window -> bf16 dst[64][40]; pad tokens and rows 49..63 are zeros
+template <typename T>
+__device__ __forceinline__ void load_window_bf16(const T* __restrict__ src, const LnRef& ln, const float* __restrict__ gate_b,
+                                                 __nv_bfloat16* dst, const WinGeom& g, int b, int wi, int wj) {
+    for (int idx = threadIdx.x; idx < kRows * 4; idx += kThreads) {
+        const int t = idx >> 2, part = idx & 3;
+        const int n = t < kL ? token_pixel(g, wi, wj, t) : -1;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (n >= 0) {
+            load8(src + ((size_t)b * g.HW + n) * kC + part * 8, v);
+            if (ln.mean) {
+                const float mu = ln.mean[(size_t)b * g.HW + n], rs = ln.rstd[(size_t)b * g.HW + n];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = (v[i] - mu) * rs * ln.gamma[part * 8 + i] + ln.beta[part * 8 + i];
+            }
+            if (gate_b) {
+                int gi = (int)(((int64_t)n * kC + part * 8) % g.HW);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { v[i] *= gate_b[gi]; if (++gi == g.HW) gi = 0; }
+            }
+        }
+        *reinterpret_cast<uint4*>(dst + t * kTS + part * 8) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+}
+
+// acc[nt] (16 rows x 8 cols each) = A[16 rows of this warp][32] . W[n][k]^T for the 4 n-tiles of a 32-wide projection
+__device__ __forceinline__ void proj_mma(const __nv_bfloat16* A, const __nv_bfloat16* Wm, int row0, int lane, float acc[4][4]) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a[4];
+        ldsm_x4(a, A + (row0 + (lane & 15)) * kTS + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            uint32_t bfr[2];
+            ldsm_x2(bfr, Wm + (nt * 8 + (lane & 7)) * kTS + ks * 16 + ((lane >> 3) & 1) * 8);
+            mma_bf16(acc[nt], a, bfr);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 4)
+win_attn_fwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef lx, LnRef ly, const float* __restrict__ gmap,
+                       const T* __restrict__ xres, T* __restrict__ out, rss_attn_params p, WinGeom g) {
+    __shared__ __align__(16) __nv_bfloat16 xs[kRows * kTS], ys[kRows * kTS], qkv[3 * kRows * kTS], Wsm[4 * kC * kTS];
+    __shared__ float bsm[4 * kC], gate[2];
+    __nv_bfloat16* qs = qkv;
+    __nv_bfloat16* ks = qkv + kRows * kTS;
+    __nv_bfloat16* vs = qkv + 2 * kRows * kTS;
+    float* stage = reinterpret_cast<float*>(qkv);          // [64][36] fp32 output staging, aliases q and k once they are dead
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
+    {
+        const float* wsrc[4] = {p.q_w, p.k_w, p.v_w, p.o_w};
+        const float* bsrc[4] = {p.q_b, p.k_b, p.v_b, p.o_b};
+        for (int idx = tid; idx < 4 * kC * kC; idx += kThreads) {
+            const int m = idx / (kC * kC), r = (idx / kC) % kC, c = idx % kC;
+            Wsm[(m * kC + r) * kTS + c] = __float2bfloat16_rn(wsrc[m][r * kC + c]);
+        }
+        for (int idx = tid; idx < 4 * kC; idx += kThreads) bsm[idx] = bsrc[idx / kC][idx % kC];
+    }
+    const int row0 = warp * 16;
+
+    for (int win = blockIdx.x; win < g.nWin; win += gridDim.x) {
+        const int b = win / (g.qh * g.qw), wi = (win / g.qw) % g.qh, wj = win % g.qw;
+        load_window_bf16(x, lx, gmap + ((size_t)b * 2 + 0) * g.HW, xs, g, b, wi, wj);
+        load_window_bf16(y, ly, gmap + ((size_t)b * 2 + 1) * g.HW, ys, g, b, wi, wj);
+        __syncthreads();
+        // ---- q, k, v projections (DAL.py:873-875); rows >= 49 are MMA padding and are stored as zeros
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            float acc[4][4];
+            proj_mma(m == 0 ? xs : ys, Wsm + m * kC * kTS, row0, lane, acc);
+            __nv_bfloat16* dst = m == 0 ? qs : (m == 1 ? ks : vs);
+            const float sc = m == 0 ? 0.25f : 1.0f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int col = nt * 8 + tq * 2;
+                const float b0 = bsm[m * kC + col], b1 = bsm[m * kC + col + 1];
+                const int r0 = row0 + gq, r1 = r0 + 8;
+                *reinterpret_cast<uint32_t*>(dst + r0 * kTS + col) = r0 < kL ? pack_bf16((acc[nt][0] + b0) * sc, (acc[nt][1] + b1) * sc) : 0u;
+                *reinterpret_cast<uint32_t*>(dst + r1 * kTS + col) = r1 < kL ? pack_bf16((acc[nt][2] + b0) * sc, (acc[nt][3] + b1) * sc) : 0u;
+            }
+        }
+        __syncthreads();
+        // ---- channel gate (DAL.py:1003-1010): S2 = q_h^T k_h (16x16) by warp h, gate = sigmoid(mean + max)
+        if (warp < 2) {
+            const int h = warp;
+            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int kt = 0; kt < 4; ++kt) {
+                uint32_t a[4];
+                const int i = lane >> 3;
+                ldsm_x4_t(a, qs + (kt * 16 + (lane & 7) + 8 * (i >> 1)) * kTS + h * kHD + 8 * (i & 1));
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    uint32_t bfr[2];
+                    ldsm_x2_t(bfr, ks + (kt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kTS + h * kHD + nb * 8);
+                    mma_bf16(acc[nb], a, bfr);
+                }
+            }
+            float sum = 0.f, mx = -INFINITY;
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { sum += acc[nb][e]; mx = fmaxf(mx, acc[nb][e]); }
+            sum = warp_sum(sum);
+            mx = warp_max(mx);
+            if (lane == 0) gate[h] = 1.0f / (1.0f + expf(-(sum * (1.0f / 256.0f) + mx)));
+        }
+        __syncthreads();
+        // ---- attention rows of this warp, both heads: S = q k^T, softmax, O = P v, gate folded into the normaliser
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t aq[4];
+            ldsm_x4(aq, qs + (row0 + (lane & 15)) * kTS + h * kHD + (lane >> 4) * 8);
+            float S[7][4];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                S[j][0] = S[j][1] = S[j][2] = S[j][3] = 0.f;
+                uint32_t bk[2];
+                ldsm_x2(bk, ks + (j * 8 + (lane & 7)) * kTS + h * kHD + ((lane >> 3) & 1) * 8);
+                mma_bf16(S[j], aq, bk);
+            }
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const int c = j * 8 + tq * 2;
+                if (c >= kL) { S[j][0] = -INFINITY; S[j][2] = -INFINITY; }
+                if (c + 1 >= kL) { S[j][1] = -INFINITY; S[j][3] = -INFINITY; }
+                m0 = fmaxf(m0, fmaxf(S[j][0], S[j][1]));
+                m1 = fmaxf(m1, fmaxf(S[j][2], S[j][3]));
+            }
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                S[j][0] = __expf(S[j][0] - m0); S[j][1] = __expf(S[j][1] - m0);
+                S[j][2] = __expf(S[j][2] - m1); S[j][3] = __expf(S[j][3] - m1);
+                s0 += S[j][0] + S[j][1];
+                s1 += S[j][2] + S[j][3];
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            float O[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {                 // keys 16kk..16kk+15: P straight from the score registers
+                uint32_t ap[4];
+                ap[0] = pack_bf16(S[2 * kk][0], S[2 * kk][1]);
+                ap[1] = pack_bf16(S[2 * kk][2], S[2 * kk][3]);
+                ap[2] = kk < 3 ? pack_bf16(S[2 * kk + 1 < 7 ? 2 * kk + 1 : 6][0], S[2 * kk + 1 < 7 ? 2 * kk + 1 : 6][1]) : 0u;
+                ap[3] = kk < 3 ? pack_bf16(S[2 * kk + 1 < 7 ? 2 * kk + 1 : 6][2], S[2 * kk + 1 < 7 ? 2 * kk + 1 : 6][3]) : 0u;
+#pragma unroll
+                for (int nd = 0; nd < 2; ++nd) {
+                    uint32_t bv[2];
+                    ldsm_x2_t(bv, vs + (kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kTS + h * kHD + nd * 8);
+                    mma_bf16(O[nd], ap, bv);
+                }
+            }
+            const float sc0 = gate[h] / s0, sc1 = gate[h] / s1;
+#pragma unroll
+            for (int nd = 0; nd < 2; ++nd) {
+                const int col = h * kHD + nd * 8 + tq * 2;
+                *reinterpret_cast<uint32_t*>(xs + (row0 + gq) * kTS + col) = pack_bf16(O[nd][0] * sc0, O[nd][1] * sc0);
+                *reinterpret_cast<uint32_t*>(xs + (row0 + gq + 8) * kTS + col) = pack_bf16(O[nd][2] * sc1, O[nd][3] * sc1);
+            }
+        }
+        __syncthreads();                                     // q/k/v dead everywhere: their storage becomes the fp32 staging tile
+        {
+            float acc[4][4];
+            proj_mma(xs, Wsm + 3 * kC * kTS, row0, lane, acc);   // out_proj (DAL.py:1020); xs now holds the merged heads
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int col = nt * 8 + tq * 2;
+                const float b0 = bsm[3 * kC + col], b1 = bsm[3 * kC + col + 1];
+                stage[(row0 + gq) * kLD + col] = acc[nt][0] + b0; stage[(row0 + gq) * kLD + col + 1] = acc[nt][1] + b1;
+                stage[(row0 + gq + 8) * kLD + col] = acc[nt][2] + b0; stage[(row0 + gq + 8) * kLD + col + 1] = acc[nt][3] + b1;
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < kL * 4; idx += kThreads) {   // un-window, crop, + residual
+            const int t = idx >> 2, part = idx & 3;
+            const int n = token_pixel(g, wi, wj, t);
+            if (n < 0) continue;
+            const size_t off = ((size_t)b * g.HW + n) * kC + part * 8;
+            float r[8];
+            if (xres) load8(xres + off, r);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] += stage[t * kLD + part * 8 + i];
+            store8(out + off, r);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // backward of the windowed Mhca: produces d(gated x tokens), d(gated y tokens), dW/db of the 4 projections
 // ------------------------------------------------------------------------------------------
 constexpr int kBwdSmemFloats = 7 * kTok + 2 * 2 * kL * kPS + 4 * kC * kLD + 4 * kC + 32;
@@ -687,8 +931,14 @@ static int attn_fwd_impl(const void* x, const void* y, const rss_attn_params* p,
     }
     int grid = num_sms() * 4;
     if (grid > g.nWin) grid = g.nWin;
-    win_attn_fwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)y, lx, ly, gmap,
-                                                         (flags & RSS_ATTN_NO_RESIDUAL) ? (const T*)nullptr : (const T*)x, (T*)out, *p, g);
+    const T* res = (flags & RSS_ATTN_NO_RESIDUAL) ? (const T*)nullptr : (const T*)x;
+    if (sizeof(T) == 2 && !(flags & RSS_ATTN_SIMT)) {       // bf16 activations: tensor-core kernel (6 CTAs/SM)
+        int gtc = num_sms() * 6;
+        if (gtc > g.nWin) gtc = g.nWin;
+        win_attn_fwd_tc_kernel<T><<<gtc, kThreads, 0, st>>>((const T*)x, (const T*)y, lx, ly, gmap, res, (T*)out, *p, g);
+    } else {
+        win_attn_fwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)y, lx, ly, gmap, res, (T*)out, *p, g);
+    }
     return check_launch();
 }
 

@@ -132,9 +132,10 @@ class GraphedTrainStep:
         self.labels = labels.clone()
         side = torch.cuda.Stream(img.device)
         side.wait_stream(torch.cuda.current_stream())
+        self.warmup_losses = []
         with torch.cuda.stream(side):
             for _ in range(warmup):                     # eager warm-up (also performs one-time kernel attribute setup)
-                train_step(model, opt, self.img, self.labels, group)
+                self.warmup_losses.append(train_step(model, opt, self.img, self.labels, group))
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
