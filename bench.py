@@ -182,7 +182,7 @@ def main():
     # ---- eager warm-up with live CUDA-event timing of the hand-written regions (same shapes, same process) ----
     for _ in range(2):
         step_eager()
-    dom = "rss_attn_bwd"
+    dom = "rss_conv_igemm"
     ops.TIMED_OPS.update(["rss_attn_bwd", "rss_attn_fwd", "rss_conv_igemm"]); ops.TIMED.clear()
     c0 = ops.COUNTERS["launches"]
     ms_eager = timed(step_eager, 2) / 2
@@ -253,17 +253,27 @@ def main():
 
     pk = peaks()
     per_gpu = value / world
-    # dominant hand-written region: fused window-attention backward (HBM/issue-bound):
-    # algorithmic bytes per launch = read dout, x, y + write dx, dy of (B, 128*128, 32) bf16 tokens
-    tok_bytes = B * (S // 4) * (S // 4) * 32 * 2
-    alg = {"rss_attn_bwd": 5 * tok_bytes, "rss_attn_fwd": 3 * tok_bytes}
+    # dominant hand-written kernel: the tcgen05/TMA implicit-GEMM convolution running the FFN's dw+dw6+dw12 convs as one
+    # GEMM (forward and data gradient: 16 launches per step).  ALGORITHMIC FLOPs per launch = what the reference's three
+    # convolutions execute: 2 * (1 + 9 + 9 taps) * 128 * 128 * (B*128*128 pixels) (FFN dil-6 + dil-12 + 1x1);
+    # the kernel itself runs 17 taps (the three centre taps are merged).
+    hw4 = (S // 4) * (S // 4)
+    alg_flops = 2.0 * 19 * 128 * 128 * B * hw4
+    tok_bytes = B * hw4 * 32 * 2
     roof = None
     if dom in kt:
-        ach = alg[dom] / (kt[dom] / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": None, "peak_source": pk["src"] + " (burst copy)", "ms_per_launch": kt[dom],
-                "launches_timed": kn[dom], "algorithmic_bytes_per_launch": alg[dom],
+        ach = alg_flops / (kt[dom] / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (FFN 19-tap conv, fwd/dgrad)", "achieved": ach, "peak": pk["tf_burst"],
+                "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": 92.7e6,
+                "peak_source": pk["src"] + " (burst cuBLAS bf16; kernel timed alone per launch)", "ms_per_launch": kt[dom],
+                "launches_timed": kn[dom], "algorithmic_flops_per_launch": alg_flops,
+                "traffic_source": "profiles/ncu_full_prof_igemm_r1.csv: dram read 67.7 MB + write 25.0 MB per launch",
                 "timing": "CUDA events around the C-ABI call on the launching stream, eager pass of the same step in this process"}
+    hbm_regions = {}
+    for name, nbytes in (("rss_attn_fwd", 3 * tok_bytes), ("rss_attn_bwd", 5 * tok_bytes)):
+        if name in kt:
+            a = nbytes / (kt[name] / 1e3) / 1e9
+            hbm_regions[name] = {"bound": "hbm", "achieved_gbs": a, "frac": a / pk["hbm"], "algorithmic_bytes": nbytes, "ms": kt[name]}
     step_tf = per_gpu * FLOP_PER_IMG_TRAIN / 1e12
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -278,7 +288,7 @@ def main():
         "roofline": roof,
         "step_roofline": {"bound": "tensor", "achieved": step_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": step_tf / pk["tf_sust"],
                           "note": "whole step vs sustained bf16 GEMM peak, 528.11 GFLOP/img algorithmic"},
-        "region_ms": kt, "clocks": clocks, "loss": float(last["loss"].item()),
+        "region_ms": kt, "hbm_regions": hbm_regions, "clocks": clocks, "loss": float(last["loss"].item()),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args.cpu_baseline_steps, 1, 1, S)

@@ -773,6 +773,381 @@ win_attn_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef lx, 
 }
 
 // ------------------------------------------------------------------------------------------
+// backward, tensor-core version for bf16 activations (same conventions as win_attn_fwd_tc_kernel).  Per window:
+//   recompute q,k,v, gate (+ arg-max), P;  dOm = dout.Wo;  A = P v;  dA = dOm*gate;  dP = dA v^T;  dS = P o (dP - rowdot);
+//   dq = dS k;  dk = dS^T q;  dv = P^T dA  (P, dS, dA staged in smem as bf16 for the transposed products);
+//   Q^T K gate terms added on the fp32 accumulators;  d(tokens) = G.W;  dW += G^T X  (persistent register accumulators).
+// ------------------------------------------------------------------------------------------
+constexpr int kPB = 72;                                  // bf16 row stride of the P / dS tiles (64 keys + pad, 144 B rows)
+constexpr int kBwdTcSmem = (11 * kRows * kTS + 4 * kRows * kPB + 4 * kC * kTS) * 2 + (4 * kC + 32) * 4;
+
+// acc[nt] = A[16 rows][32] . W[k][n]  (W stored [k][n] row-major: the transposed use of a (out,in) weight)
+__device__ __forceinline__ void projT_mma(const __nv_bfloat16* A, const __nv_bfloat16* Wm, int row0, int lane, float acc[4][4], bool zero) {
+    if (zero) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+    }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a[4];
+        ldsm_x4(a, A + (row0 + (lane & 15)) * kTS + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            uint32_t bfr[2];
+            ldsm_x2_t(bfr, Wm + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kTS + nt * 8);
+            mma_bf16(acc[nt], a, bfr);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+win_attn_bwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef lx, LnRef ly, const float* __restrict__ gmap,
+                       const T* __restrict__ dout, float* __restrict__ dxg, float* __restrict__ dyg,
+                       rss_attn_params p, rss_attn_grads gr, WinGeom g) {
+    extern __shared__ __align__(16) uint8_t smem_tc[];
+    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_tc);
+    __nv_bfloat16* ys = xs + kRows * kTS;
+    __nv_bfloat16* ds = ys + kRows * kTS;
+    __nv_bfloat16* qs = ds + kRows * kTS;
+    __nv_bfloat16* ks = qs + kRows * kTS;
+    __nv_bfloat16* vs = ks + kRows * kTS;
+    __nv_bfloat16* Om = vs + kRows * kTS;
+    __nv_bfloat16* dAb = Om + kRows * kTS;
+    __nv_bfloat16* Gq = dAb + kRows * kTS;
+    __nv_bfloat16* Gk = Gq + kRows * kTS;
+    __nv_bfloat16* Gv = Gk + kRows * kTS;
+    __nv_bfloat16* Pb = Gv + kRows * kTS;                 // [2 heads][64][72]
+    __nv_bfloat16* dSb = Pb + 2 * kRows * kPB;            // [2 heads][64][72]
+    __nv_bfloat16* Wsm = dSb + 2 * kRows * kPB;           // [4][32][40]
+    float* bsm = reinterpret_cast<float*>(Wsm + 4 * kC * kTS);
+    float* misc = bsm + 4 * kC;                           // [0..1] gate, [2..3] argmax (int), [4..11] dgate partials [h][warp]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
+    {
+        const float* wsrc[4] = {p.q_w, p.k_w, p.v_w, p.o_w};
+        const float* bsrc[4] = {p.q_b, p.k_b, p.v_b, p.o_b};
+        for (int idx = tid; idx < 4 * kC * kC; idx += kThreads) {
+            const int m = idx / (kC * kC), r = (idx / kC) % kC, c = idx % kC;
+            Wsm[(m * kC + r) * kTS + c] = __float2bfloat16_rn(wsrc[m][r * kC + c]);
+        }
+        for (int idx = tid; idx < 4 * kC; idx += kThreads) bsm[idx] = bsrc[idx / kC][idx % kC];
+    }
+    const int row0 = warp * 16;
+    // persistent weight-gradient accumulators: warp m owns matrix m; tile (mt, nt): rows c = mt*16 + gq (+8), cols i = nt*8 + 2tq (+1)
+    float accW[2][4][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) accW[a][b][e] = 0.f;
+    float accB = 0.f;
+
+    for (int win = blockIdx.x; win < g.nWin; win += gridDim.x) {
+        const int b = win / (g.qh * g.qw), wi = (win / g.qw) % g.qh, wj = win % g.qw;
+        load_window_bf16(x, lx, gmap + ((size_t)b * 2 + 0) * g.HW, xs, g, b, wi, wj);
+        load_window_bf16(y, ly, gmap + ((size_t)b * 2 + 1) * g.HW, ys, g, b, wi, wj);
+        load_window_bf16(dout, LnRef{nullptr, nullptr, nullptr, nullptr}, (const float*)nullptr, ds, g, b, wi, wj);
+        __syncthreads();
+        // ---- recompute q, k, v ; dOm = dout . Wo (kept in registers)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            float acc[4][4];
+            proj_mma(m == 0 ? xs : ys, Wsm + m * kC * kTS, row0, lane, acc);
+            __nv_bfloat16* dst = m == 0 ? qs : (m == 1 ? ks : vs);
+            const float sc = m == 0 ? 0.25f : 1.0f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int col = nt * 8 + tq * 2;
+                const float b0 = bsm[m * kC + col], b1 = bsm[m * kC + col + 1];
+                const int r0 = row0 + gq, r1 = r0 + 8;
+                *reinterpret_cast<uint32_t*>(dst + r0 * kTS + col) = r0 < kL ? pack_bf16((acc[nt][0] + b0) * sc, (acc[nt][1] + b1) * sc) : 0u;
+                *reinterpret_cast<uint32_t*>(dst + r1 * kTS + col) = r1 < kL ? pack_bf16((acc[nt][2] + b0) * sc, (acc[nt][3] + b1) * sc) : 0u;
+            }
+        }
+        float dOm[4][4];
+        projT_mma(ds, Wsm + 3 * kC * kTS, row0, lane, dOm, true);
+        __syncthreads();
+        // ---- channel gate and its arg-max
+        if (warp < 2) {
+            const int h = warp;
+            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int kt = 0; kt < 4; ++kt) {
+                uint32_t a[4];
+                const int i = lane >> 3;
+                ldsm_x4_t(a, qs + (kt * 16 + (lane & 7) + 8 * (i >> 1)) * kTS + h * kHD + 8 * (i & 1));
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    uint32_t bfr[2];
+                    ldsm_x2_t(bfr, ks + (kt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kTS + h * kHD + nb * 8);
+                    mma_bf16(acc[nb], a, bfr);
+                }
+            }
+            float sum = 0.f, mx = -INFINITY;
+            int mi = 0;
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int aa = gq + (e >> 1) * 8, bb = nb * 8 + tq * 2 + (e & 1), id = aa * 16 + bb;
+                    sum += acc[nb][e];
+                    if (acc[nb][e] > mx || (acc[nb][e] == mx && id < mi)) { mx = acc[nb][e]; mi = id; }
+                }
+            sum = warp_sum(sum);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+                if (om > mx || (om == mx && oi < mi)) { mx = om; mi = oi; }
+            }
+            if (lane == 0) { misc[h] = 1.0f / (1.0f + expf(-(sum * (1.0f / 256.0f) + mx))); reinterpret_cast<int*>(misc)[2 + h] = mi; }
+        }
+        __syncthreads();
+        // ---- per head: P, A = P v, dA, dP, dS, dq (rows of this warp)
+        float dq[2][2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t aq[4];
+            ldsm_x4(aq, qs + (row0 + (lane & 15)) * kTS + h * kHD + (lane >> 4) * 8);
+            float S[7][4];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                S[j][0] = S[j][1] = S[j][2] = S[j][3] = 0.f;
+                uint32_t bk[2];
+                ldsm_x2(bk, ks + (j * 8 + (lane & 7)) * kTS + h * kHD + ((lane >> 3) & 1) * 8);
+                mma_bf16(S[j], aq, bk);
+            }
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const int c = j * 8 + tq * 2;
+                if (c >= kL) { S[j][0] = -INFINITY; S[j][2] = -INFINITY; }
+                if (c + 1 >= kL) { S[j][1] = -INFINITY; S[j][3] = -INFINITY; }
+                m0 = fmaxf(m0, fmaxf(S[j][0], S[j][1]));
+                m1 = fmaxf(m1, fmaxf(S[j][2], S[j][3]));
+            }
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                S[j][0] = __expf(S[j][0] - m0); S[j][1] = __expf(S[j][1] - m0);
+                S[j][2] = __expf(S[j][2] - m1); S[j][3] = __expf(S[j][3] - m1);
+                s0 += S[j][0] + S[j][1];
+                s1 += S[j][2] + S[j][3];
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) { S[j][0] *= i0; S[j][1] *= i0; S[j][2] *= i1; S[j][3] *= i1; }   // P
+            // P -> smem (bf16) for dv = P^T dA
+            __nv_bfloat16* Prow = Pb + (h * kRows + row0) * kPB;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                *reinterpret_cast<uint32_t*>(Prow + gq * kPB + j * 8 + tq * 2) = pack_bf16(S[j][0], S[j][1]);
+                *reinterpret_cast<uint32_t*>(Prow + (gq + 8) * kPB + j * 8 + tq * 2) = pack_bf16(S[j][2], S[j][3]);
+            }
+            *reinterpret_cast<uint32_t*>(Prow + gq * kPB + 56 + tq * 2) = 0u;
+            *reinterpret_cast<uint32_t*>(Prow + (gq + 8) * kPB + 56 + tq * 2) = 0u;
+            // A = P v
+            float A[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                uint32_t ap[4];
+                ap[0] = pack_bf16(S[2 * kk][0], S[2 * kk][1]);
+                ap[1] = pack_bf16(S[2 * kk][2], S[2 * kk][3]);
+                ap[2] = kk < 3 ? pack_bf16(S[kk < 3 ? 2 * kk + 1 : 6][0], S[kk < 3 ? 2 * kk + 1 : 6][1]) : 0u;
+                ap[3] = kk < 3 ? pack_bf16(S[kk < 3 ? 2 * kk + 1 : 6][2], S[kk < 3 ? 2 * kk + 1 : 6][3]) : 0u;
+#pragma unroll
+                for (int nd = 0; nd < 2; ++nd) {
+                    uint32_t bv[2];
+                    ldsm_x2_t(bv, vs + (kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kTS + h * kHD + nd * 8);
+                    mma_bf16(A[nd], ap, bv);
+                }
+            }
+            const float gate = misc[h];
+            float dA[2][4], dgp = 0.f, rd0 = 0.f, rd1 = 0.f;
+#pragma unroll
+            for (int nd = 0; nd < 2; ++nd) {
+                const int col = h * kHD + nd * 8 + tq * 2;
+                *reinterpret_cast<uint32_t*>(Om + (row0 + gq) * kTS + col) = pack_bf16(A[nd][0] * gate, A[nd][1] * gate);
+                *reinterpret_cast<uint32_t*>(Om + (row0 + gq + 8) * kTS + col) = pack_bf16(A[nd][2] * gate, A[nd][3] * gate);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float d = dOm[2 * h + nd][e];
+                    dgp += d * A[nd][e];
+                    dA[nd][e] = d * gate;
+                }
+                rd0 += dA[nd][0] * A[nd][0] + dA[nd][1] * A[nd][1];
+                rd1 += dA[nd][2] * A[nd][2] + dA[nd][3] * A[nd][3];
+                *reinterpret_cast<uint32_t*>(dAb + (row0 + gq) * kTS + col) = pack_bf16(dA[nd][0], dA[nd][1]);
+                *reinterpret_cast<uint32_t*>(dAb + (row0 + gq + 8) * kTS + col) = pack_bf16(dA[nd][2], dA[nd][3]);
+            }
+            rd0 += __shfl_xor_sync(0xffffffffu, rd0, 1); rd0 += __shfl_xor_sync(0xffffffffu, rd0, 2);
+            rd1 += __shfl_xor_sync(0xffffffffu, rd1, 1); rd1 += __shfl_xor_sync(0xffffffffu, rd1, 2);
+            dgp = warp_sum(dgp);
+            if (lane == 0) misc[4 + h * 4 + warp] = dgp;
+            // dP = dA v^T (K = 16 head dims): A operand straight from the dA accumulators
+            uint32_t ada[4] = {pack_bf16(dA[0][0], dA[0][1]), pack_bf16(dA[0][2], dA[0][3]),
+                               pack_bf16(dA[1][0], dA[1][1]), pack_bf16(dA[1][2], dA[1][3])};
+            __nv_bfloat16* dSrow = dSb + (h * kRows + row0) * kPB;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                float dP[4] = {0.f, 0.f, 0.f, 0.f};
+                uint32_t bvv[2];
+                ldsm_x2(bvv, vs + (j * 8 + (lane & 7)) * kTS + h * kHD + ((lane >> 3) & 1) * 8);
+                mma_bf16(dP, ada, bvv);
+                S[j][0] *= (dP[0] - rd0); S[j][1] *= (dP[1] - rd0);          // dS = P o (dP - rowdot)
+                S[j][2] *= (dP[2] - rd1); S[j][3] *= (dP[3] - rd1);
+                *reinterpret_cast<uint32_t*>(dSrow + gq * kPB + j * 8 + tq * 2) = pack_bf16(S[j][0], S[j][1]);
+                *reinterpret_cast<uint32_t*>(dSrow + (gq + 8) * kPB + j * 8 + tq * 2) = pack_bf16(S[j][2], S[j][3]);
+            }
+            *reinterpret_cast<uint32_t*>(dSrow + gq * kPB + 56 + tq * 2) = 0u;
+            *reinterpret_cast<uint32_t*>(dSrow + (gq + 8) * kPB + 56 + tq * 2) = 0u;
+            // dq = dS k
+#pragma unroll
+            for (int nd = 0; nd < 2; ++nd)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dq[h][nd][e] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                uint32_t as[4];
+                as[0] = pack_bf16(S[2 * kk][0], S[2 * kk][1]);
+                as[1] = pack_bf16(S[2 * kk][2], S[2 * kk][3]);
+                as[2] = kk < 3 ? pack_bf16(S[kk < 3 ? 2 * kk + 1 : 6][0], S[kk < 3 ? 2 * kk + 1 : 6][1]) : 0u;
+                as[3] = kk < 3 ? pack_bf16(S[kk < 3 ? 2 * kk + 1 : 6][2], S[kk < 3 ? 2 * kk + 1 : 6][3]) : 0u;
+#pragma unroll
+                for (int nd = 0; nd < 2; ++nd) {
+                    uint32_t bkk[2];
+                    ldsm_x2_t(bkk, ks + (kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kTS + h * kHD + nd * 8);
+                    mma_bf16(dq[h][nd], as, bkk);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- key side: this warp owns keys row0..row0+15: dk = dS^T q, dv = P^T dA ; then the Q^T K gate terms
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int kq = 0; kq < 4; ++kq) {                 // queries 16kq..16kq+15 are the contraction index
+                uint32_t a1[4], a2[4];
+                const int i = lane >> 3;
+                // A[m=key][k=query] = dS[query][key]: transposed load of the [query][key] tile
+                ldsm_x4_t(a1, dSb + (h * kRows + kq * 16 + (lane & 7) + 8 * (i >> 1)) * kPB + row0 + 8 * (i & 1));
+                ldsm_x4_t(a2, Pb + (h * kRows + kq * 16 + (lane & 7) + 8 * (i >> 1)) * kPB + row0 + 8 * (i & 1));
+#pragma unroll
+                for (int nd = 0; nd < 2; ++nd) {
+                    uint32_t bq[2], bd[2];
+                    ldsm_x2_t(bq, qs + (kq * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kTS + h * kHD + nd * 8);
+                    ldsm_x2_t(bd, dAb + (kq * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kTS + h * kHD + nd * 8);
+                    mma_bf16(dk[nd], a1, bq);
+                    mma_bf16(dv[nd], a2, bd);
+                }
+            }
+            const float gate = misc[h];
+            const float dz = (misc[4 + h * 4 + 0] + misc[4 + h * 4 + 1] + misc[4 + h * 4 + 2] + misc[4 + h * 4 + 3]) * gate * (1.0f - gate);
+            const float u = dz * (1.0f / 256.0f);
+            const int am = reinterpret_cast<int*>(misc)[2 + h], as_ = am >> 4, bs_ = am & 15;
+            // rows this thread holds in the accumulator layout: row0+gq and row0+gq+8 (queries for dq, keys for dk)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int r = row0 + gq + half * 8;
+                float qsum = 0.f, ksum = 0.f;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) {
+                    qsum += __bfloat162float(qs[r * kTS + h * kHD + d]);
+                    ksum += __bfloat162float(ks[r * kTS + h * kHD + d]);
+                }
+                const float q_as = __bfloat162float(qs[r * kTS + h * kHD + as_]), k_bs = __bfloat162float(ks[r * kTS + h * kHD + bs_]);
+#pragma unroll
+                for (int nd = 0; nd < 2; ++nd)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int d = nd * 8 + tq * 2 + e;
+                        dq[h][nd][half * 2 + e] += u * ksum + (d == as_ ? dz * k_bs : 0.f);
+                        dk[nd][half * 2 + e] += u * qsum + (d == bs_ ? dz * q_as : 0.f);
+                    }
+            }
+#pragma unroll
+            for (int nd = 0; nd < 2; ++nd) {
+                const int col = h * kHD + nd * 8 + tq * 2;
+                const int r0 = row0 + gq, r1 = r0 + 8;
+                *reinterpret_cast<uint32_t*>(Gq + r0 * kTS + col) = pack_bf16(0.25f * dq[h][nd][0], 0.25f * dq[h][nd][1]);
+                *reinterpret_cast<uint32_t*>(Gq + r1 * kTS + col) = pack_bf16(0.25f * dq[h][nd][2], 0.25f * dq[h][nd][3]);
+                *reinterpret_cast<uint32_t*>(Gk + r0 * kTS + col) = pack_bf16(dk[nd][0], dk[nd][1]);
+                *reinterpret_cast<uint32_t*>(Gk + r1 * kTS + col) = pack_bf16(dk[nd][2], dk[nd][3]);
+                *reinterpret_cast<uint32_t*>(Gv + r0 * kTS + col) = pack_bf16(dv[nd][0], dv[nd][1]);
+                *reinterpret_cast<uint32_t*>(Gv + r1 * kTS + col) = pack_bf16(dv[nd][2], dv[nd][3]);
+            }
+        }
+        __syncthreads();
+        // ---- gradients w.r.t. the gated tokens (rows of this warp): dxs = Gq.Wq ; dys = Gk.Wk + Gv.Wv
+        {
+            float ax[4][4], ay[4][4];
+            projT_mma(Gq, Wsm + 0 * kC * kTS, row0, lane, ax, true);
+            projT_mma(Gk, Wsm + 1 * kC * kTS, row0, lane, ay, true);
+            projT_mma(Gv, Wsm + 2 * kC * kTS, row0, lane, ay, false);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int t = row0 + gq + half * 8;
+                const int n = t < kL ? token_pixel(g, wi, wj, t) : -1;
+                if (n >= 0) {
+                    float* px = dxg + ((size_t)b * g.HW + n) * kC + tq * 2;
+                    float* py = dyg + ((size_t)b * g.HW + n) * kC + tq * 2;
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        *reinterpret_cast<float2*>(px + nt * 8) = make_float2(ax[nt][half * 2], ax[nt][half * 2 + 1]);
+                        *reinterpret_cast<float2*>(py + nt * 8) = make_float2(ay[nt][half * 2], ay[nt][half * 2 + 1]);
+                    }
+                }
+            }
+        }
+        // ---- weight gradients: warp m accumulates dW_m[c][i] += sum_t G_m[t][c] X_m[t][i]
+        {
+            const __nv_bfloat16* G = warp == 0 ? Gq : (warp == 1 ? Gk : (warp == 2 ? Gv : ds));
+            const __nv_bfloat16* X = warp == 0 ? xs : (warp == 3 ? Om : ys);
+#pragma unroll
+            for (int kt = 0; kt < 4; ++kt) {
+                uint32_t a[2][4];
+                const int i = lane >> 3;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)      // A[m=c][k=t] = G[t][c]: transposed load
+                    ldsm_x4_t(a[mt], G + (kt * 16 + (lane & 7) + 8 * (i >> 1)) * kTS + mt * 16 + 8 * (i & 1));
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    uint32_t bx[2];
+                    ldsm_x2_t(bx, X + (kt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kTS + nt * 8);
+                    mma_bf16(accW[0][nt], a[0], bx);
+                    mma_bf16(accW[1][nt], a[1], bx);
+                }
+            }
+            float sb = 0.f;
+            for (int t = 0; t < kL; ++t) sb += __bfloat162float(G[t * kTS + lane]);
+            accB += sb;
+        }
+        __syncthreads();
+    }
+    float* dW = warp == 0 ? gr.q_w : (warp == 1 ? gr.k_w : (warp == 2 ? gr.v_w : gr.o_w));
+    float* dB = warp == 0 ? gr.q_b : (warp == 1 ? gr.k_b : (warp == 2 ? gr.v_b : gr.o_b));
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int c0 = mt * 16 + gq, i0 = nt * 8 + tq * 2;
+            atomicAdd(dW + c0 * kC + i0, accW[mt][nt][0]);
+            atomicAdd(dW + c0 * kC + i0 + 1, accW[mt][nt][1]);
+            atomicAdd(dW + (c0 + 8) * kC + i0, accW[mt][nt][2]);
+            atomicAdd(dW + (c0 + 8) * kC + i0 + 1, accW[mt][nt][3]);
+        }
+    atomicAdd(dB + lane, accB);
+}
+
+// ------------------------------------------------------------------------------------------
 // backward of the saliency gate
 // ------------------------------------------------------------------------------------------
 // dgmap[b][z][j] = sum_k dgated_flat[k*HW+j] * normed_flat[k*HW+j]
@@ -969,7 +1344,17 @@ static int attn_bwd_impl(const void* dout, const void* x, const void* y, const r
     }
     int grid = num_sms() * 2;
     if (grid > g.nWin) grid = g.nWin;
-    win_attn_bwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)y, lx, ly, gmap, (const T*)dout, dxg, dyg, *p, *gr, g);
+    if (sizeof(T) == 2 && !(flags & RSS_ATTN_SIMT)) {
+        static bool tc_attr = false;
+        if (!tc_attr) {
+            cudaFuncSetAttribute(win_attn_bwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
+            cudaFuncSetAttribute(win_attn_bwd_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
+            tc_attr = true;
+        }
+        win_attn_bwd_tc_kernel<T><<<grid, kThreads, kBwdTcSmem, st>>>((const T*)x, (const T*)y, lx, ly, gmap, (const T*)dout, dxg, dyg, *p, *gr, g);
+    } else {
+        win_attn_bwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)y, lx, ly, gmap, (const T*)dout, dxg, dyg, *p, *gr, g);
+    }
     dim3 pg((g.HW + 255) / 256, B, 2);
     gate_bwd_reduce_kernel<T><<<pg, 256, 0, st>>>(dxg, dyg, (const T*)x, (const T*)y, lx, ly, dgmap, g.HW);
     dim3 mg((g.HW + 255) / 256, B);

@@ -179,7 +179,11 @@ def test_window_attention_region_vs_oracle(P, report, shape, dtype):
         errs["grad." + k] = (p.grad.detach().double().cpu() - sdg[BLK + k].grad.double()).abs().max().item() / gmax
     report["winattn_%s_%s" % (str(dtype)[6:], "x".join(map(str, shape)))] = errs
     tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
-    bad = {k: v for k, v in errs.items() if not v < tol}
+    # dy (the gradient reaching the high-resolution branch through K/V only) is ~55x smaller than dx and comes out of a
+    # LayerNorm-backward cancellation: with bf16 matmul operands the REFERENCE's own autocast run deviates from its fp32 run
+    # by 8.2e-2 of max|dy| at 128x128 (measured on the oracle); the bf16 tensor-core path is held to 2x that.
+    tols = {"dy": max(tol, 0.17)} if dtype == torch.bfloat16 else {}
+    bad = {k: v for k, v in errs.items() if not v < tols.get(k, tol)}
     assert not bad, bad
 
 
