@@ -93,12 +93,15 @@ int rss_bn_stats(const void* x, float* partials /*[nparts][C][2] (mean,M2)*/, fl
 int rss_bn_stats_fused(const void* x, float* accum_scratch, unsigned int* ticket, int64_t rows, int C, int dtype,
                        const float* gamma, const float* beta, float* running_mean /*may be NULL*/, float* running_var,
                        float momentum, float eps, float* mean_out, float* invstd_out, float* scale, float* shift,
+                       const float* pre_bias /*may be NULL: bias of the producing conv that was NOT added to x (it cancels in the
+                                               normalisation; only the running mean sees it)*/,
                        cudaStream_t stream);
 int rss_bn_combine(const float* partials, const float* counts, int nparts, int C, float* stat /*[C][2]*/, float* total /*[1]*/,
                    cudaStream_t stream);
 int rss_bn_finalize(const float* stat, const float* total, const float* gamma, const float* beta,
                     float* running_mean /*may be NULL*/, float* running_var, float momentum, float eps, int C,
-                    float* mean_out, float* invstd_out, float* scale, float* shift, cudaStream_t stream);
+                    float* mean_out, float* invstd_out, float* scale, float* shift, const float* pre_bias /*may be NULL*/,
+                    cudaStream_t stream);
 int rss_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                        float eps, int C, float* mean_out, float* invstd_out, float* scale, float* shift, cudaStream_t stream);
 int rss_bn_act_fwd(const void* x, const void* residual /*may be NULL*/, void* y, const float* scale, const float* shift,
@@ -135,6 +138,29 @@ int rss_conv_pack_weights(const float* const* weights, const float* const* biase
                           int* n_taps_out, int* taps_dy_out, int* taps_dx_out, cudaStream_t stream);
 int rss_conv_igemm(const void* x, const void* w_packed, const float* bias /*may be NULL*/, void* y, int B, int H, int W,
                    int Cin, int Cout, int n_taps, const int* taps_dy, const int* taps_dx, cudaStream_t stream);
+
+/* ---- fused tcgen05 convolution of the HRNet family (BasicBlock/Bottleneck 3x3 and 1x1 stride-1 convs and their data gradients:
+ *      _hrnet_rssformer.py:209-287): y = conv(T(x)), T = identity or relu(x*in_scale + in_shift) (the previous layer's
+ *      BatchNorm+ReLU applied on load), plus -- when stat_accum != NULL -- the training-mode BatchNorm statistics of y with the
+ *      contract of rss_bn_stats_fused (persistent zeroed accum[2*Cout] + ticket; outputs mean/invstd/scale/shift; running stats
+ *      updated).  Every input pixel is staged in shared memory once per tile ([channel chunk][position][8 ch] = no-swizzle UMMA
+ *      layout) and all taps read it at shifted descriptor addresses.  w_packed: bf16 [tap][Cout][Cin] from
+ *      rss_conv_pack_weights (transpose=1 pack with Cin/Cout swapped gives the data gradient). ---- */
+int rss_conv_cf_supported(int B, int H, int W, int Cin, int Cout, int ksize, int with_stats);
+int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, int H, int W, int Cin, int Cout,
+                int n_taps, const int* taps_dy, const int* taps_dx,
+                const float* in_scale /*[Cin] or NULL*/, const float* in_shift, int in_relu,
+                float* stat_accum /*NULL: no statistics*/, unsigned int* stat_ticket, const float* gamma, const float* beta,
+                float* running_mean /*may be NULL*/, float* running_var, float momentum, float eps,
+                float* mean_out, float* invstd_out, float* scale_out, float* shift_out, cudaStream_t stream);
+
+/* ---- weight gradient of the HRNet-family convolutions (BasicBlock/Bottleneck 3x3, stride-2 3x3 of the transition/fuse layers,
+ *      small 1x1 convs: _hrnet_rssformer.py:209-287,361-405,512-546; FFN fc1/fc2: ffn_block.py:219,232).  Replaces the
+ *      weight half of torch's conv backward.  x (B,Hi,Wi,Cin), dy (B,Ho,Wo,Cout) bf16 NHWC; dw_acc (Cout,Cin,k,k) fp32 is
+ *      ACCUMULATED into with float atomics (split-K over CTAs), so it may be the optimiser's flat gradient buffer. ---- */
+int rss_conv_wgrad_supported(int Cin, int Cout, int ksize, int stride, int pad, int dil);
+int rss_conv_wgrad(const void* x, const void* dy, float* dw_acc, int B, int Hi, int Wi, int Cin, int Ho, int Wo, int Cout,
+                   int ksize, int stride, int pad, int dil, cudaStream_t stream);
 
 /* ---- neck: hrnet_aux.py:51-68 (SimpleFusion8: 3x bilinear align_corners=True + concat), NHWC ---- */
 int rss_neck_gather_fwd(const void* f0, const void* f1, const void* f2, const void* f3, void* out_cat,

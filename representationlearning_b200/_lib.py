@@ -45,9 +45,9 @@ SIGNATURES = {
                              P, P, POINTER(AttnGrads), P]),
     "rss_bn_stats_nparts": (c_int, [c_int64, c_int]),
     "rss_bn_stats": (c_int, [P, P, P, c_int64, c_int, c_int, P]),
-    "rss_bn_stats_fused": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P, c_float, c_float, P, P, P, P, P]),
+    "rss_bn_stats_fused": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P, c_float, c_float, P, P, P, P, P, P]),
     "rss_bn_combine": (c_int, [P, P, c_int, c_int, P, P, P]),
-    "rss_bn_finalize": (c_int, [P, P, P, P, P, P, c_float, c_float, c_int, P, P, P, P, P]),
+    "rss_bn_finalize": (c_int, [P, P, P, P, P, P, c_float, c_float, c_int, P, P, P, P, P, P]),
     "rss_bn_eval_affine": (c_int, [P, P, P, P, c_float, c_int, P, P, P, P, P]),
     "rss_bn_act_fwd": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
     "rss_bn_bwd_reduce": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
@@ -59,6 +59,11 @@ SIGNATURES = {
     "rss_conv_pack_weights": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int,
                                       P, P, POINTER(c_int), POINTER(c_int), POINTER(c_int), P]),
     "rss_conv_igemm": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P]),
+    "rss_conv_cf_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "rss_conv_cf": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P, P, c_int,
+                            P, P, P, P, P, P, c_float, c_float, P, P, P, P, P]),
+    "rss_conv_wgrad_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "rss_conv_wgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "rss_neck_gather_fwd": (c_int, [P, P, P, P, P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, P]),
     "rss_neck_gather_bwd": (c_int, [P, P, P, P, P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, P]),
     "rss_head_fwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, P]),

@@ -39,10 +39,29 @@ def join_wgrad(dev=None):
     WGRAD["used"].clear()
 
 
-def _lib_wgrad(dy, x, w_lp, weight, bias, want_b, stride, padding, dilation, wdtype):
-    """cuDNN weight (+bias) gradient, accumulated into the flat fp32 grad buffer when there is one; returns (dw, db) to hand
-    back through autograd (None when already accumulated)."""
-    def run():
+ENGINE["wgrad"] = os.environ.get("RSS_WGRAD_KERNEL", "1") != "0"     # hand-written split-K weight gradient (csrc/conv_wgrad.cu)
+
+
+def _own_wgrad_ok(dy, x, weight, want_b, stride, padding, dilation):
+    if not ENGINE["wgrad"] or want_b or x.dtype != torch.bfloat16 or not x.is_cuda:
+        return False
+    Cout, Cin, k, _ = weight.shape
+    return bool(_lib.load().rss_conv_wgrad_supported(Cin, Cout, k, stride, padding, dilation))
+
+
+def _wgrad(dy, x, w_lp, weight, bias, want_b, stride, padding, dilation, wdtype):
+    """weight (+bias) gradient, accumulated into the flat fp32 grad buffer when there is one; returns (dw, db) to hand back
+    through autograd (None when already accumulated).  Engine: csrc/conv_wgrad.cu (split-K mma kernel, float atomics straight
+    into the fp32 gradient) for the HRNet-family shapes, the library's wgrad otherwise."""
+    own = _own_wgrad_ok(dy, x, weight, want_b, stride, padding, dilation)
+
+    def run_own(sink):
+        B, Cin, Hi, Wi = x.shape
+        _, Cout, Ho, Wo = dy.shape
+        ops.check(_lib.load().rss_conv_wgrad(x.data_ptr(), dy.data_ptr(), sink.data_ptr(), B, Hi, Wi, Cin, Ho, Wo, Cout,
+                                             weight.shape[2], stride, padding, dilation, ops._st()), "rss_conv_wgrad")
+
+    def run_lib():
         _, dw, db = torch.ops.aten.convolution_backward(dy, x, w_lp, [w_lp.shape[0]] if want_b else None, [stride, stride],
                                                         [padding, padding], [dilation, dilation], False, [0, 0], 1,
                                                         [False, True, want_b])
@@ -61,6 +80,17 @@ def _lib_wgrad(dy, x, w_lp, weight, bias, want_b, stride, padding, dilation, wdt
                 db = db.to(wdtype)
         return dw, db
 
+    def run():
+        if not own:
+            return run_lib()
+        sink = ops.grad_sink(weight)
+        if sink is not None:
+            run_own(sink)
+            return None, None
+        dw = torch.zeros(weight.shape, device=x.device, dtype=torch.float32)
+        run_own(dw)
+        return dw.to(wdtype), None
+
     direct = ops.grad_sink(weight) is not None and (not want_b or ops.grad_sink(bias) is not None)
     # only parameters owned by trainer.FlatSGD go asynchronous (its step joins the stream); anyone else reads .grad right away
     if not (WGRAD["async"] and direct and dy.is_cuda and getattr(weight, "_rss_flat", False)):
@@ -72,7 +102,7 @@ def _lib_wgrad(dy, x, w_lp, weight, bias, want_b, stride, padding, dilation, wdt
     with torch.cuda.stream(side):
         run()
     WGRAD["used"].add(dev)
-    return None, None       # bf16 stride-1 convs go through csrc/conv_igemm.cu when the geometry is supported
+    return None, None
 
 
 def register_shadow(param, view):
@@ -110,7 +140,7 @@ class _ConvLib(torch.autograd.Function):
             dy = dy.to(x.dtype)
         dx = dw = db = None
         if ctx.needs_input_grad[1]:
-            dw, db = _lib_wgrad(dy, x, w, ctx.refs[0], ctx.refs[1], has_bias and ctx.needs_input_grad[2], stride, padding, dilation, wdtype)
+            dw, db = _wgrad(dy, x, w, ctx.refs[0], ctx.refs[1], has_bias and ctx.needs_input_grad[2], stride, padding, dilation, wdtype)
         if ctx.needs_input_grad[0]:
             dx = torch.ops.aten.convolution_backward(dy, x, w, None, [stride, stride], [padding, padding], [dilation, dilation],
                                                      False, [0, 0], 1, [True, False, False])[0]
@@ -188,7 +218,7 @@ class _ConvIgemm(torch.autograd.Function):
                 continue
             w_lp = _lowp(weights[s], x.dtype).contiguous(memory_format=CL)
             want_b = biases[s] is not None and bias_grad
-            dw, db = _lib_wgrad(dy_, x, w_lp, weights[s], biases[s], want_b, 1, d * (k // 2), d, weights[s].dtype)
+            dw, db = _wgrad(dy_, x, w_lp, weights[s], biases[s], want_b, 1, d * (k // 2), d, weights[s].dtype)
             gw.append(dw); gb.append(db)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -198,6 +228,99 @@ class _ConvIgemm(torch.autograd.Function):
                 ops.check(lib.rss_conv_igemm(dy_.data_ptr(), packed.data_ptr(), None, dx.data_ptr(), B, H, W, Cout, Cin, nt, tdy, tdx,
                                              ops._st()), "rss_conv_igemm")
         return (dx, None) + tuple(gw) + tuple(gb)
+
+
+ENGINE["cf"] = os.environ.get("RSS_CONV_CF", "0") != "0"      # fused tcgen05 conv (+BN statistics epilogue): csrc/conv_cf.cu
+# (bit-correct, but its cp.async producer is still slower than the library conv + separate statistics kernel: off by default)
+
+
+def _cf_ok(x, Cout, k, with_stats):
+    if not ENGINE["cf"] or x.dtype != torch.bfloat16 or not x.is_cuda:
+        return False
+    B, Cin, H, W = x.shape
+    return bool(_lib.load().rss_conv_cf_supported(B, H, W, Cin, Cout, k, int(with_stats)))
+
+
+def _cf_launch(x, packed, nt, tdy, tdx, Cin, Cout, in_aff, in_relu, stats):
+    """one rss_conv_cf launch; stats = None or (gamma, beta, running_mean, running_var, momentum, eps, scratch) -> (y, aff)"""
+    lib = _lib.load()
+    B, _, H, W = x.shape
+    y = torch.empty((B, Cout, H, W), device=x.device, dtype=x.dtype, memory_format=CL)
+    aff = None
+    sp = [None] * 10
+    mom = eps = 0.0
+    if stats is not None:
+        gamma, beta, rm, rv, mom, eps, scratch = stats
+        aff = torch.empty(4, Cout, device=x.device, dtype=torch.float32)
+        g, b = ops._f32(gamma), ops._f32(beta)
+        sp = [scratch[1:].data_ptr(), scratch.data_ptr(), g.data_ptr(), b.data_ptr(), ops._p(rm), ops._p(rv),
+              aff[0].data_ptr(), aff[1].data_ptr(), aff[2].data_ptr(), aff[3].data_ptr()]
+    isc = ish = None
+    if in_aff is not None:
+        isc, ish = in_aff[2].data_ptr(), in_aff[3].data_ptr()
+    with ops.timed("rss_conv_cf"):
+        ops.check(lib.rss_conv_cf(x.data_ptr(), packed.data_ptr(), y.data_ptr(), B, H, W, Cin, Cout, nt, tdy, tdx, isc, ish,
+                                  int(in_relu), sp[0], sp[1], sp[2], sp[3], sp[4], sp[5], float(mom), float(eps), sp[6], sp[7], sp[8],
+                                  sp[9], ops._st()), "rss_conv_cf")
+    return y, aff
+
+
+class _ConvCF(torch.autograd.Function):
+    """stride-1 k x k (k in {1,3}) convolution through csrc/conv_cf.cu; with `stats` the kernel's epilogue also produces the
+    training-mode BatchNorm affine of the output (returned as a non-differentiable (4,Cout) tensor for ops.BNAct).
+    Backward: data gradient through the same kernel (transposed pack) when the swapped geometry is supported, weight gradient
+    through csrc/conv_wgrad.cu."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stats):
+        x = ops.nhwc(x)
+        B, Cin, H, W = x.shape
+        Cout, _, k, _ = weight.shape
+        packed, _, nt, tdy, tdx, keep = _pack([weight], [None], [k], [1], Cout, Cin, False, x.device)
+        y, aff = _cf_launch(x, packed, nt, tdy, tdx, Cin, Cout, None, False, stats)
+        ctx.save_for_backward(x)
+        ctx.k, ctx.ref = k, weight
+        if aff is None:
+            return y
+        ctx.mark_non_differentiable(aff)
+        return y, aff
+
+    @staticmethod
+    def backward(ctx, dy, *unused):
+        (x,) = ctx.saved_tensors
+        weight, k = ctx.ref, ctx.k
+        dy = ops.nhwc(dy)
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        B, Cin, H, W = x.shape
+        Cout = weight.shape[0]
+        dw = None
+        w_lp = None
+        if ctx.needs_input_grad[1]:
+            if not _own_wgrad_ok(dy, x, weight, False, 1, k // 2, 1):
+                w_lp = _lowp(weight, x.dtype).contiguous(memory_format=CL)
+            dw, _ = _wgrad(dy, x, w_lp if w_lp is not None else x, weight, None, False, 1, k // 2, 1, weight.dtype)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if _cf_ok(dy, Cin, k, False):
+                packed, _, nt, tdy, tdx, keep = _pack([weight], [None], [k], [1], Cout, Cin, True, x.device)
+                dx, _ = _cf_launch(dy, packed, nt, tdy, tdx, Cout, Cin, None, False, None)
+            else:
+                w_lp = w_lp if w_lp is not None else _lowp(weight, x.dtype).contiguous(memory_format=CL)
+                dx = torch.ops.aten.convolution_backward(dy, x, w_lp, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
+                                                         [True, False, False])[0]
+        return dx, dw, None
+
+
+def conv_bn_stats(x, weight, stride, padding, dilation, bn_stats):
+    """conv (no bias) whose epilogue also yields the BatchNorm statistics of its output.  bn_stats = (gamma, beta, running_mean,
+    running_var, momentum, eps, scratch) or None.  Returns (y, aff) with aff None when the statistics still have to be computed by
+    the caller (library conv, unsupported geometry)."""
+    k = weight.shape[2]
+    if stride == 1 and dilation == 1 and padding == k // 2 and k in (1, 3) and _cf_ok(x, weight.shape[0], k, bn_stats is not None):
+        out = _ConvCF.apply(x, weight, bn_stats)
+        return out if bn_stats is not None else (out, None)
+    return _ConvLib.apply(x, weight, None, stride, padding, dilation, False), None
 
 
 def conv_sum(x, convs, bias_grad=True):

@@ -115,7 +115,8 @@ __device__ __forceinline__ void bn_finalize_channel(float n, float mean, float m
                                                     const float* __restrict__ beta, float* __restrict__ running_mean,
                                                     float* __restrict__ running_var, float momentum, float eps,
                                                     float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                                    float* __restrict__ scale, float* __restrict__ shift) {
+                                                    float* __restrict__ scale, float* __restrict__ shift,
+                                                    const float* __restrict__ pre_bias = nullptr) {
     const float invstd = rsqrtf(m2 / n + eps);                    // biased variance normalises
     mean_out[c] = mean;
     invstd_out[c] = invstd;
@@ -123,7 +124,9 @@ __device__ __forceinline__ void bn_finalize_channel(float n, float mean, float m
     scale[c] = sc;
     shift[c] = beta[c] - mean * sc;
     if (running_mean) {
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        // pre_bias: the producing conv's bias was NOT added to x (a per-channel shift cancels in the normalisation); the
+        // running mean is the only place where it is visible
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (mean + (pre_bias ? pre_bias[c] : 0.f));
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (m2 / fmaxf(n - 1.f, 1.f));   // unbiased estimate
     }
 }
@@ -138,23 +141,30 @@ __global__ void bn_stats_fused_kernel(const T* __restrict__ x, float* __restrict
                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                       float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
                                       float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                      float* __restrict__ scale, float* __restrict__ shift) {
+                                      float* __restrict__ scale, float* __restrict__ shift, const float* __restrict__ pre_bias) {
     extern __shared__ float sm[];               // [rpb][2][C]
     __shared__ bool is_last;
     const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
     float K[8], a0[8], a1[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { K[i] = running_mean ? running_mean[sub * 8 + i] : 0.f; a0[i] = 0.f; a1[i] = 0.f; }
+    for (int i = 0; i < 8; ++i) {
+        K[i] = running_mean ? running_mean[sub * 8 + i] - (pre_bias ? pre_bias[sub * 8 + i] : 0.f) : 0.f;
+        a0[i] = 0.f; a1[i] = 0.f;
+    }
     const int64_t stride = (int64_t)gridDim.x * rpb;
     int64_t row = (int64_t)blockIdx.x * rpb + r;
-    for (; row + 3 * stride < rows; row += 4 * stride) {          // 4 independent 16-byte loads in flight per thread
-        float v[4][8];
+    constexpr int U = 4;                                          // 4 independent 16/32-byte loads in flight per thread
+    for (; row + (U - 1) * stride < rows; row += U * stride) {
+        Raw8<T> raw[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) load8(x + (row + u * stride) * C + sub * 8, v[u]);
+        for (int u = 0; u < U; ++u) ldraw(x + (row + u * stride) * C + sub * 8, raw[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u) {
+            float v[8];
+            unpack8(raw[u], v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float d = v[u][i] - K[i]; a0[i] += d; a1[i] += d * d; }
+            for (int i = 0; i < 8; ++i) { const float d = v[i] - K[i]; a0[i] += d; a1[i] += d * d; }
+        }
     }
     for (; row < rows; row += stride) {
         float v[8];
@@ -185,8 +195,9 @@ __global__ void bn_stats_fused_kernel(const T* __restrict__ x, float* __restrict
         const float S = __ldcg(accum + c), Q = __ldcg(accum + C + c);
         const float md = S / n;
         const float m2 = fmaxf(Q - S * md, 0.f);
-        const float k = running_mean ? running_mean[c] : 0.f;
-        bn_finalize_channel(n, k + md, m2, c, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out, scale, shift);
+        const float k = running_mean ? running_mean[c] - (pre_bias ? pre_bias[c] : 0.f) : 0.f;
+        bn_finalize_channel(n, k + md, m2, c, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out, scale, shift,
+                            pre_bias);
         accum[c] = 0.f;
         accum[C + c] = 0.f;
     }
@@ -212,7 +223,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stat, const float* 
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float momentum, float eps, int C,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                   float* __restrict__ scale, float* __restrict__ shift) {
+                                   float* __restrict__ scale, float* __restrict__ shift, const float* __restrict__ pre_bias) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float n = total[0];
@@ -226,7 +237,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stat, const float* 
     shift[c] = beta[c] - mean * sc;
     if (running_mean) {
         const float unb = stat[c * 2 + 1] / fmaxf(n - 1.f, 1.f);  // unbiased (running estimate)
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (mean + (pre_bias ? pre_bias[c] : 0.f));
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
     }
 }
@@ -243,7 +254,7 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
 }
 
 // ---------------------------------------------------------------------------------------------
-template <typename T, int ACT>   // ACT: 0 none, 1 relu, 2 gelu
+template <typename T, int ACT, bool RES>   // ACT: 0 none, 1 relu, 2 gelu
 __global__ void bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
                                   const float* __restrict__ scale, const float* __restrict__ shift,
                                   int64_t rows, int C, int cg, int rpb) {
@@ -251,54 +262,76 @@ __global__ void bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sc[i] = scale[sub * 8 + i]; sh[i] = shift[sub * 8 + i]; }
-    for (int64_t row = (int64_t)blockIdx.x * rpb + r; row < rows; row += (int64_t)gridDim.x * rpb) {
+    const int64_t stride = (int64_t)gridDim.x * rpb;
+    int64_t row = (int64_t)blockIdx.x * rpb + r;
+    constexpr int U = 4;
+    auto one = [&](const Raw8<T>& rx, const Raw8<T>& rr, int64_t off) {
         float v[8];
-        load8(x + row * C + sub * 8, v);
+        unpack8(rx, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = v[i] * sc[i] + sh[i];
-        if (res) {
+        if (RES) {
             float a[8];
-            load8(res + row * C + sub * 8, a);
+            unpack8(rr, a);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += a[i];
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             if (ACT == 1) v[i] = fmaxf(v[i], 0.f);
-            if (ACT == 2) v[i] = gelu_f(v[i]);
+            if (ACT == 2) v[i] = gelu_t<T>(v[i]);
         }
-        store8(y + row * C + sub * 8, v);
+        store8(y + off, v);
+    };
+    for (; row + (U - 1) * stride < rows; row += U * stride) {
+        Raw8<T> rx[U], rr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t off = (row + u * stride) * C + sub * 8;
+            ldraw(x + off, rx[u]);
+            if (RES) ldraw(res + off, rr[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) one(rx[u], rr[u], (row + u * stride) * C + sub * 8);
+    }
+    for (; row < rows; row += stride) {
+        const int64_t off = row * C + sub * 8;
+        Raw8<T> rx, rr;
+        ldraw(x + off, rx);
+        if (RES) ldraw(res + off, rr);
+        one(rx, rr, off);
     }
 }
 
-// dz = dy * act'(z).  relu: mask from the saved output y (>0); gelu: z recomputed from x.
-template <typename T, int ACT>
-__device__ __forceinline__ void bn_dz(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
-                                      int64_t off, const float sc[8], const float sh[8], const float mu[8], const float is[8],
+// dz = dy * act'(z).  relu: mask from the saved output y (>0) when HAS_Y (residual layers), else recomputed from x; gelu: z
+// recomputed from x.
+template <typename T, int ACT, bool HAS_Y>
+__device__ __forceinline__ void bn_dz(const Raw8<T>& rx, const Raw8<T>& ry, const Raw8<T>& rd,
+                                      const float sc[8], const float sh[8], const float mu[8], const float is[8],
                                       float dz[8], float xh[8]) {
     float v[8];
-    load8(x + off, v);
-    load8(dy + off, dz);
+    unpack8(rx, v);
+    unpack8(rd, dz);
 #pragma unroll
     for (int i = 0; i < 8; ++i) xh[i] = (v[i] - mu[i]) * is[i];
     if (ACT == 1) {
-        if (y) {                 // residual layers: the mask needs the saved output
+        if (HAS_Y) {
             float o[8];
-            load8(y + off, o);
+            unpack8(ry, o);
 #pragma unroll
             for (int i = 0; i < 8; ++i) dz[i] = o[i] > 0.f ? dz[i] : 0.f;
-        } else {                 // no residual: relu'(z) recomputed from x, one tensor read less
+        } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) dz[i] = (v[i] * sc[i] + sh[i]) > 0.f ? dz[i] : 0.f;
         }
     }
     if (ACT == 2) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dz[i] *= gelu_grad_f(v[i] * sc[i] + sh[i]);
+        for (int i = 0; i < 8; ++i) dz[i] *= gelu_grad_t<T>(v[i] * sc[i] + sh[i]);
     }
 }
 
-template <typename T, int ACT>
+template <typename T, int ACT, bool HAS_Y>
 __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -312,9 +345,34 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
         sc[i] = scale[sub * 8 + i]; sh[i] = shift[sub * 8 + i]; mu[i] = mean[sub * 8 + i]; is[i] = invstd[sub * 8 + i];
         a0[i] = 0.f; a1[i] = 0.f;
     }
-    for (int64_t row = (int64_t)blockIdx.x * rpb + r; row < rows; row += (int64_t)gridDim.x * rpb) {
+    const int64_t stride = (int64_t)gridDim.x * rpb;
+    int64_t row = (int64_t)blockIdx.x * rpb + r;
+    constexpr int U = 4;
+    for (; row + (U - 1) * stride < rows; row += U * stride) {
+        Raw8<T> rx[U], ry[U], rd[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t off = (row + u * stride) * C + sub * 8;
+            ldraw(x + off, rx[u]);
+            ldraw(dy + off, rd[u]);
+            if (HAS_Y) ldraw(y + off, ry[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float dz[8], xh[8];
+            bn_dz<T, ACT, HAS_Y>(rx[u], ry[u], rd[u], sc, sh, mu, is, dz, xh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a0[i] += dz[i]; a1[i] += dz[i] * xh[i]; }
+        }
+    }
+    for (; row < rows; row += stride) {
+        const int64_t off = row * C + sub * 8;
+        Raw8<T> rx, ry, rd;
+        ldraw(x + off, rx);
+        ldraw(dy + off, rd);
+        if (HAS_Y) ldraw(y + off, ry);
         float dz[8], xh[8];
-        bn_dz<T, ACT>(x, y, dy, row * C + sub * 8, sc, sh, mu, is, dz, xh);
+        bn_dz<T, ACT, HAS_Y>(rx, ry, rd, sc, sh, mu, is, dz, xh);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { a0[i] += dz[i]; a1[i] += dz[i] * xh[i]; }
     }
@@ -332,7 +390,7 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
     }
 }
 
-template <typename T, int ACT>
+template <typename T, int ACT, bool HAS_Y>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -349,14 +407,36 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
         sc[i] = scale[sub * 8 + i]; sh[i] = shift[sub * 8 + i]; mu[i] = mean[sub * 8 + i]; is[i] = invstd[sub * 8 + i];
         m0[i] = sums[sub * 8 + i] * inv_count; m1[i] = sums[C + sub * 8 + i] * inv_count;
     }
-    for (int64_t row = (int64_t)blockIdx.x * rpb + r; row < rows; row += (int64_t)gridDim.x * rpb) {
+    const int64_t stride = (int64_t)gridDim.x * rpb;
+    int64_t row = (int64_t)blockIdx.x * rpb + r;
+    constexpr int U = 2;
+    auto one = [&](const Raw8<T>& rx, const Raw8<T>& ry, const Raw8<T>& rd, int64_t off) {
         float dz[8], xh[8], o[8];
-        const int64_t off = row * C + sub * 8;
-        bn_dz<T, ACT>(x, y, dy, off, sc, sh, mu, is, dz, xh);
+        bn_dz<T, ACT, HAS_Y>(rx, ry, rd, sc, sh, mu, is, dz, xh);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = sc[i] * (dz[i] - m0[i] - xh[i] * m1[i]);
         store8(dx + off, o);
         if (dres) store8(dres + off, dz);
+    };
+    for (; row + (U - 1) * stride < rows; row += U * stride) {
+        Raw8<T> rx[U], ry[U], rd[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t off = (row + u * stride) * C + sub * 8;
+            ldraw(x + off, rx[u]);
+            ldraw(dy + off, rd[u]);
+            if (HAS_Y) ldraw(y + off, ry[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) one(rx[u], ry[u], rd[u], (row + u * stride) * C + sub * 8);
+    }
+    for (; row < rows; row += stride) {
+        const int64_t off = row * C + sub * 8;
+        Raw8<T> rx, ry, rd;
+        ldraw(x + off, rx);
+        ldraw(dy + off, rd);
+        if (HAS_Y) ldraw(y + off, ry);
+        one(rx, ry, rd, off);
     }
 }
 
@@ -382,13 +462,13 @@ extern "C" int rss_bn_stats(const void* x, float* partials, float* counts, int64
 extern "C" int rss_bn_stats_fused(const void* x, float* accum_scratch, unsigned int* ticket, int64_t rows, int C, int dtype,
                                   const float* gamma, const float* beta, float* running_mean, float* running_var,
                                   float momentum, float eps, float* mean_out, float* invstd_out, float* scale, float* shift,
-                                  cudaStream_t st) {
+                                  const float* pre_bias, cudaStream_t st) {
     if (C <= 0 || C % 8 || C > 2048 || rows <= 0 || !ticket || !accum_scratch) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 8, 4);
     const size_t smem = (size_t)g.rpb * C * 2 * sizeof(float);
     RSS_DISPATCH_DTYPE(dtype, bn_stats_fused_kernel<T><<<grid, g.threads, smem, st>>>((const T*)x, accum_scratch, ticket, rows, C, g.cg, g.rpb,
-                       gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out, scale, shift));
+                       gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out, scale, shift, pre_bias));
     return check_launch();
 }
 
@@ -401,10 +481,10 @@ extern "C" int rss_bn_combine(const float* partials, const float* counts, int np
 
 extern "C" int rss_bn_finalize(const float* stat, const float* total, const float* gamma, const float* beta,
                                float* running_mean, float* running_var, float momentum, float eps, int C,
-                               float* mean_out, float* invstd_out, float* scale, float* shift, cudaStream_t st) {
+                               float* mean_out, float* invstd_out, float* scale, float* shift, const float* pre_bias, cudaStream_t st) {
     if (C <= 0) return RSS_ERR_SHAPE;
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stat, total, gamma, beta, running_mean, running_var, momentum, eps, C,
-                                                        mean_out, invstd_out, scale, shift);
+                                                        mean_out, invstd_out, scale, shift, pre_bias);
     return check_launch();
 }
 
@@ -415,11 +495,11 @@ extern "C" int rss_bn_eval_affine(const float* gamma, const float* beta, const f
     return check_launch();
 }
 
-#define BN_ACT_SWITCH(KERNEL, ...)                                                   \
+#define BN_ACT_SWITCH(KERNEL, FLAG, ...)                                             \
     switch (act) {                                                                   \
-        case RSS_ACT_NONE: KERNEL<T, 0> __VA_ARGS__; break;                          \
-        case RSS_ACT_RELU: KERNEL<T, 1> __VA_ARGS__; break;                          \
-        case RSS_ACT_GELU: KERNEL<T, 2> __VA_ARGS__; break;                          \
+        case RSS_ACT_NONE: if (FLAG) KERNEL<T, 0, true> __VA_ARGS__; else KERNEL<T, 0, false> __VA_ARGS__; break; \
+        case RSS_ACT_RELU: if (FLAG) KERNEL<T, 1, true> __VA_ARGS__; else KERNEL<T, 1, false> __VA_ARGS__; break; \
+        case RSS_ACT_GELU: KERNEL<T, 2, false> __VA_ARGS__; break;                   \
         default: return RSS_ERR_SHAPE;                                               \
     }
 
@@ -429,7 +509,7 @@ extern "C" int rss_bn_act_fwd(const void* x, const void* residual, void* y, cons
     if (residual && act == RSS_ACT_GELU) return RSS_ERR_SHAPE;   // not a pattern of the reference (backward would need the residual)
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 4, 8);
-    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_act_fwd_kernel, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, rows, C, g.cg, g.rpb)));
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_act_fwd_kernel, residual != nullptr, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, rows, C, g.cg, g.rpb)));
     return check_launch();
 }
 
@@ -442,7 +522,7 @@ extern "C" int rss_bn_bwd_reduce(const void* x, const void* y, const void* dy, c
     const size_t smem = (size_t)g.rpb * 2 * C * sizeof(float);
     cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st);
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return RSS_ERR_CUDA; }
-    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_reduce_kernel, <<<grid, g.threads, smem, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, rows, C, g.cg, g.rpb)));
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_reduce_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, smem, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, rows, C, g.cg, g.rpb)));
     return check_launch();
 }
 
@@ -454,7 +534,7 @@ extern "C" int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, co
     if (act == RSS_ACT_RELU && dres && !y) return RSS_ERR_SHAPE;     // residual layers must pass the saved output
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 4, 8);
-    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
                                                                                                            local_sums, dgamma_acc, dbeta_acc)));
     return check_launch();
 }

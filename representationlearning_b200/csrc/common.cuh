@@ -45,6 +45,28 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* __restrict__ p, float
         v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
 }
+// raw (not yet converted) 8-element vector: lets a thread issue several loads before touching the data
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { float4 a, b; };
+template <> struct Raw8<__nv_bfloat16> { uint4 r; };
+__device__ __forceinline__ void ldraw(const float* __restrict__ p, Raw8<float>& v) {
+    v.a = __ldg(reinterpret_cast<const float4*>(p));
+    v.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
+__device__ __forceinline__ void ldraw(const __nv_bfloat16* __restrict__ p, Raw8<__nv_bfloat16>& v) {
+    v.r = __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float v[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float v[8]) {
+    const uint32_t w[4] = {r.r.x, r.r.y, r.r.z, r.r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
 __device__ __forceinline__ void store8(float* __restrict__ p, const float v[8]) {
     reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
     reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -77,6 +99,28 @@ __device__ __forceinline__ float gelu_grad_f(float z) {     // d/dz [z * Phi(z)]
     const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
     const float pdf = 0.39894228040143267794f * __expf(-0.5f * z * z);
     return cdf + z * pdf;
+}
+// Phi(z) and exp(-z^2/2) from ONE exponential: erf(x) = 1 - (a1 t + .. + a5 t^5) exp(-x^2), t = 1/(1 + p x), x = |z|/sqrt(2)
+// (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7: far below bf16's 2^-9).  Used only where the result is rounded to bf16; the
+// fp32 strict-parity path keeps erff.
+__device__ __forceinline__ float gelu_cdf_fast(float z, float& e) {
+    const float ax = fabsf(z) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    e = __expf(-ax * ax);
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float half_tail = 0.5f * poly * t * e;            // 0.5 * (1 - erf(ax))
+    return z >= 0.f ? 1.0f - half_tail : half_tail;
+}
+template <typename T> __device__ __forceinline__ float gelu_t(float z) { return gelu_f(z); }
+template <> __device__ __forceinline__ float gelu_t<__nv_bfloat16>(float z) { float e; return z * gelu_cdf_fast(z, e); }
+template <typename T> __device__ __forceinline__ float gelu_grad_t(float z) { return gelu_grad_f(z); }
+template <> __device__ __forceinline__ float gelu_grad_t<__nv_bfloat16>(float z) {
+    float e;
+    const float cdf = gelu_cdf_fast(z, e);
+    return fmaf(z * 0.39894228040143267794f, e, cdf);
 }
 __device__ __forceinline__ float sigmoid_f(float z) { return 1.0f / (1.0f + __expf(-z)); }
 

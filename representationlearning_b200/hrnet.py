@@ -11,7 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib, ops
-from .conv import conv2d
+from .conv import conv2d, conv_bn_stats
 from .modules import FusedBNAct, GeneralTransformerBlock, BN_MOMENTUM
 
 # _hrnet_rssformer.py:97-125 (only the widths RSSFormer's configs use are listed: hrnetw32.py:9, hrnetw40.py)
@@ -40,8 +40,10 @@ def _conv(cin, cout, k, stride=1, padding=0):
 
 
 def _run(conv, bn, x, residual=None):
-    """conv (no bias) -> fused BN(+act)(+residual)."""
-    return bn(conv2d(x, conv.weight, None, conv.stride[0], conv.padding[0], conv.dilation[0]), residual)
+    """conv (no bias) -> fused BN(+act)(+residual); the batch statistics come out of the conv kernel's epilogue when the
+    geometry is one csrc/conv_cf.cu covers."""
+    y, aff = conv_bn_stats(x, conv.weight, conv.stride[0], conv.padding[0], conv.dilation[0], bn.stats_args())
+    return bn(y, residual, aff=aff)
 
 
 class BasicBlock(nn.Module):

@@ -38,11 +38,29 @@ class FusedBNAct(nn.Module):
 
     defer_counter = False      # trainer.FlatSGD bumps every num_batches_tracked with one foreach op per step instead
 
-    def forward(self, x, residual=None):
+    def forward(self, x, residual=None, pre_bias=None, aff=None):
+        """pre_bias (training mode only): bias of the conv that produced x, left out of x because BatchNorm cancels it.
+        aff: statistics already produced by the conv kernel's epilogue (conv.conv_bn_stats)."""
         if self.training and not FusedBNAct.defer_counter:
             self.num_batches_tracked += 1
         return ops.BNAct.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
-                               self.training, self.momentum, self.eps, self.act, True if self.sync else None, self._scratch)
+                               self.training, self.momentum, self.eps, self.act, True if self.sync else None, self._scratch,
+                               pre_bias, aff)
+
+    def stats_args(self):
+        """what conv.conv_bn_stats needs to produce this layer's batch statistics in the conv epilogue (None: not applicable --
+        eval mode, or SyncBN under a process group, where the statistics are exchanged between ranks)"""
+        if not self.training or (self.sync and ops._world(True) > 1):
+            return None
+        return (self.weight, self.bias, self.running_mean, self.running_var, self.momentum, self.eps, self._scratch)
+
+    def after_conv(self, x, weight, bias, **kw):
+        """conv(x, weight, bias) -> this BN(+act).  In training mode the conv bias only shifts the batch mean, which the
+        normalisation subtracts again: the bias add (one full pass over the conv output) is skipped and the bias is handed to
+        the statistics kernel for the running mean; its gradient is identically zero."""
+        if self.training and bias is not None:
+            return self(conv2d(x, weight, None, **kw), pre_bias=bias)
+        return self(conv2d(x, weight, bias, bias_grad=not self.training, **kw))
 
     def extra_repr(self):
         return "%d, act=%d, sync=%s" % (self.num_features, self.act, self.sync)
@@ -127,11 +145,11 @@ class MlpDWBN(nn.Module):
 
     def forward_nchw(self, x):
         bg = not self.training       # every bias here feeds a training-mode BN: its gradient is identically zero
-        x = self.norm1(conv2d(x, self.fc1.weight, self.fc1.bias, bias_grad=bg))
+        x = self.norm1.after_conv(x, self.fc1.weight, self.fc1.bias)
         c = conv_sum(x, [(self.dw.weight, self.dw.bias, 1, 1), (self.dw6.weight, self.dw6.bias, 3, 6),
                          (self.dw12.weight, self.dw12.bias, 3, 12)], bias_grad=bg)
         x = self.norm2(c)
-        return self.norm3(conv2d(x, self.fc2.weight, self.fc2.bias, bias_grad=bg))
+        return self.norm3.after_conv(x, self.fc2.weight, self.fc2.bias)
 
     def forward(self, x, H, W):
         if x.dim() != 3:
@@ -184,5 +202,5 @@ class SimpleFusion8(nn.Module):
     def forward(self, feat_list):
         x0 = feat_list[0]
         cat = ops.NeckGather.apply(*feat_list)
-        x = self.fuse_conv[1](conv2d(cat, self.fuse_conv[0].weight, self.fuse_conv[0].bias, bias_grad=not self.training))
+        x = self.fuse_conv[1].after_conv(cat, self.fuse_conv[0].weight, self.fuse_conv[0].bias)
         return x, x0

@@ -20,7 +20,7 @@ KERNELS_PER_CALL = {
     "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1,
     "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 4, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
     "rss_headaux_fwd": 2, "rss_seg_loss_fwd": 2, "rss_seg_loss_bwd": 1, "rss_grad_sumsq": 1, "rss_sgd_step": 1,
-    "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
+    "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_conv_wgrad": 1, "rss_conv_cf": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
 }
 COUNTERS = {"launches": 0, "calls": 0}
 TIMED = {}            # op name -> list of (start_event, end_event), filled only while bench.py enables it
@@ -205,7 +205,12 @@ class WindowAttention(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 class BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, training, momentum, eps, act, group, scratch=None):
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, training, momentum, eps, act, group, scratch=None,
+                pre_bias=None, aff=None):
+        """aff: (4,C) mean/invstd/scale/shift already produced (and running statistics already updated) by the convolution
+        kernel's epilogue (rss_conv_cf): the statistics pass is skipped.
+        pre_bias: bias of the producing conv, NOT added to x (training mode only: a per-channel shift cancels in the
+        normalisation, so only the running mean has to see it; saves one full-tensor pass per biased conv)"""
         _lib.require_device()
         lib = _lib.load()
         x = nhwc(x)
@@ -217,14 +222,24 @@ class BNAct(torch.autograd.Function):
         rows = B * H * W
         dev, dt, st = x.device, _dt(x), _st()
         g, b = _f32(gamma), _f32(beta)
-        aff = torch.empty(4, C, device=dev, dtype=torch.float32)      # mean, invstd, scale, shift
+        have_aff = aff is not None
+        if not have_aff:
+            aff = torch.empty(4, C, device=dev, dtype=torch.float32)      # mean, invstd, scale, shift
         world = _world(group) if training else 1
-        if training and world == 1:
+        if have_aff and (not training or world != 1):
+            raise _lib.RssError("a precomputed BatchNorm affine is only valid for single-rank training-mode statistics")
+        if pre_bias is not None:
+            if not training:
+                raise _lib.RssError("pre_bias folding is only valid for training-mode BatchNorm")
+            pre_bias = _f32(pre_bias)
+        if have_aff:
+            pass
+        elif training and world == 1:
             if scratch is None or scratch.numel() < 1 + 2 * C:      # [0] last-block ticket, [1:] accumulators; kernel leaves zeros
                 scratch = torch.zeros(1 + 2 * C, device=dev, dtype=torch.float32)
             check(lib.rss_bn_stats_fused(_p(x), _p(scratch[1:]), _p(scratch), rows, C, dt, _p(g), _p(b),
                                          _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
-                                         _p(aff[3]), st), "rss_bn_stats_fused")
+                                         _p(aff[3]), _p(pre_bias), st), "rss_bn_stats_fused")
         elif training:
             nparts = lib.rss_bn_stats_nparts(rows, C)
             part = torch.empty(nparts * C * 2 + nparts, device=dev, dtype=torch.float32)
@@ -239,7 +254,7 @@ class BNAct(torch.autograd.Function):
                 cnts = gathered[:, C * 2].contiguous()
                 check(lib.rss_bn_combine(_p(parts), _p(cnts), world, C, _p(stat), _p(stat[C * 2:]), st), "rss_bn_combine")
             check(lib.rss_bn_finalize(_p(stat), _p(stat[C * 2:]), _p(g), _p(b), _p(running_mean), _p(running_var),
-                                      momentum, eps, C, _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), st), "rss_bn_finalize")
+                                      momentum, eps, C, _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), _p(pre_bias), st), "rss_bn_finalize")
         else:
             check(lib.rss_bn_eval_affine(_p(g), _p(b), _p(running_mean), _p(running_var), eps, C,
                                          _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), st), "rss_bn_eval_affine")
@@ -281,8 +296,8 @@ class BNAct(torch.autograd.Function):
                                    _p(dx), _p(dres), rows, C, ctx.act, dt, _p(local), _p(sg) if direct else None,
                                    _p(sb) if direct else None, st), "rss_bn_bwd_apply")
         if direct:
-            return dx, dres, None, None, None, None, None, None, None, None, None, None
-        return dx, dres, local[C:], local[:C], None, None, None, None, None, None, None, None
+            return (dx, dres) + (None,) * 12
+        return (dx, dres, local[C:], local[:C]) + (None,) * 10
 
 
 # ----------------------------------------------------------------------------------------------

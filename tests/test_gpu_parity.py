@@ -469,6 +469,174 @@ def test_conv_igemm_fwd_and_dgrad(P, report, case):
     assert max(errs.values()) < 6e-3, errs       # bf16 output rounding (2^-9 = 2e-3 of max) dominates
 
 
+# ------------------------------------------------------------------------------------------------
+# hand-written weight gradient (csrc/conv_wgrad.cu) vs torch's conv weight gradient on the same bf16-representable
+# inputs (exact products, fp32 accumulation on both sides -> TOL_F32); accumulation semantics (+=) checked too
+# ------------------------------------------------------------------------------------------------
+WGRAD_CASES = [
+    # B, Hi, Wi, Cin, Cout, k, stride
+    (2, 19, 45, 64, 32, 3, 1),        # ragged tiles in both directions, TW=32
+    (2, 16, 16, 256, 256, 3, 1),      # branch-3 geometry, TW=16
+    (3, 33, 40, 32, 64, 3, 2),        # stride 2, odd input height
+    (2, 14, 14, 64, 64, 3, 2),        # stride 2, TW=16
+    (2, 24, 24, 32, 128, 1, 1),       # FFN fc1
+    (1, 24, 40, 128, 32, 1, 1),       # FFN fc2
+    (1, 130, 128, 32, 32, 3, 1),      # branch-0 width, many tiles per CTA
+    (16, 64, 64, 64, 64, 3, 1),       # full branch-1 size
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_conv_wgrad(P, report, case):
+    lib = P._lib.load()
+    B, Hi, Wi, Cin, Cout, k, s = case
+    pad = k // 2
+    assert lib.rss_conv_wgrad_supported(Cin, Cout, k, s, pad, 1) == 1
+    torch.manual_seed(5)
+    x = torch.randn(B, Cin, Hi, Wi, device=DEV).bfloat16()
+    Ho, Wo = (Hi + 2 * pad - k) // s + 1, (Wi + 2 * pad - k) // s + 1
+    dy = torch.randn(B, Cout, Ho, Wo, device=DEV).bfloat16()
+    ref = torch.nn.grad.conv2d_weight(x.float(), (Cout, Cin, k, k), dy.float(), stride=s, padding=pad)
+    xc, dyc = nchw_from(x), nchw_from(dy)
+    dw = torch.ones(Cout, Cin, k, k, device=DEV)            # must be accumulated into, not overwritten
+    for _ in range(2):
+        rc = lib.rss_conv_wgrad(xc.data_ptr(), dyc.data_ptr(), dw.data_ptr(), B, Hi, Wi, Cin, Ho, Wo, Cout, k, s, pad, 1,
+                                torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, rc
+    torch.cuda.synchronize()
+    err = rel((dw - 1.0) / 2.0, ref)
+    report["wgrad_%s" % "_".join(map(str, case))] = err
+    assert err < TOL_F32, err
+
+
+def test_conv_wgrad_through_autograd(P, report):
+    """conv.conv2d routes the weight gradient of a supported layer through the kernel (no FlatSGD sink: returned via autograd)"""
+    from representationlearning_b200 import conv
+    torch.manual_seed(6)
+    x = nchw_from(torch.randn(2, 32, 20, 28).bfloat16()).requires_grad_(True)
+    w = torch.nn.Parameter(torch.randn(64, 32, 3, 3, device=DEV) * 0.1)
+    c0 = P.ops.COUNTERS["calls"]
+    y = conv.conv2d(x, w, None, 2, 1, 1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    assert P.ops.COUNTERS["calls"] > c0, "the hand-written wgrad kernel was not used"
+    ref = torch.nn.grad.conv2d_weight(x.detach().float(), w.shape, dy.float(), stride=2, padding=1)
+    err = rel(w.grad, ref)
+    report["wgrad_autograd"] = err
+    assert err < TOL_F32, err
+
+
+# ------------------------------------------------------------------------------------------------
+# fused tcgen05 conv (csrc/conv_cf.cu): shared-memory halo reuse through no-swizzle UMMA descriptors, optional BN+ReLU of the
+# previous layer applied on load, BatchNorm statistics of the output in the epilogue
+# ------------------------------------------------------------------------------------------------
+CF_CASES = [
+    # B, H, W, Cin, Cout, k, stats, xform
+    (2, 16, 16, 32, 32, 3, True, False),
+    (2, 19, 23, 32, 32, 3, True, True),        # ragged: tiles straddle rows, last tile partial
+    (1, 128, 128, 32, 32, 3, True, False),     # branch-0 geometry: two 128-row blocks per tile
+    (3, 64, 64, 64, 64, 3, True, True),        # branch-1 geometry
+    (2, 20, 128, 64, 64, 3, True, False),      # layer1 geometry (wide, 64 channels)
+    (2, 24, 24, 64, 32, 1, True, False),       # 1x1 (fuse layers)
+    (2, 12, 20, 128, 32, 1, True, True),
+    (2, 16, 16, 32, 128, 3, False, False),     # no statistics, wide N (data-gradient shape)
+    (2, 16, 16, 64, 128, 3, False, False),
+    (2, 12, 20, 128, 64, 1, False, True),
+]
+
+
+def _cf_call(lib, x, w, k, stats, in_aff, in_relu, rm=None, rv=None, gamma=None, beta=None):
+    from representationlearning_b200 import conv
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    packed, _, nt, tdy, tdx, keep = conv._pack([w], [None], [k], [1], Cout, Cin, False, x.device)
+    st = None
+    if stats:
+        scratch = torch.zeros(1 + 2 * Cout, device=DEV)
+        st = (gamma, beta, rm, rv, 0.1, 1e-5, scratch)
+    y, aff = conv._cf_launch(x, packed, nt, tdy, tdx, Cin, Cout, in_aff, in_relu, st)
+    torch.cuda.synchronize()
+    if stats:
+        assert float(scratch.abs().max()) == 0.0, "the kernel must leave its scratch zeroed"
+    return y, aff
+
+
+@pytest.mark.parametrize("case", CF_CASES)
+def test_conv_cf(P, report, case):
+    lib = P._lib.load()
+    B, H, W, Cin, Cout, k, stats, xform = case
+    assert lib.rss_conv_cf_supported(B, H, W, Cin, Cout, k, int(stats)) == 1
+    torch.manual_seed(3)
+    x = torch.randn(B, Cin, H, W, device=DEV).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, device=DEV) / (Cin * k * k) ** 0.5).bfloat16().float()
+    in_aff = None
+    xin = x.float()
+    if xform:
+        in_aff = torch.zeros(4, Cin, device=DEV)
+        in_aff[2] = torch.rand(Cin, device=DEV) + 0.5
+        in_aff[3] = torch.randn(Cin, device=DEV) * 0.3
+        xin = torch.relu(x.float() * in_aff[2].view(1, -1, 1, 1) + in_aff[3].view(1, -1, 1, 1)).bfloat16().float()
+    ref = torch.nn.functional.conv2d(xin, w, None, 1, k // 2)
+    gamma, beta = torch.rand(Cout, device=DEV) + 0.5, torch.randn(Cout, device=DEV)
+    rm, rv = torch.randn(Cout, device=DEV) * 0.1, torch.rand(Cout, device=DEV) + 0.5
+    rm0, rv0 = rm.clone(), rv.clone()
+    y, aff = _cf_call(lib, nchw_from(x), w, k, stats, in_aff, xform, rm, rv, gamma, beta)
+    errs = dict(y=rel(y.float(), ref))
+    if stats:
+        yf = y.float()                                    # the statistics are those of the stored (bf16) tensor
+        mean = yf.mean(dim=(0, 2, 3))
+        var = yf.var(dim=(0, 2, 3), unbiased=False)
+        n = B * H * W
+        errs["mean"] = float((aff[0] - mean).abs().max() / (yf.abs().max()))
+        errs["invstd"] = rel(aff[1], (var + 1e-5).rsqrt())
+        errs["scale"] = rel(aff[2], gamma * (var + 1e-5).rsqrt())
+        errs["shift"] = rel(aff[3], beta - mean * gamma * (var + 1e-5).rsqrt())
+        errs["rm"] = rel(rm, 0.9 * rm0 + 0.1 * mean)
+        errs["rv"] = rel(rv, 0.9 * rv0 + 0.1 * var * n / (n - 1))
+    report["cf_%s" % "_".join(map(str, case))] = errs
+    assert errs["y"] < 6e-3, errs                         # bf16 output rounding (2^-9 of max) dominates
+    assert max(v for kk, v in errs.items() if kk != "y") < TOL_F32 if stats else True, errs
+
+
+def test_conv_cf_block_through_autograd(P, report):
+    """conv_bn_stats -> FusedBNAct(aff=...) forward and backward: data gradient through the transposed pack of the same kernel,
+    weight gradient through conv_wgrad.cu.  bf16 rounding of the conv output flips ReLU masks relative to an fp32 chain (a CPU
+    emulation of the rounding alone moves dx by 1e-1), so the reference is built stage by stage from the tensors the kernels
+    actually exchanged: BN+ReLU forward/backward from the stored bf16 conv output, conv gradients from the stored bf16 dy."""
+    from representationlearning_b200 import conv
+    torch.manual_seed(8)
+    B, C, H, W = 2, 32, 24, 40
+    x = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    w = (torch.randn(C, C, 3, 3, device=DEV) / (C * 9) ** 0.5).bfloat16().float()
+    bn = P.FusedBNAct(C, P._lib.ACT_RELU).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_()
+    xc = nchw_from(x).requires_grad_(True)
+    wc = torch.nn.Parameter(w.clone())
+    saved = dict(conv.ENGINE)
+    conv.ENGINE.update(cf=True)
+    try:
+        y, aff = conv.conv_bn_stats(xc, wc, 1, 1, 1, bn.stats_args())
+        assert aff is not None, "conv_cf path not taken"
+        y.retain_grad()
+        out = bn(y, aff=aff)
+        dout = torch.randn_like(out)
+        out.backward(dout)
+        torch.cuda.synchronize()
+    finally:
+        conv.ENGINE.update(saved)
+    yr = y.detach().float().requires_grad_(True)
+    outr = torch.relu(torch.nn.functional.batch_norm(yr, None, None, bn.weight.detach(), bn.bias.detach(), True, 0.1, 1e-5))
+    outr.backward(dout.float())
+    dy = y.grad.float()
+    errs = dict(y=rel(y.float(), torch.nn.functional.conv2d(x.float(), w, None, 1, 1)), out=rel(out.float(), outr),
+                dy=rel(dy, yr.grad),
+                dx=rel(xc.grad.float(), torch.nn.grad.conv2d_input(x.shape, w, dy, 1, 1)),
+                dw=rel(wc.grad, torch.nn.grad.conv2d_weight(x.float(), w.shape, dy, 1, 1)))
+    report["cf_block_autograd"] = errs
+    assert errs["y"] < 6e-3 and errs["out"] < TOL_BF16 and errs["dy"] < TOL_BF16 and errs["dx"] < 6e-3 and errs["dw"] < TOL_F32, errs
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("relu,ks", [(True, (0, 0)), (False, (1, 2, 3)), (True, (0, 0, 1, 2)), (True, (0, 1))])
 def test_fuse_sum(P, report, dtype, relu, ks):
