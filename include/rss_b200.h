@@ -117,6 +117,22 @@ int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, const float* 
                      const float* local_sums /*this rank's sums (== sums without SyncBN)*/,
                      float* dgamma_acc /*may be NULL*/, float* dbeta_acc, cudaStream_t stream);
 
+/* One-launch versions for activations that stay L2-resident between the two passes (<= 40 MB, ReLU / no activation):
+ * statistics -> device-wide spin barrier -> apply, and reduce -> barrier -> apply.  Grid <= one block per SM, >= 4 resident blocks
+ * per SM, so up to 4 concurrent streams can each hold a full grid.  accum_scratch: persistent zeroed float[2*C]; sync_scratch:
+ * persistent zeroed unsigned[2]; both are left zeroed.  Single rank only (SyncBN under a process group keeps the split kernels). */
+int rss_bn_fused_supported(int64_t rows, int C, int act, int dtype);
+int rss_bn_fwd_fused(const void* x, const void* residual /*may be NULL*/, void* y, float* accum_scratch, unsigned int* sync_scratch,
+                     int64_t rows, int C, int act, int dtype, const float* gamma, const float* beta,
+                     float* running_mean /*may be NULL*/, float* running_var, float momentum, float eps,
+                     float* mean_out, float* invstd_out, float* scale, float* shift, const float* pre_bias /*may be NULL*/,
+                     cudaStream_t stream);
+int rss_bn_bwd_fused(const void* x, const void* y /*saved output, residual ReLU layers only*/, const void* dy,
+                     const float* scale, const float* shift, const float* mean, const float* invstd,
+                     float* accum_scratch, unsigned int* sync_scratch, void* dx, void* dresidual /*may be NULL*/,
+                     int64_t rows, int C, int act, int dtype, float* sums_out /*[2C] or NULL*/,
+                     float* dgamma_acc /*may be NULL*/, float* dbeta_acc, cudaStream_t stream);
+
 /* ---- multi-resolution fuse sum of HighResolutionModule.forward (_hrnet_rssformer.py:418-435) and the residual+ReLU closing a
  *      transformer block (MTFM.py:109, _hrnet_rssformer.py:435): out = [relu](sum_j nearest_up_{2^k_j}(term_j)), NHWC ---- */
 int rss_fuse_sum_fwd(const void* const* terms, const int* log2_up, int n_terms /*1..4*/, void* out, int B, int H, int W, int C,
@@ -161,6 +177,13 @@ int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, int H, int 
 int rss_conv_wgrad_supported(int Cin, int Cout, int ksize, int stride, int pad, int dil);
 int rss_conv_wgrad(const void* x, const void* dy, float* dw_acc, int B, int Hi, int Wi, int Cin, int Ho, int Wo, int Cout,
                    int ksize, int stride, int pad, int dil, cudaStream_t stream);
+
+/* tcgen05 version for the stride-1 layers (3x3 pad 1, 1x1): both operands staged by TMA as zero-padded rows in the MN-major
+ * 128B-swizzled UMMA layout (positions = K), taps = row shifts of the X operand, accumulators in TMEM, split-K over CTAs.
+ * in_scale/in_shift/in_relu: optional relu(x*scale+shift) applied to x on load (BatchNorm+ReLU of a tensor never materialised). */
+int rss_conv_wgrad_tc_supported(int B, int H, int W, int Cin, int Cout, int ksize);
+int rss_conv_wgrad_tc(const void* x, const void* dy, float* dw_acc, int B, int H, int W, int Cin, int Cout, int ksize,
+                      const float* in_scale /*[Cin] or NULL*/, const float* in_shift, int in_relu, cudaStream_t stream);
 
 /* ---- neck: hrnet_aux.py:51-68 (SimpleFusion8: 3x bilinear align_corners=True + concat), NHWC ---- */
 int rss_neck_gather_fwd(const void* f0, const void* f1, const void* f2, const void* f3, void* out_cat,

@@ -52,6 +52,9 @@ SIGNATURES = {
     "rss_bn_act_fwd": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
     "rss_bn_bwd_reduce": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
     "rss_bn_bwd_apply": (c_int, [P, P, P, P, P, P, P, P, c_float, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
+    "rss_bn_fused_supported": (c_int, [c_int64, c_int, c_int, c_int]),
+    "rss_bn_fwd_fused": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P, c_float, c_float, P, P, P, P, P, P]),
+    "rss_bn_bwd_fused": (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
     "rss_fuse_sum_fwd": (c_int, [POINTER(c_void_p), POINTER(c_int), c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "rss_fuse_sum_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "rss_conv_igemm_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
@@ -64,6 +67,8 @@ SIGNATURES = {
                             P, P, P, P, P, P, c_float, c_float, P, P, P, P, P]),
     "rss_conv_wgrad_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "rss_conv_wgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "rss_conv_wgrad_tc_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "rss_conv_wgrad_tc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P]),
     "rss_neck_gather_fwd": (c_int, [P, P, P, P, P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, P]),
     "rss_neck_gather_bwd": (c_int, [P, P, P, P, P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, P]),
     "rss_head_fwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, P]),

@@ -42,10 +42,32 @@ def join_wgrad(dev=None):
 ENGINE["wgrad"] = os.environ.get("RSS_WGRAD_KERNEL", "1") != "0"     # hand-written split-K weight gradient (csrc/conv_wgrad.cu)
 
 
+# tcgen05 split-K weight gradient (csrc/conv_wgrad_tc.cu): bit-correct, but every M128 x N<=128 x K16 MMA costs ~350-400 cycles of
+# operand fetch (profiles/wgrad_microbench_r1.json), which makes it slower than both other engines on these layers: off by default
+ENGINE["wgrad_tc"] = os.environ.get("RSS_WGRAD_TC", "0") != "0"
+# per-shape policy for the mma.sync kernel from the same microbench (ncu kernel durations, B=16): it beats the library's wgrad +
+# the separate fp32 accumulate on the 32->32 3x3 layers of branch 0 (31.7 vs 47.6+8 us) and on the small 1x1 fuse convs
+# (10.8 vs 25.6 us); elsewhere the re-reads of X/dY per 32x32 channel block lose against the library kernel
+ENGINE["wgrad_policy"] = os.environ.get("RSS_WGRAD_POLICY", "measured")
+
+
+def _tc_wgrad_ok(x, weight, stride, padding, dilation):
+    Cout, Cin, k, _ = weight.shape
+    if not ENGINE["wgrad_tc"] or stride != 1 or dilation != 1 or padding != k // 2:
+        return False
+    B, _, H, W = x.shape
+    return bool(_lib.load().rss_conv_wgrad_tc_supported(B, H, W, Cin, Cout, k))
+
+
 def _own_wgrad_ok(dy, x, weight, want_b, stride, padding, dilation):
     if not ENGINE["wgrad"] or want_b or x.dtype != torch.bfloat16 or not x.is_cuda:
         return False
     Cout, Cin, k, _ = weight.shape
+    if _tc_wgrad_ok(x, weight, stride, padding, dilation):
+        return True
+    if ENGINE["wgrad_policy"] == "measured":
+        if not ((k == 3 and stride == 1 and Cin == 32 and Cout == 32) or (k == 1 and Cin * Cout <= 64 * 32)):
+            return False
     return bool(_lib.load().rss_conv_wgrad_supported(Cin, Cout, k, stride, padding, dilation))
 
 
@@ -58,6 +80,10 @@ def _wgrad(dy, x, w_lp, weight, bias, want_b, stride, padding, dilation, wdtype)
     def run_own(sink):
         B, Cin, Hi, Wi = x.shape
         _, Cout, Ho, Wo = dy.shape
+        if _tc_wgrad_ok(x, weight, stride, padding, dilation):
+            ops.check(_lib.load().rss_conv_wgrad_tc(x.data_ptr(), dy.data_ptr(), sink.data_ptr(), B, Hi, Wi, Cin, Cout, weight.shape[2],
+                                                    None, None, 0, ops._st()), "rss_conv_wgrad_tc")
+            return
         ops.check(_lib.load().rss_conv_wgrad(x.data_ptr(), dy.data_ptr(), sink.data_ptr(), B, Hi, Wi, Cin, Ho, Wo, Cout,
                                              weight.shape[2], stride, padding, dilation, ops._st()), "rss_conv_wgrad")
 
@@ -253,7 +279,7 @@ def _cf_launch(x, packed, nt, tdy, tdx, Cin, Cout, in_aff, in_relu, stats):
         gamma, beta, rm, rv, mom, eps, scratch = stats
         aff = torch.empty(4, Cout, device=x.device, dtype=torch.float32)
         g, b = ops._f32(gamma), ops._f32(beta)
-        sp = [scratch[1:].data_ptr(), scratch.data_ptr(), g.data_ptr(), b.data_ptr(), ops._p(rm), ops._p(rv),
+        sp = [scratch[2:].data_ptr(), scratch.data_ptr(), g.data_ptr(), b.data_ptr(), ops._p(rm), ops._p(rv),
               aff[0].data_ptr(), aff[1].data_ptr(), aff[2].data_ptr(), aff[3].data_ptr()]
     isc = ish = None
     if in_aff is not None:

@@ -15,10 +15,14 @@
 //     ABSOLUTE shared-memory address bits [7,10), so a start address on any 128-byte row works with base_offset = 0 (setting
 //     base_offset = (start >> 7) & 7 produces garbage).  (A first version used the no-swizzle "interleave" layout, whose shifts need no
 //     phase at all; it was bit-correct but its operand fetch ran at ~16 B/cycle: ~450 cycles per M128xN32xK16 MMA.)
-//   * 4 producer warps fill the tile with cp.async (zero fill = padding), optionally apply the previous layer's BN+ReLU in
-//     place, fence to the async proxy and arrive on the stage's mbarrier; one thread issues tcgen05.mma (M=128 rows = 128
-//     consecutive positions, N = Cout, K = 16 channels) for every tap; 4 epilogue warps drain TMEM (tcgen05.ld), round to
-//     bf16, store, and keep per-thread running sums of (y-K), (y-K)^2 per channel for the whole persistent loop.
+//   * the tile is staged by ONE TMA box load per 64-channel plane: whole padded rows {64 ch, W+2 pixels from x=-1, NR rows from
+//     y=r_lo} -- TMA's out-of-bounds zero fill IS the padding (columns -1 and W, rows -1 and H), and the dense box order
+//     [row][x][64 ch] IS the padded-linear position order.  (A first version filled the tile with per-thread cp.async: its
+//     address arithmetic alone cost ~11 k cycles per tile, profiles/ncu_cf_probe_r1.csv.)  Optionally 3 helper warps apply the
+//     previous layer's BN+ReLU in place (padding kept zero), fence to the async proxy and hand the stage to the MMA warp;
+//   * one thread issues tcgen05.mma (M=128 rows = 128 consecutive positions, N = Cout, K = 16 channels) for every tap; 4
+//     epilogue warps drain TMEM (tcgen05.ld), round to bf16, store, and keep per-thread running sums of (y-K), (y-K)^2 per
+//     channel for the whole persistent loop.
 // HBM traffic: x read once (+halo rows through L2), y written once; the BN statistics pass and (optionally) the BN-apply
 // pass of the previous layer disappear.
 #include <stdlib.h>
@@ -26,20 +30,22 @@
 
 namespace rss {
 
-constexpr int kCfThreads = 288;          // warps 0-3 producers, warp 4 MMA issuer, warps 5-8 epilogue
-constexpr int kCfProducers = 128;
+constexpr int kCfThreads = 288;          // warp 0 TMA producer, warps 1-3 input-transform helpers, warp 4 MMA issuer, warps 5-8 epilogue
+constexpr int kCfHelpers = 96;
 constexpr int kCfMaxTaps = 9;
+constexpr int kCfMaxStages = 3;
 
 struct CfGeom {
     int B, H, W, Cin, Cout;
     int halo, Wp, Q;                     // padded pitch W + 2*halo, positions per image H*Wp
     int MM, MT;                          // 128-row MMA blocks per tile, MT = 128*MM
     int tiles_per_img, n_tiles;
-    int P;                               // staged positions per tile: MT + 2*halo*(Wp+1)
-    int n_taps;
-    int tap_off[kCfMaxTaps];             // (dy+halo)*Wp + dx + halo
-    int in_relu;
+    int NR, P;                           // staged padded rows per tile; plane pitch in positions (>= NR*Wp, multiple of 8)
     int KC;                              // 64-channel planes per position: ceil(Cin/64)
+    int S;                               // ring stages (2 or 3)
+    int n_taps;
+    int tap_off[kCfMaxTaps];             // dy*Wp + dx (signed)
+    int in_relu;
     int desc_swap;                       // debugging aid (RSS_CF_DESC_SWAP=1): base-offset field = (start >> 7) & 7 (measured WRONG)
 };
 
@@ -56,23 +62,18 @@ struct CfStats {                         // all NULL when no statistics are want
 __device__ __forceinline__ uint32_t cf_idesc(int n) {       // kind::f16, D=f32, A=B=bf16, K-major both, M=128
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ void cf_cp16(uint32_t dst, const void* src, bool valid) {
-    const int n = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cf_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cf_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cf_epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// first staged padded row of the tile starting at padded-linear position q0 (floor division, q0 - halo may be negative)
+__device__ __forceinline__ int cf_row_lo(int q0, int halo, int Wp) { return (q0 - halo + Wp) / Wp - 1 - halo; }
 
 // COUT_S: compile-time Cout when statistics are produced (32 or 64), 0 = no statistics (Cout from the geometry).
-// LA: producer look-ahead in tiles; the ring has LA+1 stages.
-template <int COUT_S, int LA>
+template <int COUT_S>
 __global__ void __launch_bounds__(kCfThreads, 1)
-conv_cf_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ y,
+conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ y,
                const float* __restrict__ in_scale, const float* __restrict__ in_shift, const __grid_constant__ CfGeom g,
                const __grid_constant__ CfStats st) {
-    constexpr int S = LA + 1;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int S = g.S;
     const int CH = g.Cin >> 3;                                        // 16-byte channel chunks per position
     // every operand tile starts 1024-byte aligned (one swizzle period); P % 8 == 0 and Cout % 8 == 0 keep it so
     const uint32_t w_bytes = (uint32_t)g.n_taps * g.KC * g.Cout * 128;         // [tap][plane][cout row of 128 B]
@@ -81,25 +82,32 @@ conv_cf_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
     const uint32_t w_s = smem_u32(smem);
     const uint32_t a_s = w_s + w_bytes;
     uint8_t* tail = smem + w_bytes + (size_t)S * stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);              // [0,S) full, [S,2S) empty, [2S,2S+NACC) tmem_full, then tmem_empty
+    // barriers: [0,3) landed (TMA bytes), [3,6) ready (transformed), [6,9) empty, [9,13) tmem_full, [13,17) tmem_empty
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* bar_landed = bars, *bar_ready = bars + 3, *bar_empty = bars + 6, *bar_tfull = bars + 9, *bar_tempty = bars + 13;
     const int NACC = 2 * g.MM;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 2 * 4);
-    float* red = reinterpret_cast<float*>(tmem_slot + 4);            // [4 warps][2*Cout] statistics staging
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);                 // +144 B; `red` below lands 16-byte aligned
+    float* red = reinterpret_cast<float*>(tmem_slot + 4);            // [4 warps][2*Cout] statistics staging, then K[Cout]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool xform = in_scale != nullptr;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < NACC * g.Cout) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(smem_u32(bars + s), kCfProducers / 32); mbar_init(smem_u32(bars + S + s), 1); }
-        for (int a = 0; a < NACC; ++a) { mbar_init(smem_u32(bars + 2 * S + a), 1); mbar_init(smem_u32(bars + 2 * S + 4 + a), 4); }
+        for (int s = 0; s < kCfMaxStages; ++s) {
+            mbar_init(smem_u32(bar_landed + s), 1); mbar_init(smem_u32(bar_ready + s), kCfHelpers / 32); mbar_init(smem_u32(bar_empty + s), 1);
+        }
+        for (int a = 0; a < 4; ++a) { mbar_init(smem_u32(bar_tfull + a), 1); mbar_init(smem_u32(bar_tempty + a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
     }
     if (warp == 4) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
     // weights: packed global [tap][co][ci] -> smem [tap][plane][co][64 ci] rows of 128 B, 128B-swizzled (K-major B operand)
     {
         const int total = g.n_taps * g.Cout * CH;
+        const int chs = CH == 4 ? 2 : (CH == 8 ? 3 : 4);                    // CH in {4, 8, 16}
         for (int i = threadIdx.x; i < total; i += kCfThreads) {
-            const int kc = i % CH, co = (i / CH) % g.Cout, tap = i / (CH * g.Cout);
+            const int kc = i & (CH - 1), row = i >> chs, co = row % g.Cout, tap = row / g.Cout;
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(wp + ((size_t)(tap * g.Cout + co) * g.Cin + kc * 8)));
             const int plane = kc >> 3, c = kc & 7;
             *reinterpret_cast<uint4*>(smem + ((size_t)(tap * g.KC + plane) * g.Cout + co) * 128 + ((c ^ (co & 7)) << 4)) = v;
@@ -111,107 +119,111 @@ conv_cf_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // ================= producers: global -> [chunk][position][8ch] shared tile =================
-        const int tid = threadIdx.x;
-        const int ch = tid % CH, pslot = tid / CH, step = kCfProducers / CH;
-        const bool xform = in_scale != nullptr;
-        float sc[8], sh[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { sc[i] = xform ? in_scale[ch * 8 + i] : 1.f; sh[i] = xform ? in_shift[ch * 8 + i] : 0.f; }
-
-        auto issue = [&](int tile, int stage) {
-            const int b = tile / g.tiles_per_img, t = tile % g.tiles_per_img;
-            const int qs = t * g.MT - g.halo * g.Wp - g.halo + pslot;        // padded linear index of this thread's first position
-            int r = (qs + 2 * g.Wp) / g.Wp - 2;
-            int c = qs - r * g.Wp - g.halo;
-            const uint32_t dst0 = a_s + stage * stage_bytes + (uint32_t)((ch >> 3) * g.P) * 128;
-            const __nv_bfloat16* img = x + (size_t)b * g.H * g.W * g.Cin + ch * 8;
-            for (int p = pslot; p < g.P; p += step) {
-                const bool ok = r >= 0 && r < g.H && c >= 0 && c < g.W;
-                cf_cp16(dst0 + (uint32_t)p * 128 + (uint32_t)(((ch & 7) ^ (p & 7)) << 4), ok ? img + ((size_t)r * g.W + c) * g.Cin : x, ok);
-                c += step;
-                while (c >= g.Wp - g.halo) { c -= g.Wp; ++r; }
+    if (warp == 0) {
+        // ================= TMA producer: NR padded rows x Wp pixels x 64 channels per plane, OOB zero fill = padding =================
+        if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)g.KC * g.NR * g.Wp * 128;
+            int i = 0;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++i) {
+                const int si = i % S, use = i / S;
+                if (use > 0) mbar_wait(smem_u32(bar_empty + si), (use - 1) & 1);         // MMAs that read this stage retired
+                const int b = tile / g.tiles_per_img, t = tile % g.tiles_per_img;
+                const int r_lo = cf_row_lo(t * g.MT, g.halo, g.Wp);
+                const uint32_t full = smem_u32(bar_landed + si);
+                mbar_expect_tx(full, tx_bytes);
+                for (int pl = 0; pl < g.KC; ++pl)
+                    tma_load_4d(a_s + si * stage_bytes + (uint32_t)(pl * g.P) * 128, &tmap_x, full, pl * 64, -g.halo, r_lo, b);
             }
-        };
-        auto transform = [&](int tile, int stage) {
-            const int t = tile % g.tiles_per_img;
-            const int qs = t * g.MT - g.halo * g.Wp - g.halo + pslot;
-            int r = (qs + 2 * g.Wp) / g.Wp - 2;
-            int c = qs - r * g.Wp - g.halo;
-            uint8_t* dst0 = smem + (a_s - w_s) + (size_t)stage * stage_bytes + (size_t)((ch >> 3) * g.P) * 128;
-            for (int p = pslot; p < g.P; p += step) {
-                if (r >= 0 && r < g.H && c >= 0 && c < g.W) {               // padding stays exactly zero
-                    uint4* ptr = reinterpret_cast<uint4*>(dst0 + (size_t)p * 128 + (((ch & 7) ^ (p & 7)) << 4));
-                    Raw8<__nv_bfloat16> raw;
-                    raw.r = *ptr;
-                    float v[8];
-                    unpack8(raw, v);
+        }
+    } else if (warp < 4) {
+        // ================= helpers: previous layer's BN(+ReLU) applied in place on the landed tile =================
+        if (xform) {
+            const int ht = threadIdx.x - 32;                      // 0..95
+            const int ch = ht % CH, pslot = ht / CH, step = kCfHelpers / CH;      // CH in {4, 8, 16} divides 96
+            float sc[8], sh[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        v[i] = fmaf(v[i], sc[i], sh[i]);
-                        if (g.in_relu) v[i] = fmaxf(v[i], 0.f);
+            for (int k = 0; k < 8; ++k) { sc[k] = in_scale[ch * 8 + k]; sh[k] = in_shift[ch * 8 + k]; }
+            const int npos = g.NR * g.Wp;
+            int i = 0;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++i) {
+                const int si = i % S;
+                mbar_wait(smem_u32(bar_landed + si), (i / S) & 1);
+                const int t = tile % g.tiles_per_img;
+                const int r_lo = cf_row_lo(t * g.MT, g.halo, g.Wp);
+                uint8_t* base = smem + w_bytes + (size_t)si * stage_bytes + (size_t)((ch >> 3) * g.P) * 128;
+                int r = r_lo + pslot / g.Wp, c = pslot % g.Wp - g.halo;
+                for (int p = pslot; p < npos; p += step) {
+                    if (r >= 0 && r < g.H && c >= 0 && c < g.W) {               // padding stays exactly zero
+                        uint4* ptr = reinterpret_cast<uint4*>(base + (size_t)p * 128 + (((ch & 7) ^ (p & 7)) << 4));
+                        Raw8<__nv_bfloat16> raw;
+                        raw.r = *ptr;
+                        float v[8];
+                        unpack8(raw, v);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            v[k] = fmaf(v[k], sc[k], sh[k]);
+                            if (g.in_relu) v[k] = fmaxf(v[k], 0.f);
+                        }
+                        store8(reinterpret_cast<__nv_bfloat16*>(ptr), v);
                     }
-                    store8(reinterpret_cast<__nv_bfloat16*>(ptr), v);
+                    c += step;
+                    while (c >= g.Wp - g.halo) { c -= g.Wp; ++r; }
                 }
-                c += step;
-                while (c >= g.Wp - g.halo) { c -= g.Wp; ++r; }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(bar_ready + si));
             }
-        };
-
-        // ring bookkeeping: tile number i of this CTA uses stage i % S; a stage is re-filled only after the MMAs that read it retired
-        int n_my = 0;
-        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) ++n_my;
-        for (int i = 0; i < LA; ++i) {                                     // prologue: the first LA tiles (stages are free)
-            if (i < n_my) issue(blockIdx.x + i * gridDim.x, i % S);
-            cf_commit();
         }
-        for (int i = 0; i < n_my; ++i) {
-            const int j = i + LA;                                          // tile to prefetch now
-            if (j < n_my) {
-                const int sj = j % S;
-                if (j >= S) mbar_wait(smem_u32(bars + S + sj), ((j / S) - 1) & 1);   // MMAs of tile j-S done with this stage
-                issue(blockIdx.x + j * gridDim.x, sj);
-            }
-            cf_commit();
-            cf_wait<LA>();                                                 // this thread's copies of tile i have landed
-            const int si = i % S;
-            if (xform) transform(blockIdx.x + i * gridDim.x, si);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(bars + si));
-        }
-        cf_wait<0>();
     } else if (warp == 4) {
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = cf_idesc(g.Cout);
-            const int ksteps = g.Cin >> 4;
+            const int kpp = g.Cin >= 64 ? 4 : (g.Cin >> 4);                 // K=16 steps per 64-channel plane
+            uint64_t* bar_in = xform ? bar_ready : bar_landed;
+            const uint64_t desc_hi = make_sw128_desc_bo(0, 0);              // SWIZZLE_128B K-major, SBO 1024, start address 0
+            const uint32_t w_lo = w_s >> 4;
+            const uint32_t plane_a8 = (uint32_t)g.P * 8, plane_b8 = (uint32_t)g.Cout * 8;
+            int tap_off8[kCfMaxTaps];
+#pragma unroll
+            for (int tp = 0; tp < kCfMaxTaps; ++tp) tap_off8[tp] = tp < g.n_taps ? g.tap_off[tp] * 8 : 0;
             int i = 0, acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++i) {
                 const int si = i % S;
-                mbar_wait(smem_u32(bars + si), (i / S) & 1);               // tile staged
+                mbar_wait(smem_u32(bar_in + si), (i / S) & 1);             // tile staged (and transformed)
                 fence_proxy_async_smem();
                 tc_fence_after();
-                const uint32_t a0 = a_s + si * stage_bytes;
+                const int t = tile % g.tiles_per_img;
+                const int q0 = t * g.MT;
+                const int pbase = q0 - cf_row_lo(q0, g.halo, g.Wp) * g.Wp;          // staged index of output position q0
+                // descriptors differ only in their 14-bit start-address field (address >> 4): everything below is adds on that field
+                // (a row of 128 B = 8 units, a K=16 step of 32 B = 2 units); the issue loop is the critical path of this kernel
+                const uint32_t a_lo0 = ((a_s + si * stage_bytes) >> 4) + (uint32_t)pbase * 8;
                 for (int mm = 0; mm < g.MM; ++mm) {
-                    mbar_wait(smem_u32(bars + 2 * S + 4 + acc), acc_phase ^ 1);          // epilogue drained this accumulator
+                    mbar_wait(smem_u32(bar_tempty + acc), acc_phase ^ 1);                // epilogue drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * g.Cout;
-                    for (int t = 0; t < g.n_taps; ++t) {
-                        for (int k = 0; k < ksteps; ++k) {
-                            const int plane = k >> 2, kk = k & 3;                        // 4 K=16 steps (32 B each) per 128-byte row
-                            const uint32_t a_addr = a0 + (uint32_t)(plane * g.P + mm * 128 + g.tap_off[t]) * 128 + kk * 32;
-                            const uint32_t b_addr = w_s + (uint32_t)((t * g.KC + plane) * g.Cout) * 128 + kk * 32;
-                            const uint32_t phase = g.desc_swap ? ((a_addr >> 7) & 7u) : 0u;    // measured: the XOR uses absolute address bits
-                            umma_bf16(d_tmem, make_sw128_desc_bo(a_addr, phase), make_sw128_desc_bo(b_addr, 0), idesc, (t | k) != 0);
+                    const uint32_t a_lo1 = a_lo0 + (uint32_t)mm * 128 * 8;
+                    uint32_t b_lo = w_lo;
+                    uint32_t accum = 0;
+                    for (int tp = 0; tp < g.n_taps; ++tp) {
+                        uint32_t a_lo = a_lo1 + (uint32_t)(tap_off8[tp]);
+                        for (int pl = 0; pl < g.KC; ++pl) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                if (kk < kpp) {
+                                    umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + kk * 2), desc_hi | (uint64_t)(b_lo + kk * 2), idesc, accum);
+                                    accum = 1;
+                                }
+                            }
+                            a_lo += plane_a8;
+                            b_lo += plane_b8;
                         }
                     }
-                    umma_commit(smem_u32(bars + 2 * S + acc));                           // accumulator complete -> epilogue
+                    umma_commit(smem_u32(bar_tfull + acc));                              // accumulator complete -> epilogue
                     if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(smem_u32(bars + S + si));                                     // stage free once these MMAs retire
+                umma_commit(smem_u32(bar_empty + si));                                    // stage free once these MMAs retire
             }
         }
     } else {
@@ -236,7 +248,7 @@ conv_cf_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
                 const int r = q / g.Wp, c = q - r * g.Wp - g.halo;
                 const bool live = q < g.Q && c >= 0 && c < g.W;
                 __nv_bfloat16* dst = y + (((size_t)b * g.H + r) * g.W + c) * g.Cout;
-                mbar_wait(smem_u32(bars + 2 * S + acc), acc_phase);
+                mbar_wait(smem_u32(bar_tfull + acc), acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * g.Cout;
                 if (COUT_S > 0) {
@@ -252,10 +264,12 @@ conv_cf_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
                             store8(dst + c0, v);
                             store8(dst + c0 + 8, v + 8);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {                 // statistics of the ROUNDED values (what the apply pass reads)
-                                const float d = __bfloat162float(__float2bfloat16_rn(v[i])) - Ksm[c0 + i];
-                                s1[c0 + i] += d;
-                                s2[c0 + i] = fmaf(d, d, s2[c0 + i]);
+                            for (int i4 = 0; i4 < 16; i4 += 4) {          // statistics of the fp32 accumulators (rounding is zero-mean)
+                                const float4 k4 = *reinterpret_cast<const float4*>(Ksm + c0 + i4);
+                                const float d0 = v[i4] - k4.x, d1 = v[i4 + 1] - k4.y, d2 = v[i4 + 2] - k4.z, d3 = v[i4 + 3] - k4.w;
+                                s1[c0 + i4] += d0; s1[c0 + i4 + 1] += d1; s1[c0 + i4 + 2] += d2; s1[c0 + i4 + 3] += d3;
+                                s2[c0 + i4] = fmaf(d0, d0, s2[c0 + i4]); s2[c0 + i4 + 1] = fmaf(d1, d1, s2[c0 + i4 + 1]);
+                                s2[c0 + i4 + 2] = fmaf(d2, d2, s2[c0 + i4 + 2]); s2[c0 + i4 + 3] = fmaf(d3, d3, s2[c0 + i4 + 3]);
                             }
                         }
                     }
@@ -275,7 +289,7 @@ conv_cf_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(bars + 2 * S + 4 + acc));
+                if (lane == 0) mbar_arrive(smem_u32(bar_tempty + acc));
                 if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -324,14 +338,14 @@ conv_cf_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
     if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-struct CfPlan { CfGeom g; size_t smem; int la; int grid; };
+struct CfPlan { CfGeom g; size_t smem; int grid; };
 
 static int cf_plan(int B, int H, int W, int Cin, int Cout, int n_taps, const int* dy, const int* dx, CfPlan* pl) {
     if (B <= 0 || H <= 0 || W <= 0 || n_taps < 1 || n_taps > kCfMaxTaps) return RSS_ERR_SHAPE;
-    if (Cin != 32 && Cin != 64 && Cin != 128) return RSS_ERR_SHAPE;          // 128 producer threads / (Cin/8) chunks
+    if (Cin != 32 && Cin != 64 && Cin != 128) return RSS_ERR_SHAPE;          // 96 helper threads / (Cin/8) chunks; 64-channel planes
     if (Cout < 16 || Cout % 16 || Cout > 128) return RSS_ERR_SHAPE;
     CfGeom& g = pl->g;
-    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.n_taps = n_taps; g.in_relu = 0;
+    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.n_taps = n_taps; g.in_relu = 0; g.desc_swap = 0;
     int halo = 0;
     for (int t = 0; t < n_taps; ++t) {
         const int a = dy[t] < 0 ? -dy[t] : dy[t], b = dx[t] < 0 ? -dx[t] : dx[t];
@@ -340,20 +354,24 @@ static int cf_plan(int B, int H, int W, int Cin, int Cout, int n_taps, const int
     }
     if (halo > 1) return RSS_ERR_SHAPE;
     g.halo = halo; g.Wp = W + 2 * halo; g.Q = H * g.Wp;
-    for (int t = 0; t < n_taps; ++t) g.tap_off[t] = (dy[t] + halo) * g.Wp + dx[t] + halo;
+    if (g.Wp > 256) return RSS_ERR_SHAPE;                                     // TMA box dimension limit
+    for (int t = 0; t < n_taps; ++t) g.tap_off[t] = dy[t] * g.Wp + dx[t];
     g.KC = (Cin + 63) / 64;
     const size_t w_bytes = (size_t)n_taps * g.KC * Cout * 128;
-    const size_t tail = (2 * 3 + 8) * 8 + 16 + (size_t)(4 * 2 + 1) * Cout * 4 + 64;
+    const size_t tail = 18 * 8 + 16 + (size_t)(4 * 2 + 1) * Cout * 4 + 64;
     const size_t budget = 225 * 1024 - 1024;                                  // 1024: manual alignment of the dynamic segment
     // two 128-row blocks per tile halve the halo over-fetch on wide images; needs 4 accumulators in TMEM
     for (int mm = (W >= 128 && 4 * Cout <= 512) ? 2 : 1; mm >= 1; --mm) {
         g.MM = mm; g.MT = 128 * mm;
-        g.P = (g.MT + 2 * halo * (g.Wp + 1) + 7) & ~7;                        // multiple of 8 rows: planes/stages stay 1024-aligned
+        const int L = g.MT + 2 * halo;                                        // padded-linear span a tile reads within its own rows
+        g.NR = (L + g.Wp - 2) / g.Wp + 1 + 2 * halo;                          // rows that span can touch, + halo rows above and below
+        if (g.NR > 256) continue;
+        g.P = (g.NR * g.Wp + 7) & ~7;                                         // multiple of 8 rows: planes/stages stay 1024-aligned
         const size_t stage = (size_t)g.KC * g.P * 128;
-        for (int la = 2; la >= 1; --la) {
-            const size_t need = w_bytes + (size_t)(la + 1) * stage + tail;
+        for (int s = kCfMaxStages; s >= 2; --s) {
+            const size_t need = w_bytes + (size_t)s * stage + tail;
             if (need <= budget) {
-                pl->la = la; pl->smem = need + 1024;
+                g.S = s; pl->smem = need + 1024;
                 g.tiles_per_img = (g.Q + g.MT - 1) / g.MT;
                 g.n_tiles = B * g.tiles_per_img;
                 pl->grid = g.n_tiles < num_sms() ? g.n_tiles : num_sms();
@@ -362,6 +380,20 @@ static int cf_plan(int B, int H, int W, int Cin, int Cout, int n_taps, const int
         }
     }
     return RSS_ERR_SHAPE;
+}
+
+typedef CUresult (*CfEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static CfEncodeTiledFn cf_encode_tiled() {
+    static CfEncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (CfEncodeTiledFn)p;
+    }
+    return fn;
 }
 
 }  // namespace rss
@@ -392,6 +424,7 @@ extern "C" int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, 
     int rc = cf_plan(B, H, W, Cin, Cout, n_taps, taps_dy, taps_dx, &pl);
     if (rc != RSS_OK) return rc;
     if ((in_scale == nullptr) != (in_shift == nullptr)) return RSS_ERR_SHAPE;
+    if ((uintptr_t)x & 15) return RSS_ERR_SHAPE;
     pl.g.in_relu = in_relu;
     {
         const char* sw = getenv("RSS_CF_DESC_SWAP");
@@ -406,25 +439,36 @@ extern "C" int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, 
         st.running_var = running_var; st.momentum = momentum; st.eps = eps; st.mean_out = mean_out; st.invstd_out = invstd_out;
         st.scale_out = scale_out; st.shift_out = shift_out; st.count = (float)((double)B * H * W);
     }
+    CUtensorMap tm;
+    {
+        CfEncodeTiledFn enc = cf_encode_tiled();
+        if (!enc) return RSS_ERR_CUDA;
+        const CfGeom& g = pl.g;
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)g.Wp, (cuuint32_t)g.NR, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return RSS_ERR_CUDA; }
+    }
     cudaError_t e = cudaSuccess;
-#define CF_LAUNCH(CS, LA_)                                                                                                  \
+#define CF_LAUNCH(CS)                                                                                                       \
     do {                                                                                                                     \
         static bool attr = false;                                                                                            \
         if (!attr) {                                                                                                         \
-            e = cudaFuncSetAttribute(conv_cf_kernel<CS, LA_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)); \
+            e = cudaFuncSetAttribute(conv_cf_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));   \
             attr = (e == cudaSuccess);                                                                                       \
         }                                                                                                                    \
         if (e == cudaSuccess)                                                                                                \
-            conv_cf_kernel<CS, LA_><<<pl.grid, kCfThreads, pl.smem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w_packed, \
-                                                                              (__nv_bfloat16*)y, in_scale, in_shift, pl.g, st); \
+            conv_cf_kernel<CS><<<pl.grid, kCfThreads, pl.smem, stream>>>(tm, (const __nv_bfloat16*)w_packed, (__nv_bfloat16*)y, \
+                                                                         in_scale, in_shift, pl.g, st);                     \
     } while (0)
     const int cs = stats ? Cout : 0;
-    if (cs == 0 && pl.la == 2) CF_LAUNCH(0, 2);
-    else if (cs == 0) CF_LAUNCH(0, 1);
-    else if (cs == 32 && pl.la == 2) CF_LAUNCH(32, 2);
-    else if (cs == 32) CF_LAUNCH(32, 1);
-    else if (cs == 64 && pl.la == 2) CF_LAUNCH(64, 2);
-    else CF_LAUNCH(64, 1);
+    if (cs == 0) CF_LAUNCH(0);
+    else if (cs == 32) CF_LAUNCH(32);
+    else CF_LAUNCH(64);
 #undef CF_LAUNCH
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; (void)cudaGetLastError(); return RSS_ERR_CUDA; }
     return check_launch();

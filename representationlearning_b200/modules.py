@@ -32,9 +32,9 @@ class FusedBNAct(nn.Module):
         self.register_buffer("running_mean", torch.zeros(num_features))
         self.register_buffer("running_var", torch.ones(num_features))
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
-        # private scratch of rss_bn_stats_fused ([0] ticket, [1:] per-channel accumulators; the kernel leaves it zeroed).
+        # private scratch of the BN kernels ([0:2] barrier/ticket counters, [2:] per-channel accumulators; kernels leave it zeroed).
         # One per layer: layers may run concurrently on different streams.  Not part of the state_dict.
-        self.register_buffer("_scratch", torch.zeros(1 + 2 * num_features), persistent=False)
+        self.register_buffer("_scratch", torch.zeros(2 + 2 * num_features), persistent=False)
 
     defer_counter = False      # trainer.FlatSGD bumps every num_batches_tracked with one foreach op per step instead
 

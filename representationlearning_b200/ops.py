@@ -17,10 +17,10 @@ CL = torch.channels_last
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; counted from the csrc/*.cu launch sites)
 KERNELS_PER_CALL = {
     "rss_layernorm_fwd": 1, "rss_layernorm_bwd": 1, "rss_attn_fwd": 5, "rss_attn_bwd": 7, "rss_bn_stats": 1, "rss_bn_combine": 1,
-    "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1,
+    "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1, "rss_bn_fwd_fused": 1, "rss_bn_bwd_fused": 1,
     "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 4, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
     "rss_headaux_fwd": 2, "rss_seg_loss_fwd": 2, "rss_seg_loss_bwd": 1, "rss_grad_sumsq": 1, "rss_sgd_step": 1,
-    "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_conv_wgrad": 1, "rss_conv_cf": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
+    "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_conv_wgrad": 1, "rss_conv_wgrad_tc": 1, "rss_conv_cf": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
 }
 COUNTERS = {"launches": 0, "calls": 0}
 TIMED = {}            # op name -> list of (start_event, end_event), filled only while bench.py enables it
@@ -89,6 +89,13 @@ def grad_sink(p):
     if g is None or g.dtype != torch.float32 or not g.is_contiguous():
         return None
     return g
+
+
+import os
+# one-launch BatchNorm (statistics/reduce + device-wide spin barrier + apply) for L2-resident activations.  Measured on the B=16 step
+# (gpurun 2026-10-17): the barrier costs more than the launch it saves -- 13-32 us per fused kernel vs ~10 + ~5 us for the two
+# split kernels, 382 vs 418 img/s -- so it is OFF by default; the kernels stay in the library (tests run them) for round 2.
+BN_FUSED = {"on": os.environ.get("RSS_BN_FUSED", "0") != "0"}
 
 
 def _world(group):
@@ -232,34 +239,43 @@ class BNAct(torch.autograd.Function):
             if not training:
                 raise _lib.RssError("pre_bias folding is only valid for training-mode BatchNorm")
             pre_bias = _f32(pre_bias)
-        if have_aff:
-            pass
-        elif training and world == 1:
-            if scratch is None or scratch.numel() < 1 + 2 * C:      # [0] last-block ticket, [1:] accumulators; kernel leaves zeros
-                scratch = torch.zeros(1 + 2 * C, device=dev, dtype=torch.float32)
-            check(lib.rss_bn_stats_fused(_p(x), _p(scratch[1:]), _p(scratch), rows, C, dt, _p(g), _p(b),
-                                         _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
-                                         _p(aff[3]), _p(pre_bias), st), "rss_bn_stats_fused")
-        elif training:
-            nparts = lib.rss_bn_stats_nparts(rows, C)
-            part = torch.empty(nparts * C * 2 + nparts, device=dev, dtype=torch.float32)
-            cnt = part[nparts * C * 2:]
-            check(lib.rss_bn_stats(_p(x), _p(part), _p(cnt), rows, C, dt, st), "rss_bn_stats")
-            stat = torch.empty(C * 2 + 1, device=dev, dtype=torch.float32)
-            check(lib.rss_bn_combine(_p(part), _p(cnt), nparts, C, _p(stat), _p(stat[C * 2:]), st), "rss_bn_combine")
-            if world > 1:     # SyncBN: exchange (mean, M2, count) per rank, Chan-combine again
-                gathered = torch.empty(world, C * 2 + 1, device=dev, dtype=torch.float32)
-                dist.all_gather_into_tensor(gathered, stat, group=None if group is True else group)
-                parts = gathered[:, :C * 2].contiguous()
-                cnts = gathered[:, C * 2].contiguous()
-                check(lib.rss_bn_combine(_p(parts), _p(cnts), world, C, _p(stat), _p(stat[C * 2:]), st), "rss_bn_combine")
-            check(lib.rss_bn_finalize(_p(stat), _p(stat[C * 2:]), _p(g), _p(b), _p(running_mean), _p(running_var),
-                                      momentum, eps, C, _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), _p(pre_bias), st), "rss_bn_finalize")
-        else:
-            check(lib.rss_bn_eval_affine(_p(g), _p(b), _p(running_mean), _p(running_var), eps, C,
-                                         _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), st), "rss_bn_eval_affine")
+        fused = BN_FUSED["on"] and training and world == 1 and bool(lib.rss_bn_fused_supported(rows, C, act, dt))
+        if fused and (scratch is None or scratch.numel() < 2 + 2 * C):
+            scratch = torch.zeros(2 + 2 * C, device=dev, dtype=torch.float32)   # [0:2] barrier counters, [2:] accumulators; left zeroed
         y = torch.empty_like(x, memory_format=CL)
-        check(lib.rss_bn_act_fwd(_p(x), _p(residual), _p(y), _p(aff[2]), _p(aff[3]), rows, C, act, dt, st), "rss_bn_act_fwd")
+        if fused and not have_aff:          # statistics + apply in ONE launch (device-wide barrier in between)
+            check(lib.rss_bn_fwd_fused(_p(x), _p(residual), _p(y), _p(scratch[2:]), _p(scratch), rows, C, act, dt, _p(g), _p(b),
+                                       _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
+                                       _p(aff[3]), _p(pre_bias), st), "rss_bn_fwd_fused")
+        else:
+            if have_aff:
+                pass
+            elif training and world == 1:
+                if scratch is None or scratch.numel() < 2 + 2 * C:      # [0] last-block ticket, [2:] accumulators; kernel leaves zeros
+                    scratch = torch.zeros(2 + 2 * C, device=dev, dtype=torch.float32)
+                check(lib.rss_bn_stats_fused(_p(x), _p(scratch[2:]), _p(scratch), rows, C, dt, _p(g), _p(b),
+                                             _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
+                                             _p(aff[3]), _p(pre_bias), st), "rss_bn_stats_fused")
+            elif training:
+                nparts = lib.rss_bn_stats_nparts(rows, C)
+                part = torch.empty(nparts * C * 2 + nparts, device=dev, dtype=torch.float32)
+                cnt = part[nparts * C * 2:]
+                check(lib.rss_bn_stats(_p(x), _p(part), _p(cnt), rows, C, dt, st), "rss_bn_stats")
+                stat = torch.empty(C * 2 + 1, device=dev, dtype=torch.float32)
+                check(lib.rss_bn_combine(_p(part), _p(cnt), nparts, C, _p(stat), _p(stat[C * 2:]), st), "rss_bn_combine")
+                if world > 1:     # SyncBN: exchange (mean, M2, count) per rank, Chan-combine again
+                    gathered = torch.empty(world, C * 2 + 1, device=dev, dtype=torch.float32)
+                    dist.all_gather_into_tensor(gathered, stat, group=None if group is True else group)
+                    parts = gathered[:, :C * 2].contiguous()
+                    cnts = gathered[:, C * 2].contiguous()
+                    check(lib.rss_bn_combine(_p(parts), _p(cnts), world, C, _p(stat), _p(stat[C * 2:]), st), "rss_bn_combine")
+                check(lib.rss_bn_finalize(_p(stat), _p(stat[C * 2:]), _p(g), _p(b), _p(running_mean), _p(running_var),
+                                          momentum, eps, C, _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), _p(pre_bias), st), "rss_bn_finalize")
+            else:
+                check(lib.rss_bn_eval_affine(_p(g), _p(b), _p(running_mean), _p(running_var), eps, C,
+                                             _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), st), "rss_bn_eval_affine")
+            check(lib.rss_bn_act_fwd(_p(x), _p(residual), _p(y), _p(aff[2]), _p(aff[3]), rows, C, act, dt, st), "rss_bn_act_fwd")
+        ctx.fused, ctx.scratch = fused, scratch
         ctx.save_for_backward(x, y if (act == _lib.ACT_RELU and residual is not None) else None, aff)
         ctx.act, ctx.training, ctx.group, ctx.world, ctx.has_res = act, training, group, world, residual is not None
         ctx.refs = (gamma, beta)
@@ -275,6 +291,19 @@ class BNAct(torch.autograd.Function):
         B, C, H, W = x.shape
         rows = B * H * W
         dt, st = _dt(x), _st()
+        sg, sb = grad_sink(ctx.refs[0]), grad_sink(ctx.refs[1])
+        direct = sg is not None and sb is not None
+        dx = torch.empty_like(x, memory_format=CL)
+        dres = torch.empty_like(x, memory_format=CL) if ctx.has_res else None
+        if ctx.fused:                       # reduce + apply in ONE launch (training mode, single rank, L2-resident tensor)
+            local = None if direct else torch.empty(2 * C, device=x.device, dtype=torch.float32)
+            sc = ctx.scratch
+            check(lib.rss_bn_bwd_fused(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(sc[2:]), _p(sc),
+                                       _p(dx), _p(dres), rows, C, ctx.act, dt, _p(local), _p(sg) if direct else None,
+                                       _p(sb) if direct else None, st), "rss_bn_bwd_fused")
+            if direct:
+                return (dx, dres) + (None,) * 12
+            return (dx, dres, local[C:], local[:C]) + (None,) * 10
         sums = torch.empty(2 * C, device=x.device, dtype=torch.float32)
         check(lib.rss_bn_bwd_reduce(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(sums),
                                     rows, C, ctx.act, dt, st), "rss_bn_bwd_reduce")
@@ -288,10 +317,6 @@ class BNAct(torch.autograd.Function):
         else:                       # eval-mode BN is a fixed affine map: no batch-statistic terms
             red = torch.zeros_like(sums)
             inv_count = 0.0
-        dx = torch.empty_like(x, memory_format=CL)
-        dres = torch.empty_like(x, memory_format=CL) if ctx.has_res else None
-        sg, sb = grad_sink(ctx.refs[0]), grad_sink(ctx.refs[1])
-        direct = sg is not None and sb is not None
         check(lib.rss_bn_bwd_apply(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(red), inv_count,
                                    _p(dx), _p(dres), rows, C, ctx.act, dt, _p(local), _p(sg) if direct else None,
                                    _p(sb) if direct else None, st), "rss_bn_bwd_apply")

@@ -65,8 +65,10 @@ def test_layernorm(P, report, dtype, shape):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("act", [0, 1, 2])
 @pytest.mark.parametrize("shape,res", [((2, 32, 16, 16), False), ((2, 64, 9, 11), True), ((1, 480, 8, 8), False), ((4, 128, 32, 32), True)])
-def test_bn_act(P, report, dtype, act, shape, res):
+@pytest.mark.parametrize("fused", [False, True])
+def test_bn_act(P, report, dtype, act, shape, res, fused, monkeypatch):
     from representationlearning_b200 import ops
+    monkeypatch.setitem(ops.BN_FUSED, "on", fused)        # split kernels / one-launch kernels with the device-wide barrier
     torch.manual_seed(2)
     B, C, H, W = shape
     if act == 2 and res:      # not a pattern of the reference: the ABI must refuse it, loudly
@@ -101,7 +103,7 @@ def test_bn_act(P, report, dtype, act, shape, res):
                 rv=rel(rvc, ctx.new_stats["bn.running_var"]))
     if res:
         errs["dres"] = rel(rc.grad.float(), rr.grad)
-    report["bn_act%d_%s_%s" % (act, str(dtype)[6:], "x".join(map(str, shape)))] = errs
+    report["bn_act%d_%s_%s%s" % (act, str(dtype)[6:], "x".join(map(str, shape)), "_fused" if fused else "")] = errs
     tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
     assert max(errs.values()) < tol, errs
 
@@ -509,18 +511,57 @@ def test_conv_wgrad(P, report, case):
     assert err < TOL_F32, err
 
 
+WGRAD_TC_CASES = [
+    # B, H, W, Cin, Cout, k, xform
+    (2, 19, 45, 64, 32, 3, False),        # ragged: tiles straddle rows, last tile partial
+    (2, 16, 16, 256, 256, 3, False),      # branch-3 geometry: 2x2 channel blocks x 3 tap groups
+    (2, 24, 24, 32, 128, 1, False),       # FFN fc1
+    (1, 24, 40, 128, 32, 1, True),        # FFN fc2 + transform on load
+    (1, 130, 128, 32, 32, 3, True),       # branch-0 width, many tiles per CTA, transform on load
+    (16, 64, 64, 64, 64, 3, False),       # full branch-1 size: two tap groups (scalar reductions)
+    (4, 32, 32, 128, 128, 3, False),      # branch-2 geometry
+    (2, 20, 128, 256, 64, 1, False),      # layer1 1x1
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_TC_CASES)
+def test_conv_wgrad_tc(P, report, case):
+    lib = P._lib.load()
+    B, H, W, Cin, Cout, k, xform = case
+    assert lib.rss_conv_wgrad_tc_supported(B, H, W, Cin, Cout, k) == 1
+    torch.manual_seed(5)
+    x = torch.randn(B, Cin, H, W, device=DEV).bfloat16()
+    dy = torch.randn(B, Cout, H, W, device=DEV).bfloat16()
+    xin, sc, sh = x.float(), None, None
+    if xform:
+        sc, sh = torch.rand(Cin, device=DEV) + 0.5, torch.randn(Cin, device=DEV) * 0.3
+        xin = torch.relu(x.float() * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).bfloat16().float()
+    ref = torch.nn.grad.conv2d_weight(xin, (Cout, Cin, k, k), dy.float(), stride=1, padding=k // 2)
+    xc, dyc = nchw_from(x), nchw_from(dy)
+    dw = torch.ones(Cout, Cin, k, k, device=DEV)            # must be accumulated into, not overwritten
+    for _ in range(2):
+        rc = lib.rss_conv_wgrad_tc(xc.data_ptr(), dyc.data_ptr(), dw.data_ptr(), B, H, W, Cin, Cout, k,
+                                   None if sc is None else sc.data_ptr(), None if sh is None else sh.data_ptr(), int(xform),
+                                   torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, (rc, lib.rss_last_cuda_error())
+    torch.cuda.synchronize()
+    err = rel((dw - 1.0) / 2.0, ref)
+    report["wgrad_tc_%s" % "_".join(map(str, case))] = err
+    assert err < TOL_F32, err
+
+
 def test_conv_wgrad_through_autograd(P, report):
     """conv.conv2d routes the weight gradient of a supported layer through the kernel (no FlatSGD sink: returned via autograd)"""
     from representationlearning_b200 import conv
     torch.manual_seed(6)
     x = nchw_from(torch.randn(2, 32, 20, 28).bfloat16()).requires_grad_(True)
-    w = torch.nn.Parameter(torch.randn(64, 32, 3, 3, device=DEV) * 0.1)
+    w = torch.nn.Parameter(torch.randn(32, 32, 3, 3, device=DEV) * 0.1)
     c0 = P.ops.COUNTERS["calls"]
-    y = conv.conv2d(x, w, None, 2, 1, 1)
+    y = conv.conv2d(x, w, None, 1, 1, 1)
     dy = torch.randn_like(y)
     y.backward(dy)
     assert P.ops.COUNTERS["calls"] > c0, "the hand-written wgrad kernel was not used"
-    ref = torch.nn.grad.conv2d_weight(x.detach().float(), w.shape, dy.float(), stride=2, padding=1)
+    ref = torch.nn.grad.conv2d_weight(x.detach().float(), w.shape, dy.float(), stride=1, padding=1)
     err = rel(w.grad, ref)
     report["wgrad_autograd"] = err
     assert err < TOL_F32, err
@@ -552,7 +593,7 @@ def _cf_call(lib, x, w, k, stats, in_aff, in_relu, rm=None, rv=None, gamma=None,
     packed, _, nt, tdy, tdx, keep = conv._pack([w], [None], [k], [1], Cout, Cin, False, x.device)
     st = None
     if stats:
-        scratch = torch.zeros(1 + 2 * Cout, device=DEV)
+        scratch = torch.zeros(2 + 2 * Cout, device=DEV)
         st = (gamma, beta, rm, rv, 0.1, 1e-5, scratch)
     y, aff = conv._cf_launch(x, packed, nt, tdy, tdx, Cin, Cout, in_aff, in_relu, st)
     torch.cuda.synchronize()

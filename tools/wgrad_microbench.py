@@ -53,11 +53,17 @@ for Hi, Cin, Cout, k, s, tag in SHAPES:
         g = torch.ops.aten.convolution_backward(dy, x, w, None, [s, s], [pad, pad], [1, 1], False, [0, 0], 1, [False, True, False])[1]
         dw.add_(g)
 
+    def own_tc():
+        rc = lib.rss_conv_wgrad_tc(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), B, Hi, Hi, Cin, Cout, k, None, None, 0, st)
+        assert rc == 0, rc
+
     r = dict(tag=tag, Hi=Hi, Cin=Cin, Cout=Cout, k=k, stride=s, gflop=2.0 * B * Ho * Ho * Cin * Cout * k * k / 1e9,
              mbytes=(x.numel() + dy.numel()) * 2 / 1e6, own_us=timeit(own), lib_us=timeit(ref))
+    if s == 1 and lib.rss_conv_wgrad_tc_supported(B, Hi, Hi, Cin, Cout, k):
+        r["tc_us"] = timeit(own_tc)
     r["own_gbs"] = r["mbytes"] / r["own_us"] * 1e3 / 1e3
     out.append(r)
-    print("%-22s Hi=%3d %3d->%3d k%d s%d | own %7.1f us (%5.0f GB/s algorithmic)  lib+add %7.1f us" %
-          (tag, Hi, Cin, Cout, k, s, r["own_us"], r["own_gbs"], r["lib_us"]))
+    print("%-22s Hi=%3d %3d->%3d k%d s%d | mma.sync %7.1f us  tcgen05 %7.1f us  lib+add %7.1f us  (CPU-launch-bound below ~60 us)" %
+          (tag, Hi, Cin, Cout, k, s, r["own_us"], r.get("tc_us", float("nan")), r["lib_us"]))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/wgrad_microbench.json", "w"), indent=1)
