@@ -47,6 +47,7 @@ struct CfGeom {
     int tap_off[kCfMaxTaps];             // dy*Wp + dx (signed)
     int in_relu;
     int desc_swap;                       // debugging aid (RSS_CF_DESC_SWAP=1): base-offset field = (start >> 7) & 7 (measured WRONG)
+    int dbg;                             // profiling aid (RSS_CF_DBG bits): 1 no epilogue stores/stats, 2 no TMA after the first S tiles, 4 no MMAs
 };
 
 struct CfStats {                         // all NULL when no statistics are wanted (data gradients)
@@ -130,6 +131,7 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                 const int b = tile / g.tiles_per_img, t = tile % g.tiles_per_img;
                 const int r_lo = cf_row_lo(t * g.MT, g.halo, g.Wp);
                 const uint32_t full = smem_u32(bar_landed + si);
+                if ((g.dbg & 2) && use > 0) { mbar_arrive(full); continue; }
                 mbar_expect_tx(full, tx_bytes);
                 for (int pl = 0; pl < g.KC; ++pl)
                     tma_load_4d(a_s + si * stage_bytes + (uint32_t)(pl * g.P) * 128, &tmap_x, full, pl * 64, -g.halo, r_lo, b);
@@ -175,17 +177,16 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
             }
         }
     } else if (warp == 4) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =================
+        {
             const uint32_t idesc = cf_idesc(g.Cout);
             const int kpp = g.Cin >= 64 ? 4 : (g.Cin >> 4);                 // K=16 steps per 64-channel plane
             uint64_t* bar_in = xform ? bar_ready : bar_landed;
             const uint64_t desc_hi = make_sw128_desc_bo(0, 0);              // SWIZZLE_128B K-major, SBO 1024, start address 0
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t leader = elect_one();
             const uint32_t w_lo = w_s >> 4;
             const uint32_t plane_a8 = (uint32_t)g.P * 8, plane_b8 = (uint32_t)g.Cout * 8;
-            int tap_off8[kCfMaxTaps];
-#pragma unroll
-            for (int tp = 0; tp < kCfMaxTaps; ++tp) tap_off8[tp] = tp < g.n_taps ? g.tap_off[tp] * 8 : 0;
             int i = 0, acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++i) {
@@ -202,17 +203,17 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                 for (int mm = 0; mm < g.MM; ++mm) {
                     mbar_wait(smem_u32(bar_tempty + acc), acc_phase ^ 1);                // epilogue drained this accumulator
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * g.Cout;
+                    const uint32_t d_tmem = tmem_u + acc * g.Cout;
                     const uint32_t a_lo1 = a_lo0 + (uint32_t)mm * 128 * 8;
                     uint32_t b_lo = w_lo;
                     uint32_t accum = 0;
                     for (int tp = 0; tp < g.n_taps; ++tp) {
-                        uint32_t a_lo = a_lo1 + (uint32_t)(tap_off8[tp]);
+                        uint32_t a_lo = a_lo1 + (uint32_t)(g.tap_off[tp] * 8);
                         for (int pl = 0; pl < g.KC; ++pl) {
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
-                                if (kk < kpp) {
-                                    umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + kk * 2), desc_hi | (uint64_t)(b_lo + kk * 2), idesc, accum);
+                                if (kk < kpp && !(g.dbg & 4)) {
+                                    umma_bf16_elect(leader, d_tmem, desc_hi | (uint64_t)(a_lo + kk * 2), desc_hi | (uint64_t)(b_lo + kk * 2), idesc, accum);
                                     accum = 1;
                                 }
                             }
@@ -220,10 +221,10 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                             b_lo += plane_b8;
                         }
                     }
-                    umma_commit(smem_u32(bar_tfull + acc));                              // accumulator complete -> epilogue
+                    umma_commit_elect(leader, smem_u32(bar_tfull + acc));                        // accumulator complete -> epilogue
                     if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(smem_u32(bar_empty + si));                                    // stage free once these MMAs retire
+                umma_commit_elect(leader, smem_u32(bar_empty + si));                              // stage free once these MMAs retire
             }
         }
     } else {
@@ -246,7 +247,7 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
             for (int mm = 0; mm < g.MM; ++mm) {
                 const int q = t * g.MT + mm * 128 + m;
                 const int r = q / g.Wp, c = q - r * g.Wp - g.halo;
-                const bool live = q < g.Q && c >= 0 && c < g.W;
+                const bool live = q < g.Q && c >= 0 && c < g.W && !(g.dbg & 1);
                 __nv_bfloat16* dst = y + (((size_t)b * g.H + r) * g.W + c) * g.Cout;
                 mbar_wait(smem_u32(bar_tfull + acc), acc_phase);
                 tc_fence_after();
@@ -345,7 +346,7 @@ static int cf_plan(int B, int H, int W, int Cin, int Cout, int n_taps, const int
     if (Cin != 32 && Cin != 64 && Cin != 128) return RSS_ERR_SHAPE;          // 96 helper threads / (Cin/8) chunks; 64-channel planes
     if (Cout < 16 || Cout % 16 || Cout > 128) return RSS_ERR_SHAPE;
     CfGeom& g = pl->g;
-    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.n_taps = n_taps; g.in_relu = 0; g.desc_swap = 0;
+    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.n_taps = n_taps; g.in_relu = 0; g.desc_swap = 0; g.dbg = 0;
     int halo = 0;
     for (int t = 0; t < n_taps; ++t) {
         const int a = dy[t] < 0 ? -dy[t] : dy[t], b = dx[t] < 0 ? -dx[t] : dx[t];
@@ -429,6 +430,8 @@ extern "C" int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, 
     {
         const char* sw = getenv("RSS_CF_DESC_SWAP");
         pl.g.desc_swap = (sw && sw[0] == '1') ? 1 : 0;
+        const char* dbg = getenv("RSS_CF_DBG");
+        pl.g.dbg = dbg ? atoi(dbg) : 0;
     }
     CfStats st{};
     const bool stats = stat_accum != nullptr;

@@ -101,28 +101,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =================
+        // (under `if (lane == 0)` the compiler cannot prove the descriptors warp-uniform and wraps every UTCHMMA in an
+        //  ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall: ~150 cycles per MMA, tools/probe/mma_probe.cu)
+        {
             const uint32_t idesc = make_idesc(g.block_n);
+            const uint32_t leader = elect_one();
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint64_t desc_hi = make_sw128_desc(0);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(smem_u32(bars + 2 * g.stages + 2 + acc), acc_phase ^ 1);       // epilogue drained this TMEM stage?
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * g.block_n;
+                const uint32_t d_tmem = tmem_u + acc * g.block_n;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     const int kc = kb % g.kchunks;
                     int ksteps = (g.Cin - kc * kBlockK + kUmmaK - 1) / kUmmaK;            // skip zero-filled tail channels
                     if (ksteps > kBlockK / kUmmaK) ksteps = kBlockK / kUmmaK;
                     mbar_wait(smem_u32(bars + stage), phase);                             // TMA landed?
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(a_addr + kATileBytes);
-                    for (int k = 0; k < ksteps; ++k)     // +32 B per K=16 step inside the 128 B swizzle atom
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                    umma_commit(smem_u32(bars + g.stages + stage));                      // frees the smem slot when MMAs finish
+                    const uint32_t a_lo = smem_u32(smem + (size_t)stage * stage_bytes) >> 4;
+                    const uint32_t b_lo = a_lo + (kATileBytes >> 4);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)     // +32 B (2 units of 16 B) per K=16 step inside the 128 B swizzle atom
+                        if (k < ksteps)
+                            umma_bf16_elect(leader, d_tmem, desc_hi | (uint64_t)(a_lo + k * 2), desc_hi | (uint64_t)(b_lo + k * 2), idesc,
+                                            (kb | k) != 0);
+                    umma_commit_elect(leader, smem_u32(bars + g.stages + stage));        // frees the smem slot when MMAs finish
                     if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(smem_u32(bars + 2 * g.stages + acc));                        // accumulator complete -> epilogue
+                umma_commit_elect(leader, smem_u32(bars + 2 * g.stages + acc));          // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

@@ -150,14 +150,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             }
         }
     } else if (warp == 4) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =================
+        {
             const uint32_t idesc = wt_idesc(N);
             uint64_t* bar_in = xform ? bar_ready : bar_landed;
             const uint64_t a_hi = wt_desc_mn(0, (uint32_t)g.Pd * 128), b_hi = wt_desc_mn(0, (uint32_t)g.Px * 128);
-            int tap_off8[9];
-#pragma unroll
-            for (int tp = 0; tp < 9; ++tp) tap_off8[tp] = tp < ntap ? g.tap_off[tap0 + tp] * 8 : 0;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t leader = elect_one();
             int i = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++i) {
                 const int si = i & 1;
@@ -175,17 +174,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 for (int ks = 0; ks < kWtKT / 16; ++ks) {
                     const uint64_t adesc = a_hi | (uint64_t)a_lo;
                     const uint32_t accum = (i | ks) != 0;
-#pragma unroll
-                    for (int tp = 0; tp < 9; ++tp) {
-                        if (tp < ntap)
-                            umma_bf16(tmem_base + tp * N, adesc, b_hi | (uint64_t)(b_lo + tap_off8[tp]), idesc, accum);
-                    }
+                    for (int tp = 0; tp < ntap; ++tp)
+                        umma_bf16_elect(leader, tmem_u + tp * N, adesc, b_hi | (uint64_t)(b_lo + (uint32_t)(g.tap_off[tap0 + tp] * 8)), idesc, accum);
                     a_lo += 16 * 8;
                     b_lo += 16 * 8;
                 }
-                umma_commit(smem_u32(bar_empty + si));
+                umma_commit_elect(leader, smem_u32(bar_empty + si));
             }
-            umma_commit(smem_u32(bar_done));
+            umma_commit_elect(leader, smem_u32(bar_done));
         }
     }
     // ================= flush: TMEM -> smem [co][ci][tap] -> vector reductions into dW =================
@@ -195,7 +191,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     }
     __syncthreads();                                            // all MMAs retired: the staging ring is free
     float* stg = reinterpret_cast<float*>(smem);
-    const int T = g.ks * g.ks;                                  // taps in the output layout (== n_taps)
+    const int T = g.ks * g.ks;                                  // taps in the output layout (== n_taps == ntap: one tap group)
+    const int row = N * ntap;                                   // floats per cout row of this block, contiguous in dW
+    const int pitch = row + 4;                                  // +16 B: rows of consecutive lanes fall into different banks
     if (warp >= 5) {
         const int q4 = warp & 3;
         const int m = q4 * 32 + lane;                           // TMEM lane == cout row of the block
@@ -207,28 +205,23 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 tmem_ld_wait();
                 if (m < g.co_blk) {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) stg[((size_t)m * N + c0 + k) * ntap + tp] = __uint_as_float(rr[k]);
+                    for (int k = 0; k < 16; ++k) stg[(size_t)m * pitch + (c0 + k) * ntap + tp] = __uint_as_float(rr[k]);
                 }
             }
     }
     tc_fence_before();
     __syncthreads();
-    {
-        // stg row m holds [ci][tap-in-group] contiguous; dW row (co0+m) wants [ci][all taps]: with one tap group the whole row is
-        // contiguous (vector reductions), otherwise scalar reductions
-        const int row = N * ntap;
-        if (g.n_tap_grp == 1 && (row & 3) == 0) {
-            for (int e = threadIdx.x * 4; e < g.co_blk * row; e += kWtThreads * 4) {
-                const int m = e / row, off = e % row;
-                float* dst = dw + ((size_t)(co0 + m) * g.Cin + ci0) * T + off;
-                wt_red4(dst, stg[e], stg[e + 1], stg[e + 2], stg[e + 3]);
-            }
-        } else {
-            for (int e = threadIdx.x; e < g.co_blk * row; e += kWtThreads) {
-                const int m = e / row, off = e % row;
-                const int ci = off / ntap, tp = off % ntap;
-                atomicAdd(dw + ((size_t)(co0 + m) * g.Cin + ci0 + ci) * T + tap0 + tp, stg[e]);
-            }
+    if ((row & 3) == 0 && g.n_tap_grp == 1) {
+        for (int e = threadIdx.x * 4; e < g.co_blk * row; e += kWtThreads * 4) {
+            const int m = e / row, off = e % row;
+            const float* src = stg + (size_t)m * pitch + off;
+            wt_red4(dw + ((size_t)(co0 + m) * g.Cin + ci0) * T + off, src[0], src[1], src[2], src[3]);
+        }
+    } else {
+        for (int e = threadIdx.x; e < g.co_blk * row; e += kWtThreads) {
+            const int m = e / row, off = e % row;
+            const int ci = off / ntap, tp = off % ntap;
+            atomicAdd(dw + ((size_t)(co0 + m) * g.Cin + ci0 + ci) * T + tap0 + tp, stg[(size_t)m * pitch + off]);
         }
     }
     __syncthreads();
@@ -246,7 +239,10 @@ static int wt_plan(int B, int H, int W, int Cin, int Cout, int ksize, WtPlan* pl
     if (g.Wp > 256) return RSS_ERR_SHAPE;
     g.n_taps = ksize * ksize;
     for (int a = 0, n = 0; a < ksize; ++a) for (int b = 0; b < ksize; ++b, ++n) g.tap_off[n] = (a - g.halo) * g.Wp + (b - g.halo);
-    g.ci_blk = Cin > 128 ? 128 : Cin; g.co_blk = Cout > 128 ? 128 : Cout;
+    // every CTA owns ALL taps of a (<=128 cout) x (32 cin) block: 9 x 32 = 288 TMEM columns, and each cout row of the block is one
+    // contiguous run of 32*k*k floats in the (Cout,Cin,k,k) gradient -> 16-byte vector reductions.  (A first version gave each CTA
+    // 128 cin and a third of the taps: 3-float runs, scalar atomics, 130 us on the 256-channel layers.)
+    g.ci_blk = 32; g.co_blk = Cout > 128 ? 128 : Cout;
     if (Cin % g.ci_blk || Cout % g.co_blk) return RSS_ERR_SHAPE;
     if (g.ci_blk % 16) return RSS_ERR_SHAPE;
     g.n_ci_blk = Cin / g.ci_blk; g.n_co_blk = Cout / g.co_blk;
@@ -265,7 +261,7 @@ static int wt_plan(int B, int H, int W, int Cin, int Cout, int ksize, WtPlan* pl
     // with a single dY plane the second (don't-care) group falls into the X planes of the same stage
     size_t need = 2 * stage + 16 * 8 + 64;
     if ((size_t)g.KCd * g.Pd + (size_t)g.KCx * g.Px < (size_t)2 * g.Pd) return RSS_ERR_SHAPE;
-    const size_t flush = (size_t)g.co_blk * g.ci_blk * g.taps_per_grp * 4;
+    const size_t flush = (size_t)g.co_blk * (g.ci_blk * g.taps_per_grp + 4) * 4;
     if (flush > need) need = flush;
     if (need + 1024 > 225 * 1024) return RSS_ERR_SHAPE;
     pl->smem = need + 1024;

@@ -76,6 +76,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
+// Warp-uniform issue: the WHOLE warp executes these with identical operands and one elected lane issues the instruction.
+// Keeping the issuing code warp-uniform lets the compiler hold descriptors in uniform registers; under `if (lane == 0)` it
+// cannot prove uniformity and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~22 instructions,
+// ~150 cycles per MMA measured by tools/probe/mma_probe.cu -- more than the tensor-pipe time of any N <= 256).
+__device__ __forceinline__ uint32_t elect_one() {            // 1 in exactly one (converged) lane of the warp
+    uint32_t is;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(is));
+    return is;
+}
+__device__ __forceinline__ void umma_bf16_elect(uint32_t leader, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t leader, uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader) : "memory");
+}
+
 // generic-proxy shared-memory writes (st.shared by producer threads) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
