@@ -111,6 +111,17 @@ int rss_bn_act_fwd(const void* x, const void* residual /*may be NULL*/, void* y,
 int rss_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
                       const float* mean, const float* invstd, float* sums, int64_t rows, int C, int act, int dtype,
                       cudaStream_t stream);
+/* same, without the memset node in front of the kernel: accum_scratch (float[2C]) + ticket (one counter) are a persistent
+ * per-layer scratch, zero on entry and left zero (the last block to arrive publishes the totals into `sums`); both may be
+ * NULL (then `sums` is cleared by a memset node first). */
+int rss_bn_bwd_reduce_ws(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, float* sums, float* accum_scratch, unsigned int* ticket,
+                         void* dz_out /*may be NULL: [rows][C] activation dtype, receives dz for rss_bn_bwd_apply_dz*/,
+                         int64_t rows, int C, int act, int dtype, cudaStream_t stream);
+/* second pass from the stored dz (used for the GELU layers, whose derivative is too expensive to recompute in both passes) */
+int rss_bn_bwd_apply_dz(const void* x, const void* dz, const float* scale, const float* mean, const float* invstd,
+                        const float* sums, float inv_count, void* dx, int64_t rows, int C, int dtype,
+                        const float* local_sums, float* dgamma_acc /*may be NULL*/, float* dbeta_acc, cudaStream_t stream);
 int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
                      const float* mean, const float* invstd, const float* sums, float inv_count,
                      void* dx, void* dresidual /*may be NULL: receives dz*/, int64_t rows, int C, int act, int dtype,
@@ -218,6 +229,11 @@ int rss_grad_sumsq(const float* grads, int64_t n, float grad_scale, double* sums
 int rss_sgd_step(float* params, float* grads, float* momentum_buf, int64_t n, const double* sumsq, float grad_scale,
                  float max_norm, const float* lr, float momentum, float weight_decay, int zero_grad,
                  void* bf16_shadow /*may be NULL*/, cudaStream_t stream);
+/* channels-last (Cout,kh,kw,Cin) bf16 copies of the k>1 convolution weights living in the flat fp32 parameter buffer, all in one
+ * launch.  table[e] = {src offset in floats, dst offset in elements, Cin, kh*kw} (int64 x4, device memory); row_start[e] = sum of
+ * Cout over the entries before e, row_start[n_entries] = total (int64, device memory); max_row_floats = max Cin*kh*kw. */
+int rss_shadow_cl_refresh(const float* params, void* shadow_cl, const int64_t* table, const int64_t* row_start,
+                          int n_entries, int max_row_floats, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,8 @@ SIGNATURES = {
     "rss_bn_eval_affine": (c_int, [P, P, P, P, c_float, c_int, P, P, P, P, P]),
     "rss_bn_act_fwd": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
     "rss_bn_bwd_reduce": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
+    "rss_bn_bwd_reduce_ws": (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
+    "rss_bn_bwd_apply_dz": (c_int, [P, P, P, P, P, P, c_float, P, c_int64, c_int, c_int, P, P, P, P]),
     "rss_bn_bwd_apply": (c_int, [P, P, P, P, P, P, P, P, c_float, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
     "rss_bn_fused_supported": (c_int, [c_int64, c_int, c_int, c_int]),
     "rss_bn_fwd_fused": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P, c_float, c_float, P, P, P, P, P, P]),
@@ -80,6 +82,7 @@ SIGNATURES = {
     "rss_seg_loss_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     "rss_grad_sumsq": (c_int, [P, c_int64, c_float, P, P]),
     "rss_sgd_step": (c_int, [P, P, P, c_int64, P, c_float, c_float, P, c_float, c_float, c_int, P, P]),
+    "rss_shadow_cl_refresh": (c_int, [P, P, P, P, c_int, c_int, P]),
 }
 
 _lib = None

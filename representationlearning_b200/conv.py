@@ -136,9 +136,18 @@ def register_shadow(param, view):
     param._rss_shadow = view
 
 
-def _lowp(w, dtype):
+def register_shadow_cl(param, view):
+    """channels-last bf16 view ((Cout,Cin,kh,kw) logical shape, (Cout,kh,kw,Cin) memory) refreshed once per step by trainer.py"""
+    param._rss_shadow_cl = view
+
+
+def _lowp(w, dtype, channels_last=False):
     if w is None or w.dtype == dtype:
         return w
+    if channels_last:
+        s = getattr(w, "_rss_shadow_cl", None)
+        if s is not None and s.dtype == dtype and s.shape == w.shape:
+            return s
     s = getattr(w, "_rss_shadow", None)
     if s is not None and s.dtype == dtype and s.numel() == w.numel():
         return s.view(w.shape)
@@ -149,7 +158,7 @@ class _ConvLib(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, dilation, bias_grad):
         x = ops.nhwc(x)
-        w = _lowp(weight, x.dtype).contiguous(memory_format=CL)
+        w = _lowp(weight, x.dtype, channels_last=True).contiguous(memory_format=CL)     # no-op on the per-step channels-last shadow
         b = _lowp(bias, x.dtype)
         y = torch.ops.aten.convolution(x, w, b, [stride, stride], [padding, padding], [dilation, dilation], False, [0, 0], 1)
         ctx.save_for_backward(x, w)
@@ -242,7 +251,7 @@ class _ConvIgemm(torch.autograd.Function):
             if not ctx.needs_input_grad[2 + s]:
                 gw.append(None); gb.append(None)
                 continue
-            w_lp = _lowp(weights[s], x.dtype).contiguous(memory_format=CL)
+            w_lp = _lowp(weights[s], x.dtype, channels_last=True).contiguous(memory_format=CL)
             want_b = biases[s] is not None and bias_grad
             dw, db = _wgrad(dy_, x, w_lp, weights[s], biases[s], want_b, 1, d * (k // 2), d, weights[s].dtype)
             gw.append(dw); gb.append(db)
@@ -324,7 +333,7 @@ class _ConvCF(torch.autograd.Function):
         w_lp = None
         if ctx.needs_input_grad[1]:
             if not _own_wgrad_ok(dy, x, weight, False, 1, k // 2, 1):
-                w_lp = _lowp(weight, x.dtype).contiguous(memory_format=CL)
+                w_lp = _lowp(weight, x.dtype, channels_last=True).contiguous(memory_format=CL)
             dw, _ = _wgrad(dy, x, w_lp if w_lp is not None else x, weight, None, False, 1, k // 2, 1, weight.dtype)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -332,7 +341,7 @@ class _ConvCF(torch.autograd.Function):
                 packed, _, nt, tdy, tdx, keep = _pack([weight], [None], [k], [1], Cout, Cin, True, x.device)
                 dx, _ = _cf_launch(dy, packed, nt, tdy, tdx, Cout, Cin, None, False, None)
             else:
-                w_lp = w_lp if w_lp is not None else _lowp(weight, x.dtype).contiguous(memory_format=CL)
+                w_lp = w_lp if w_lp is not None else _lowp(weight, x.dtype, channels_last=True).contiguous(memory_format=CL)
                 dx = torch.ops.aten.convolution_backward(dy, x, w_lp, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
                                                          [True, False, False])[0]
         return dx, dw, None

@@ -73,32 +73,107 @@ __global__ void gate_pool_kernel(const T* __restrict__ x, const T* __restrict__ 
     amax[((size_t)b * 2 + z) * HW + j] = (uint8_t)am;
 }
 
-__global__ void gate_map_kernel(const float* __restrict__ pooled, const float* __restrict__ w_sa1, const float* __restrict__ w_sa2,
-                                const float* __restrict__ lvl_w, const float* __restrict__ lvl_b,
-                                float* __restrict__ smap, float* __restrict__ gmap, int H, int W) {
+// 8 consecutive flat positions of one "channel" row k per thread (HW % 8 == 0): one 16/32-byte load instead of eight scalar ones,
+// and the 8 elements f0..f0+7 (f0 % 8 == 0) belong to ONE token, so the LayerNorm statistics are fetched once per vector.
+// Same per-element expressions and the same k order as the scalar kernel above.
+template <typename T>
+__device__ __forceinline__ void normed8_at(const T* __restrict__ base, const LnRef& ln, size_t img_row0, size_t f0, float v[8]) {
+    load8(base + f0, v);
+    if (ln.mean) {
+        const size_t n = img_row0 + f0 / kC;
+        const int c0 = (int)(f0 % kC);
+        const float mu = ln.mean[n], rs = ln.rstd[n];
+        float g[8], b[8];
+        load8(ln.gamma + c0, g);
+        load8(ln.beta + c0, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (v[i] - mu) * rs * g[i] + b[i];
+    }
+}
+
+// Four lanes share one group of 8 positions and split the 32 "channel" rows k between them (k = kq, kq + 4, ...: 8 rows each,
+// all 8 loads in flight at once), then combine with two xor-shuffles -- 4x the loads in flight of a one-thread-per-group loop,
+// which on this latency-bound pass (33.5 MB, 2 x 16 images) is what sets the run time.
+template <typename T>
+__global__ void __launch_bounds__(128) gate_pool_vec_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef lx, LnRef ly,
+                                                            float* __restrict__ pooled, uint8_t* __restrict__ amax, int HW) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kq = t & 3;
+    int j0 = (t >> 2) * 8;
+    const bool live = j0 < HW;
+    if (!live) j0 = 0;                                   // keep the whole warp in the shuffles
+    const int b = blockIdx.y, z = blockIdx.z;
+    const T* base = (z == 0 ? x : y) + (size_t)b * HW * kC;
+    const LnRef ln = z == 0 ? lx : ly;
+    float s[8], mx[8];
+    int am[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; mx[i] = -INFINITY; am[i] = 0; }
+#pragma unroll
+    for (int kk = 0; kk < kC / 4; ++kk) {
+        const int k = kk * 4 + kq;
+        float v[8];
+        normed8_at(base, ln, (size_t)b * HW, (size_t)k * HW + j0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s[i] += v[i];
+            if (v[i] > mx[i]) { mx[i] = v[i]; am[i] = k; }          // k ascending within a lane: first occurrence wins
+        }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+            const float om = __shfl_xor_sync(0xffffffffu, mx[i], o);
+            const int oa = __shfl_xor_sync(0xffffffffu, am[i], o);
+            if (om > mx[i] || (om == mx[i] && oa < am[i])) { mx[i] = om; am[i] = oa; }     // torch.max: first arg-max on ties
+        }
+    }
+    if (!live || kq != 0) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] *= (1.0f / kC);
+    store8(pooled + ((size_t)b * 4 + z * 2 + 0) * HW + j0, s);
+    store8(pooled + ((size_t)b * 4 + z * 2 + 1) * HW + j0, mx);
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { lo |= (uint32_t)am[i] << (8 * i); hi |= (uint32_t)am[4 + i] << (8 * i); }
+    *reinterpret_cast<uint2*>(amax + ((size_t)b * 2 + z) * HW + j0) = make_uint2(lo, hi);
+}
+
+// 32x8-pixel tile per block: the four pooled maps of the tile (+3-pixel halo, zero outside the image = the conv's padding) are
+// staged in shared memory once, so the 2 x 2 x 49 taps per pixel are shared-memory reads instead of bounds-checked global loads.
+constexpr int kGmTW = 32, kGmTH = 8, kGmHW = kGmTW + 6, kGmHH = kGmTH + 6;
+__global__ void __launch_bounds__(kGmTW * kGmTH)
+gate_map_kernel(const float* __restrict__ pooled, const float* __restrict__ w_sa1, const float* __restrict__ w_sa2,
+                const float* __restrict__ lvl_w, const float* __restrict__ lvl_b,
+                float* __restrict__ smap, float* __restrict__ gmap, int H, int W) {
     __shared__ float ws[2][98];
+    __shared__ float tile[4][kGmHH][kGmHW + 1];
     for (int i = threadIdx.x; i < 196; i += blockDim.x) ws[i / 98][i % 98] = (i < 98 ? w_sa1[i] : w_sa2[i - 98]);
-    __syncthreads();
     const int HW = H * W, b = blockIdx.y;
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= HW) return;
-    const int h = pix / W, w = pix % W;
+    const int tiles_x = (W + kGmTW - 1) / kGmTW;
+    const int h0 = (blockIdx.x / tiles_x) * kGmTH, w0 = (blockIdx.x % tiles_x) * kGmTW;
+    for (int i = threadIdx.x; i < 4 * kGmHH * kGmHW; i += blockDim.x) {
+        const int m = i / (kGmHH * kGmHW), r = (i / kGmHW) % kGmHH, c = i % kGmHW;
+        const int yy = h0 + r - 3, xx = w0 + c - 3;
+        tile[m][r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(pooled + ((size_t)b * 4 + m) * HW + yy * W + xx) : 0.f;
+    }
+    __syncthreads();
+    const int tr = threadIdx.x / kGmTW, tc = threadIdx.x % kGmTW;
+    const int h = h0 + tr, w = w0 + tc;
+    if (h >= H || w >= W) return;
+    const int pix = h * W + w;
     float s[2];
 #pragma unroll
     for (int z = 0; z < 2; ++z) {
         float acc = 0.f;
-        for (int ci = 0; ci < 2; ++ci) {
-            const float* src = pooled + ((size_t)b * 4 + z * 2 + ci) * HW;
-            for (int dy = 0; dy < 7; ++dy) {
-                const int yy = h + dy - 3;
-                if (yy < 0 || yy >= H) continue;
-                for (int dx = 0; dx < 7; ++dx) {
-                    const int xx = w + dx - 3;
-                    if (xx < 0 || xx >= W) continue;
-                    acc += src[yy * W + xx] * ws[z][ci * 49 + dy * 7 + dx];
-                }
-            }
-        }
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+            for (int dy = 0; dy < 7; ++dy)                       // same tap order as the reference conv; out-of-image taps add 0
+#pragma unroll
+                for (int dx = 0; dx < 7; ++dx) acc += tile[z * 2 + ci][tr + dy][tc + dx] * ws[z][ci * 49 + dy * 7 + dx];
         s[z] = 1.0f / (1.0f + expf(-acc));
     }
     const float l0 = lvl_w[0] * s[0] + lvl_w[1] * s[1] + lvl_b[0];
@@ -1166,6 +1241,38 @@ __global__ void gate_bwd_reduce_kernel(const float* __restrict__ dxg, const floa
     dgmap[((size_t)b * 2 + z) * HW + j] = s;
 }
 
+template <typename T>
+__global__ void __launch_bounds__(128) gate_bwd_reduce_vec_kernel(const float* __restrict__ dxg, const float* __restrict__ dyg,
+                                                                  const T* __restrict__ x, const T* __restrict__ y, LnRef lx, LnRef ly,
+                                                                  float* __restrict__ dgmap, int HW) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;         // 4 lanes per group of 8 positions, rows k split between them
+    const int kq = t & 3;
+    int j0 = (t >> 2) * 8;
+    const bool live = j0 < HW;
+    if (!live) j0 = 0;
+    const int b = blockIdx.y, z = blockIdx.z;
+    const float* d = (z == 0 ? dxg : dyg) + (size_t)b * HW * kC;
+    const T* n = (z == 0 ? x : y) + (size_t)b * HW * kC;
+    const LnRef ln = z == 0 ? lx : ly;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < kC / 4; ++kk) {
+        const int k = kk * 4 + kq;
+        float v[8], g[8];
+        load8(d + (size_t)k * HW + j0, g);
+        normed8_at(n, ln, (size_t)b * HW, (size_t)k * HW + j0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += g[i] * v[i];
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+    if (live && kq == 0) store8(dgmap + ((size_t)b * 2 + z) * HW + j0, s);
+}
+
 // softmax(2) -> 1x1 conv -> sigmoid backward; writes dpre (grad at the 7x7 conv outputs), accumulates dlvl_w/dlvl_b
 __global__ void gate_bwd_map_kernel(const float* __restrict__ dgmap, const float* __restrict__ gmap, const float* __restrict__ smap,
                                     const float* __restrict__ lvl_w, float* __restrict__ dpre,
@@ -1261,10 +1368,23 @@ __global__ void gate_bwd_apply_kernel(const float* __restrict__ dxg, const float
         float v[8];
         load8(src + f0, v);
         int j = (int)(f0 % HW), kk = (int)(f0 / HW);
+        if ((HW & 7) == 0) {                 // the 8 positions stay inside one row k of the flat view: vector loads of the maps
+            float g8[8], a8[8], m8[8];
+            load8(gm + j, g8);
+            load8(da + j, a8);
+            load8(dm + j, m8);
+            const uint2 am8 = __ldg(reinterpret_cast<const uint2*>(am + j));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            v[i] = v[i] * gm[j] + da[j] * (1.0f / kC) + ((int)am[j] == kk ? dm[j] : 0.f);
-            if (++j == HW) { j = 0; ++kk; }
+            for (int i = 0; i < 8; ++i) {
+                const int a = (int)(((i < 4 ? am8.x : am8.y) >> (8 * (i & 3))) & 0xffu);
+                v[i] = v[i] * g8[i] + a8[i] * (1.0f / kC) + (a == kk ? m8[i] : 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] = v[i] * gm[j] + da[j] * (1.0f / kC) + ((int)am[j] == kk ? dm[j] : 0.f);
+                if (++j == HW) { j = 0; ++kk; }
+            }
         }
         if (add) {
             float a[8];
@@ -1293,10 +1413,16 @@ static int attn_fwd_impl(const void* x, const void* y, const rss_attn_params* p,
         if ((rc = rss_layernorm_fwd(y, nullptr, ln_stats + 2 * rows, ln_stats + 3 * rows, p->ln_w, p->ln_b, p->ln_eps, rows, kC, dt, st)) != RSS_OK) return rc;
     }
     const LnRef lx = ln_ref(p, ln_stats, rows, 0), ly = ln_ref(p, ln_stats, rows, 1);
-    dim3 pg((g.HW + 255) / 256, B, 2);
-    gate_pool_kernel<T><<<pg, 256, 0, st>>>((const T*)x, (const T*)y, lx, ly, pooled, amax, g.HW);
-    dim3 mg((g.HW + 127) / 128, B);
-    gate_map_kernel<<<mg, 128, 0, st>>>(pooled, p->sa1_w, p->sa2_w, p->lvl_w, p->lvl_b, smap, gmap, H, W);
+    // (every pointer below is an allocation base + a multiple of HW elements: HW % 8 == 0 keeps the 16/32-byte vectors aligned)
+    if (g.HW % 8 == 0) {
+        dim3 pg((g.HW / 8 * 4 + 127) / 128, B, 2);
+        gate_pool_vec_kernel<T><<<pg, 128, 0, st>>>((const T*)x, (const T*)y, lx, ly, pooled, amax, g.HW);
+    } else {
+        dim3 pg((g.HW + 255) / 256, B, 2);
+        gate_pool_kernel<T><<<pg, 256, 0, st>>>((const T*)x, (const T*)y, lx, ly, pooled, amax, g.HW);
+    }
+    dim3 mg(((W + kGmTW - 1) / kGmTW) * ((H + kGmTH - 1) / kGmTH), B);
+    gate_map_kernel<<<mg, kGmTW * kGmTH, 0, st>>>(pooled, p->sa1_w, p->sa2_w, p->lvl_w, p->lvl_b, smap, gmap, H, W);
     const size_t smem = kFwdSmemFloats * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -1355,8 +1481,13 @@ static int attn_bwd_impl(const void* dout, const void* x, const void* y, const r
     } else {
         win_attn_bwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)y, lx, ly, gmap, (const T*)dout, dxg, dyg, *p, *gr, g);
     }
-    dim3 pg((g.HW + 255) / 256, B, 2);
-    gate_bwd_reduce_kernel<T><<<pg, 256, 0, st>>>(dxg, dyg, (const T*)x, (const T*)y, lx, ly, dgmap, g.HW);
+    if (g.HW % 8 == 0) {
+        dim3 pg((g.HW / 8 * 4 + 127) / 128, B, 2);
+        gate_bwd_reduce_vec_kernel<T><<<pg, 128, 0, st>>>(dxg, dyg, (const T*)x, (const T*)y, lx, ly, dgmap, g.HW);
+    } else {
+        dim3 pg((g.HW + 255) / 256, B, 2);
+        gate_bwd_reduce_kernel<T><<<pg, 256, 0, st>>>(dxg, dyg, (const T*)x, (const T*)y, lx, ly, dgmap, g.HW);
+    }
     dim3 mg((g.HW + 255) / 256, B);
     gate_bwd_map_kernel<<<mg, 256, 0, st>>>(dgmap, gmap, smap, p->lvl_w, dpre, gr->lvl_w, gr->lvl_b, g.HW);
     dim3 cg(((H + 31) / 32) * ((W + 31) / 32), B, 2);

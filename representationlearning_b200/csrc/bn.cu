@@ -336,8 +336,11 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      float* __restrict__ sums /*[2][C]: sum dz, sum dz*xhat*/,
+                                     float* __restrict__ accum /*[2][C] persistent zeroed scratch, or NULL: sums was zeroed by the caller*/,
+                                     unsigned int* __restrict__ ticket, T* __restrict__ dz_out /*NULL or [rows][C]: dz kept for the apply pass*/,
                                      int64_t rows, int C, int cg, int rpb) {
     extern __shared__ float sm[];           // [rpb][2][C]
+    __shared__ bool is_last;
     const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
     float sc[8], sh[8], mu[8], is[8], a0[8], a1[8];
 #pragma unroll
@@ -361,6 +364,7 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
         for (int u = 0; u < U; ++u) {
             float dz[8], xh[8];
             bn_dz<T, ACT, HAS_Y>(rx[u], ry[u], rd[u], sc, sh, mu, is, dz, xh);
+            if (dz_out) store8(dz_out + (row + u * stride) * C + sub * 8, dz);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { a0[i] += dz[i]; a1[i] += dz[i] * xh[i]; }
         }
@@ -373,6 +377,7 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
         if (HAS_Y) ldraw(y + off, ry);
         float dz[8], xh[8];
         bn_dz<T, ACT, HAS_Y>(rx, ry, rd, sc, sh, mu, is, dz, xh);
+        if (dz_out) store8(dz_out + off, dz);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { a0[i] += dz[i]; a1[i] += dz[i] * xh[i]; }
     }
@@ -386,8 +391,22 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
         const int which = c / C, ch = c % C;
         float s = 0.f;
         for (int rr = 0; rr < rpb; ++rr) s += sm[((size_t)rr * 2 + which) * C + ch];
-        atomicAdd(sums + which * C + ch, s);
+        atomicAdd((accum ? accum : sums) + which * C + ch, s);
     }
+    if (!accum) return;
+    // no memset node in front of the kernel (one launch + one dependency edge less per layer on a latency-bound chain): the
+    // totals are built in a persistent scratch that every launch leaves zeroed; the last block to arrive publishes them
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+        sums[c] = __ldcg(accum + c);
+        accum[c] = 0.f;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
 }
 
 template <typename T, int ACT, bool HAS_Y>
@@ -437,6 +456,55 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
         ldraw(dy + off, rd);
         if (HAS_Y) ldraw(y + off, ry);
         one(rx, ry, rd, off);
+    }
+}
+
+// apply pass when the reduce pass kept dz = dy*act'(z) (GELU layers: the derivative costs ~30 instructions and two MUFU ops per
+// element, which made BOTH passes issue-bound at ~3x their HBM time; with dz stored once the second pass is a plain stream)
+template <typename T>
+__global__ void bn_bwd_apply_dz_kernel(const T* __restrict__ x, const T* __restrict__ dz, const float* __restrict__ scale,
+                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       const float* __restrict__ sums, float inv_count, T* __restrict__ dx,
+                                       int64_t rows, int C, int cg, int rpb,
+                                       const float* __restrict__ local_sums, float* __restrict__ dgamma_acc, float* __restrict__ dbeta_acc) {
+    const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
+    if (dgamma_acc && blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta_acc[c] += local_sums[c]; dgamma_acc[c] += local_sums[C + c]; }
+    }
+    float sc[8], mu[8], is[8], m0[8], m1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = scale[sub * 8 + i]; mu[i] = mean[sub * 8 + i]; is[i] = invstd[sub * 8 + i];
+        m0[i] = sums[sub * 8 + i] * inv_count; m1[i] = sums[C + sub * 8 + i] * inv_count;
+    }
+    const int64_t stride = (int64_t)gridDim.x * rpb;
+    int64_t row = (int64_t)blockIdx.x * rpb + r;
+    constexpr int U = 4;
+    auto one = [&](const Raw8<T>& rx, const Raw8<T>& rz, int64_t off) {
+        float v[8], d[8], o[8];
+        unpack8(rx, v);
+        unpack8(rz, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = sc[i] * (d[i] - m0[i] - (v[i] - mu[i]) * is[i] * m1[i]);
+        store8(dx + off, o);
+    };
+    for (; row + (U - 1) * stride < rows; row += U * stride) {
+        Raw8<T> rx[U], rz[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t off = (row + u * stride) * C + sub * 8;
+            ldraw(x + off, rx[u]);
+            ldraw(dz + off, rz[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) one(rx[u], rz[u], (row + u * stride) * C + sub * 8);
+    }
+    for (; row < rows; row += stride) {
+        const int64_t off = row * C + sub * 8;
+        Raw8<T> rx, rz;
+        ldraw(x + off, rx);
+        ldraw(dz + off, rz);
+        one(rx, rz, off);
     }
 }
 
@@ -765,17 +833,27 @@ extern "C" int rss_bn_act_fwd(const void* x, const void* residual, void* y, cons
     return check_launch();
 }
 
-extern "C" int rss_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
-                                 const float* mean, const float* invstd, float* sums, int64_t rows, int C, int act, int dtype,
-                                 cudaStream_t st) {
-    if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
+// accum_scratch/ticket: optional persistent per-layer scratch (float[2C] + one counter, zero on entry, left zero): with it the
+// launch needs no memset of `sums` in front of it.  Both NULL: `sums` is cleared by a memset node first.
+extern "C" int rss_bn_bwd_reduce_ws(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
+                                    const float* mean, const float* invstd, float* sums, float* accum_scratch, unsigned int* ticket,
+                                    void* dz_out, int64_t rows, int C, int act, int dtype, cudaStream_t st) {
+    if (C <= 0 || C % 8 || rows <= 0 || (accum_scratch == nullptr) != (ticket == nullptr)) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 8, 4);
     const size_t smem = (size_t)g.rpb * 2 * C * sizeof(float);
-    cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st);
-    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return RSS_ERR_CUDA; }
-    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_reduce_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, smem, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, rows, C, g.cg, g.rpb)));
+    if (!accum_scratch) {
+        cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st);
+        if (e != cudaSuccess) { g_last_cuda_error = (int)e; return RSS_ERR_CUDA; }
+    }
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_reduce_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, smem, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, accum_scratch, ticket, (T*)dz_out, rows, C, g.cg, g.rpb)));
     return check_launch();
+}
+
+extern "C" int rss_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
+                                 const float* mean, const float* invstd, float* sums, int64_t rows, int C, int act, int dtype,
+                                 cudaStream_t st) {
+    return rss_bn_bwd_reduce_ws(x, y, dy, scale, shift, mean, invstd, sums, nullptr, nullptr, nullptr, rows, C, act, dtype, st);
 }
 
 extern "C" int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
@@ -788,6 +866,18 @@ extern "C" int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, co
     const int grid = bn_grid(rows, g.rpb * 4, 8);
     RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
                                                                                                            local_sums, dgamma_acc, dbeta_acc)));
+    return check_launch();
+}
+
+// dx = scale*(dz - sum_dz/n - xhat*sum_dzxhat/n) from the dz = dy*act'(.) kept by rss_bn_bwd_reduce_ws(dz_out)
+extern "C" int rss_bn_bwd_apply_dz(const void* x, const void* dz, const float* scale, const float* mean, const float* invstd,
+                                   const float* sums, float inv_count, void* dx, int64_t rows, int C, int dtype,
+                                   const float* local_sums, float* dgamma_acc, float* dbeta_acc, cudaStream_t st) {
+    if (C <= 0 || C % 8 || rows <= 0 || !dz) return RSS_ERR_SHAPE;
+    const BnGeom g = bn_geom(C);
+    const int grid = bn_grid(rows, g.rpb * 4, 8);
+    RSS_DISPATCH_DTYPE(dtype, bn_bwd_apply_dz_kernel<T><<<grid, g.threads, 0, st>>>((const T*)x, (const T*)dz, scale, mean, invstd, sums,
+                       inv_count, (T*)dx, rows, C, g.cg, g.rpb, local_sums, dgamma_acc, dbeta_acc));
     return check_launch();
 }
 

@@ -30,72 +30,81 @@ __device__ __forceinline__ void bilinear_src_l(int o, float scale, int in, int& 
 }
 
 // acc layout (floats): [0] ce_sum, [1] n_valid, [2..2+B) A_b, then ints: [2+B .. 2+2B) has_fg, [2+2B .. 2+3B) has_bg
+//
+// Gradient w.r.t. the low-resolution logits = transpose of the bilinear up-sampling applied to the per-pixel softmax gradient.
+// The transpose is done as a GATHER in two separable passes over shared memory (x, then y): every low-resolution cell sums the
+// <= 9 output columns (rows) that touch it.  (A first version scattered with shared-memory float atomics: sm_100 has no native
+// shared fp32 add -- SASS showed ATOMS.CAST.SPIN loops, ~16-way contended -- and the kernel took 674 us for 37 MB of traffic.)
 __global__ void __launch_bounds__(kTile * kTile)
 seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ acc,
                     float* __restrict__ gdir /*[B][h][w][8], zeroed*/, int B, int h, int w, int H, int W,
                     float sy, float sx, int ignore_index) {
-    __shared__ float tile[kFoot][kFoot][kNCP];
+    __shared__ float G[kTile][kTile][kNC];          // per-pixel d CE / d z (0 where ignored / outside the image)
+    __shared__ float T[kTile][kFoot][kNC];          // after the x pass: [output row][low-res column][class]
     __shared__ float red[3][kTile * kTile / 32];
     __shared__ int flags[2];
+    __shared__ int cx0[kTile], cx1[kTile], cy0[kTile], cy1[kTile];     // footprint-relative source indices per output column / row
+    __shared__ float clx[kTile], cly[kTile];
     const int tiles_x = (W + kTile - 1) / kTile;
     const int ty0 = (blockIdx.x / tiles_x) * kTile, tx0 = (blockIdx.x % tiles_x) * kTile;
     const int b = blockIdx.y;
     int fy0, fx0, tmp; float tl;
     bilinear_src_l(ty0, sy, h, fy0, tmp, tl);
     bilinear_src_l(tx0, sx, w, fx0, tmp, tl);
-    for (int i = threadIdx.x; i < kFoot * kFoot * kNCP; i += blockDim.x) (&tile[0][0][0])[i] = 0.f;
     if (threadIdx.x < 2) flags[threadIdx.x] = 0;
     __syncthreads();
-    const int oy = ty0 + threadIdx.x / kTile, ox = tx0 + threadIdx.x % kTile;
+    const int r = threadIdx.x / kTile, c = threadIdx.x % kTile;
+    const int oy = ty0 + r, ox = tx0 + c;
     float ce = 0.f, nv = 0.f, A = 0.f;
-    if (oy < H && ox < W) {
+    float gk[kNC];
+#pragma unroll
+    for (int k = 0; k < kNC; ++k) gk[k] = 0.f;
+    {
         int y0, y1, x0, x1; float ly, lx;
-        bilinear_src_l(oy, sy, h, y0, y1, ly);
-        bilinear_src_l(ox, sx, w, x0, x1, lx);
-        const float* base = logits + (int64_t)b * h * w * kNCP;
-        const float4* p00 = reinterpret_cast<const float4*>(base + ((int64_t)y0 * w + x0) * kNCP);
-        const float4* p01 = reinterpret_cast<const float4*>(base + ((int64_t)y0 * w + x1) * kNCP);
-        const float4* p10 = reinterpret_cast<const float4*>(base + ((int64_t)y1 * w + x0) * kNCP);
-        const float4* p11 = reinterpret_cast<const float4*>(base + ((int64_t)y1 * w + x1) * kNCP);
-        float a[8], bq[8], c[8], d[8];
-        *reinterpret_cast<float4*>(a) = __ldg(p00); *reinterpret_cast<float4*>(a + 4) = __ldg(p00 + 1);
-        *reinterpret_cast<float4*>(bq) = __ldg(p01); *reinterpret_cast<float4*>(bq + 4) = __ldg(p01 + 1);
-        *reinterpret_cast<float4*>(c) = __ldg(p10); *reinterpret_cast<float4*>(c + 4) = __ldg(p10 + 1);
-        *reinterpret_cast<float4*>(d) = __ldg(p11); *reinterpret_cast<float4*>(d + 4) = __ldg(p11 + 1);
-        const float hy = 1.f - ly, hx = 1.f - lx;
-        float z[kNC], mx = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < kNC; ++k) {
-            z[k] = hy * (hx * a[k] + lx * bq[k]) + ly * (hx * c[k] + lx * d[k]);
-            mx = fmaxf(mx, z[k]);
-        }
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < kNC; ++k) s += expf(z[k] - mx);
-        const float lse = mx + logf(s);
-        const int64_t lbl = labels[((int64_t)b * H + oy) * W + ox];
-        const bool valid = lbl != (int64_t)ignore_index;
-        const int t = valid ? (int)lbl : 0;
-        float zt = 0.f;
-#pragma unroll
-        for (int k = 0; k < kNC; ++k) zt = (k == t) ? z[k] : zt;
-        A = 1.f - expf(zt - lse);
-        if (lbl > 0) flags[0] = 1; else flags[1] = 1;          // benign race: all writers store 1
-        if (valid) {
-            ce = lse - zt;
-            nv = 1.f;
-            const int ry0 = y0 - fy0, ry1 = y1 - fy0, rx0 = x0 - fx0, rx1 = x1 - fx0;
-            const float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
+        bilinear_src_l(oy < H ? oy : H - 1, sy, h, y0, y1, ly);
+        bilinear_src_l(ox < W ? ox : W - 1, sx, w, x0, x1, lx);
+        if (r == 0) { cx0[c] = ox < W ? x0 - fx0 : -1; cx1[c] = ox < W ? x1 - fx0 : -1; clx[c] = lx; }
+        if (c == 0) { cy0[r] = oy < H ? y0 - fy0 : -1; cy1[r] = oy < H ? y1 - fy0 : -1; cly[r] = ly; }
+        if (oy < H && ox < W) {
+            const float* base = logits + (int64_t)b * h * w * kNCP;
+            const float4* p00 = reinterpret_cast<const float4*>(base + ((int64_t)y0 * w + x0) * kNCP);
+            const float4* p01 = reinterpret_cast<const float4*>(base + ((int64_t)y0 * w + x1) * kNCP);
+            const float4* p10 = reinterpret_cast<const float4*>(base + ((int64_t)y1 * w + x0) * kNCP);
+            const float4* p11 = reinterpret_cast<const float4*>(base + ((int64_t)y1 * w + x1) * kNCP);
+            float a[8], bq[8], cc[8], d[8];
+            *reinterpret_cast<float4*>(a) = __ldg(p00); *reinterpret_cast<float4*>(a + 4) = __ldg(p00 + 1);
+            *reinterpret_cast<float4*>(bq) = __ldg(p01); *reinterpret_cast<float4*>(bq + 4) = __ldg(p01 + 1);
+            *reinterpret_cast<float4*>(cc) = __ldg(p10); *reinterpret_cast<float4*>(cc + 4) = __ldg(p10 + 1);
+            *reinterpret_cast<float4*>(d) = __ldg(p11); *reinterpret_cast<float4*>(d + 4) = __ldg(p11 + 1);
+            const float hy = 1.f - ly, hx = 1.f - lx;
+            float z[kNC], mx = -INFINITY;
 #pragma unroll
             for (int k = 0; k < kNC; ++k) {
-                const float gk = expf(z[k] - lse) - (k == t ? 1.f : 0.f);
-                atomicAdd(&tile[ry0][rx0][k], w00 * gk);
-                atomicAdd(&tile[ry0][rx1][k], w01 * gk);
-                atomicAdd(&tile[ry1][rx0][k], w10 * gk);
-                atomicAdd(&tile[ry1][rx1][k], w11 * gk);
+                z[k] = hy * (hx * a[k] + lx * bq[k]) + ly * (hx * cc[k] + lx * d[k]);
+                mx = fmaxf(mx, z[k]);
+            }
+            float e[kNC], s = 0.f;
+#pragma unroll
+            for (int k = 0; k < kNC; ++k) { e[k] = expf(z[k] - mx); s += e[k]; }
+            const float lse = mx + logf(s);
+            const int64_t lbl = labels[((int64_t)b * H + oy) * W + ox];
+            const bool valid = lbl != (int64_t)ignore_index;
+            const int t = valid ? (int)lbl : 0;
+            float zt = 0.f;
+#pragma unroll
+            for (int k = 0; k < kNC; ++k) zt = (k == t) ? z[k] : zt;
+            A = 1.f - expf(zt - lse);
+            if (lbl > 0) flags[0] = 1; else flags[1] = 1;          // benign race: all writers store 1
+            if (valid) {
+                ce = lse - zt;
+                nv = 1.f;
+#pragma unroll
+                for (int k = 0; k < kNC; ++k) gk[k] = expf(z[k] - lse) - (k == t ? 1.f : 0.f);
             }
         }
     }
+#pragma unroll
+    for (int k = 0; k < kNC; ++k) G[r][c][k] = gk[k];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     ce = warp_sum(ce); nv = warp_sum(nv); A = warp_sum(A);
     if (lane == 0) { red[0][warp] = ce; red[1][warp] = nv; red[2][warp] = A; }
@@ -107,9 +116,43 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
     }
     if (threadIdx.x == 3 && flags[0]) atomicOr(reinterpret_cast<int*>(acc + 2 + B) + b, 1);
     if (threadIdx.x == 4 && flags[1]) atomicOr(reinterpret_cast<int*>(acc + 2 + 2 * B) + b, 1);
+    // ---- x pass: T[row][rx][k] = sum over the output columns whose bilinear footprint contains low-res column fx0 + rx
+    for (int i = threadIdx.x; i < kTile * kFoot * kNC; i += blockDim.x) {
+        const int k = i % kNC, rx = (i / kNC) % kFoot, row = i / (kNC * kFoot);
+        int lo = 0, hi = kTile - 1;
+        if (sx > 0.f) {                      // columns with scale*ox in (xx - 1, xx + 1), padded by one against rounding
+            const float xx = (float)(fx0 + rx);
+            lo = (int)((xx - 1.f) / sx) - 1 - tx0;
+            hi = (int)((xx + 1.f) / sx) + 1 - tx0;
+            lo = lo < 0 ? 0 : lo;
+            hi = hi > kTile - 1 ? kTile - 1 : hi;
+        }
+        float s = 0.f;
+        for (int cc = lo; cc <= hi; ++cc) {
+            const float v = G[row][cc][k], l = clx[cc];
+            if (cx0[cc] == rx) s += (1.f - l) * v;
+            if (cx1[cc] == rx) s += l * v;
+        }
+        T[row][rx][k] = s;
+    }
+    __syncthreads();
+    // ---- y pass, straight into the global low-resolution gradient (cells on tile borders are shared with the neighbours)
     for (int i = threadIdx.x; i < kFoot * kFoot * kNC; i += blockDim.x) {
         const int k = i % kNC, rx = (i / kNC) % kFoot, ry = i / (kNC * kFoot);
-        const float vsum = tile[ry][rx][k];
+        int lo = 0, hi = kTile - 1;
+        if (sy > 0.f) {
+            const float yy = (float)(fy0 + ry);
+            lo = (int)((yy - 1.f) / sy) - 1 - ty0;
+            hi = (int)((yy + 1.f) / sy) + 1 - ty0;
+            lo = lo < 0 ? 0 : lo;
+            hi = hi > kTile - 1 ? kTile - 1 : hi;
+        }
+        float vsum = 0.f;
+        for (int rr = lo; rr <= hi; ++rr) {
+            const float v = T[rr][rx][k], l = cly[rr];
+            if (cy0[rr] == ry) vsum += (1.f - l) * v;
+            if (cy1[rr] == ry) vsum += l * v;
+        }
         const int yy = fy0 + ry, xx = fx0 + rx;
         if (vsum != 0.f && yy < h && xx < w) atomicAdd(gdir + (((int64_t)b * h + yy) * w + xx) * kNCP + k, vsum);
     }
@@ -189,9 +232,48 @@ __global__ void sgd_step_kernel(float* __restrict__ p, float* __restrict__ g, fl
     }
 }
 
+// Channels-last bf16 copies of the k x k (k > 1) convolution weights, refreshed once per step right after the update:
+// the library convolutions want (Cout, kh, kw, Cin) operands for NHWC activations, and converting the (Cout, Cin, kh, kw)
+// shadow per call cost one small permute kernel in front of every 3x3 convolution (~170 per step, each on a latency-bound
+// chain).  One "row" = one output channel of one weight: Cin*kk contiguous floats in, Cin*kk contiguous bf16 out, permuted
+// through shared memory so both sides are coalesced.  table[e] = {src offset (floats), dst offset (elements), Cin, kk};
+// row_start[e] = first global row of entry e (row_start[n_entries] = total rows).
+__global__ void shadow_cl_kernel(const float* __restrict__ p, __nv_bfloat16* __restrict__ out, const int64_t* __restrict__ table,
+                                 const int64_t* __restrict__ row_start, int n_entries) {
+    extern __shared__ float row_sm[];
+    const int64_t total = row_start[n_entries];
+    for (int64_t row = blockIdx.x; row < total; row += gridDim.x) {
+        int lo = 0, hi = n_entries - 1;                     // last entry with row_start <= row
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (row_start[mid] <= row) lo = mid; else hi = mid - 1;
+        }
+        const int64_t* e = table + (int64_t)lo * 4;
+        const int cin = (int)e[2], kk = (int)e[3], L = cin * kk;
+        const int64_t local = row - row_start[lo];
+        const float* src = p + e[0] + local * L;
+        __nv_bfloat16* dst = out + e[1] + local * L;
+        for (int j = threadIdx.x; j < L; j += blockDim.x) row_sm[j] = src[j];
+        __syncthreads();
+        for (int j = threadIdx.x; j < L; j += blockDim.x) {
+            const int t = j / cin, ci = j - t * cin;
+            dst[j] = __float2bfloat16_rn(row_sm[ci * kk + t]);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace rss
 
 using namespace rss;
+
+extern "C" int rss_shadow_cl_refresh(const float* params, void* shadow_cl, const int64_t* table, const int64_t* row_start,
+                                     int n_entries, int max_row_floats, cudaStream_t st) {
+    if (n_entries <= 0 || max_row_floats <= 0 || max_row_floats > 12 * 1024) return RSS_ERR_SHAPE;
+    shadow_cl_kernel<<<num_sms() * 8, 256, (size_t)max_row_floats * sizeof(float), st>>>(params, (__nv_bfloat16*)shadow_cl, table,
+                                                                                          row_start, n_entries);
+    return check_launch();
+}
 
 extern "C" size_t rss_seg_loss_acc_floats(int B) { return (size_t)(2 + 3 * B); }
 

@@ -24,7 +24,9 @@ MODEL_EXTRA = {
 }
 
 
-BRANCH_STREAMS = {"on": os.environ.get("RSS_BRANCH_STREAMS", "1") != "0"}
+# RSS_BRANCH_STREAMS: 0 = everything on one stream, 1 = branches forked/joined inside each module, 2 (default) = data-flow schedule
+# (HighResolutionModule.flow)
+BRANCH_STREAMS = {"on": os.environ.get("RSS_BRANCH_STREAMS", "2") != "0", "flow": os.environ.get("RSS_BRANCH_STREAMS", "2") == "2"}
 _SIDE = {}
 
 
@@ -158,10 +160,7 @@ class HighResolutionModule(nn.Module):
         return x, 0
 
     def _run_branches(self, x):
-        """The branches of a module are independent until the fuse step: the low-resolution ones (few tiles, latency-bound
-        kernels) run on side streams next to the 128x128 branch, so that inside the captured CUDA graph they become
-        parallel sub-graphs that fill SMs the high-resolution kernels leave idle.  Autograd replays each branch's backward
-        on the stream of its forward, so the backward pass is overlapped the same way."""
+        """RSS_BRANCH_STREAMS=1 schedule: the branches of a module run on side streams and are joined before the fuse step."""
         if not BRANCH_STREAMS["on"] or not x[0].is_cuda:
             return [self.branches[i](x[i]) for i in range(self.num_branches)]
         dev = x[0].device
@@ -183,6 +182,8 @@ class HighResolutionModule(nn.Module):
     def forward(self, x):
         if self.num_branches == 1:
             return [self.branches[0](x[0])]
+        if _dataflow(x[0]):
+            return flow_join(self.flow(x))
         x = self._run_branches(x)
         x_fuse = []
         for i in range(len(self.fuse_layers)):
@@ -196,6 +197,79 @@ class HighResolutionModule(nn.Module):
             else:
                 x_fuse.append(ops.fuse_sum(terms, ks, relu=True))      # (:433,435)
         return x_fuse
+
+    def flow(self, x):
+        """Data-flow schedule of the module (default on CUDA): resolution i lives on stream i (0 = the caller's stream) ACROSS
+        modules.  The only cross-stream edges are the ones the reference's data flow has -- every fuse row reads every branch
+        output -- expressed as events recorded right after the producing kernel, so nothing waits for more than it needs:
+          * branch i, then the terms it contributes to row 0 (1x1 conv + BN at its own resolution), on stream i;
+          * fuse rows i >= 1 (stride-2 conv chains + sum) on stream i, issued BEFORE the transformer so they do not wait for it;
+          * row-0 sum + the transformer block (the long pole: ~0.6 ms forward, ~1.2 ms backward) on stream 0.
+        The coarse resolutions of the NEXT module start as soon as their own row is done, i.e. they overlap this module's
+        transformer instead of queueing behind it, and autograd replays the same structure in the backward pass.  Inside the
+        captured CUDA graph the streams become parallel sub-graphs.  Returns tensors still living on their streams
+        (flow_join() before handing them to stream-unaware code)."""
+        nb = self.num_branches
+        dev = x[0].device
+        cur = torch.cuda.current_stream(dev)
+        S = [cur] + _side_streams(dev, nb - 1)[:nb - 1]
+        out = [None] * nb
+        for i in range(nb - 1, -1, -1):                    # coarse branches first: their launches are queued before the long one
+            with torch.cuda.stream(S[i]):
+                out[i] = _mark(self.branches[i](_bring(x[i], S[i], cur)), S[i])
+        terms0 = []
+        for j in range(1, nb):
+            with torch.cuda.stream(S[j]):
+                t, k = self._fuse(0, j, out[j])
+                terms0.append((_mark(t, S[j]), k))
+        rows = len(self.fuse_layers)
+        x_fuse = [None] * rows
+        for i in range(rows - 1, 0, -1):
+            with torch.cuda.stream(S[i]):
+                terms, ks = [], []
+                for j in range(nb):
+                    t, k = (out[j], 0) if i == j else self._fuse(i, j, _bring(out[j], S[i], cur))
+                    terms.append(t); ks.append(k)
+                x_fuse[i] = _mark(ops.fuse_sum(terms, ks, relu=True), S[i])      # (:433,435)
+        low = ops.fuse_sum([_bring(t, cur, cur) for t, _ in terms0], [k for _, k in terms0], relu=False)
+        x_fuse[0] = _mark(self.transformer(low, out[0], relu=True), cur)         # (:430-431,435)
+        return x_fuse
+
+
+def _dataflow(t):
+    return BRANCH_STREAMS["on"] and BRANCH_STREAMS["flow"] and t.is_cuda
+
+
+def _mark(t, s):
+    """remember the stream a tensor was produced on and an event right after its producer"""
+    ev = torch.cuda.Event()
+    ev.record(s)
+    t._rss_home, t._rss_ev = s, ev
+    return t
+
+
+def _bring(t, s, origin):
+    """make stream `s` safe to read `t`: wait for t's producer only (not for whatever was queued on its stream afterwards).
+    A tensor without a mark was produced on `origin` (the stream of the stream-unaware caller)."""
+    h = getattr(t, "_rss_home", None)
+    if h is None:
+        if origin != s:
+            s.wait_stream(origin)
+            t.record_stream(s)
+    elif h != s:
+        s.wait_event(t._rss_ev)
+        t.record_stream(s)
+    return t
+
+
+def flow_join(tensors):
+    """hand data-flow tensors to the current stream"""
+    cur = torch.cuda.current_stream(tensors[0].device)
+    for t in tensors:
+        _bring(t, cur, cur)
+        if hasattr(t, "_rss_home"):
+            del t._rss_home, t._rss_ev
+    return tensors
 
 
 class HighResolutionNet(nn.Module):
@@ -268,19 +342,43 @@ class HighResolutionNet(nn.Module):
             return x
         return _run(layer[0], layer[1], x)
 
+    def _stage(self, stage, x_list):
+        if not _dataflow(x_list[0]):
+            return stage(x_list)
+        for m in stage:                                  # tensors stay on their resolution's stream from module to module
+            x_list = m.flow(x_list) if m.num_branches > 1 else m(x_list)
+        return x_list
+
+    def _next_inputs(self, transitions, y_list, n):
+        """inputs of the next stage: existing resolutions pass through (or get their 3x3 conv), the new coarsest one is a
+        stride-2 chain from the last output; in the data-flow schedule each lands on its resolution's stream"""
+        if not _dataflow(y_list[0]):
+            return [y_list[i] if transitions[i] is None else self._transition(transitions[i], y_list[min(i, len(y_list) - 1)])
+                    for i in range(n)]
+        dev = y_list[0].device
+        cur = torch.cuda.current_stream(dev)
+        S = [cur] + _side_streams(dev, n - 1)[:n - 1]
+        x_list = []
+        for i in range(n):
+            if transitions[i] is None:
+                x_list.append(y_list[i])
+                continue
+            src = y_list[min(i, len(y_list) - 1)]
+            with torch.cuda.stream(S[i]):
+                x_list.append(_mark(self._transition(transitions[i], _bring(src, S[i], cur)), S[i]))
+        return x_list
+
     def forward(self, x):
         x = _run(self.conv1, self.bn1, x)
         x = _run(self.conv2, self.bn2, x)
         x = self.layer1(x)
-        x_list = [x if self.transition1[i] is None else self._transition(self.transition1[i], x)
-                  for i in range(self.stage2_cfg["num_branches"])]
-        y_list = self.stage2(x_list)
-        x_list = [y_list[i] if self.transition2[i] is None else self._transition(self.transition2[i], y_list[-1])
-                  for i in range(self.stage3_cfg["num_branches"])]
-        y_list = self.stage3(x_list)
-        x_list = [y_list[i] if self.transition3[i] is None else self._transition(self.transition3[i], y_list[-1])
-                  for i in range(self.stage4_cfg["num_branches"])]
-        return self.stage4(x_list)
+        x_list = self._next_inputs(self.transition1, [x], self.stage2_cfg["num_branches"])
+        y_list = self._stage(self.stage2, x_list)
+        x_list = self._next_inputs(self.transition2, y_list, self.stage3_cfg["num_branches"])
+        y_list = self._stage(self.stage3, x_list)
+        x_list = self._next_inputs(self.transition3, y_list, self.stage4_cfg["num_branches"])
+        y_list = self._stage(self.stage4, x_list)
+        return flow_join(y_list) if _dataflow(y_list[0]) else y_list
 
     def train(self, mode=True):
         super().train(mode)

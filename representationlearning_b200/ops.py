@@ -96,6 +96,7 @@ import os
 # (gpurun 2026-10-17): the barrier costs more than the launch it saves -- 13-32 us per fused kernel vs ~10 + ~5 us for the two
 # split kernels, 382 vs 418 img/s -- so it is OFF by default; the kernels stay in the library (tests run them) for round 2.
 BN_FUSED = {"on": os.environ.get("RSS_BN_FUSED", "0") != "0"}
+BN_KEEP_DZ = {"on": os.environ.get("RSS_BN_KEEP_DZ", "1") != "0"}
 
 
 def _world(group):
@@ -305,8 +306,13 @@ class BNAct(torch.autograd.Function):
                 return (dx, dres) + (None,) * 12
             return (dx, dres, local[C:], local[:C]) + (None,) * 10
         sums = torch.empty(2 * C, device=x.device, dtype=torch.float32)
-        check(lib.rss_bn_bwd_reduce(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(sums),
-                                    rows, C, ctx.act, dt, st), "rss_bn_bwd_reduce")
+        sc = ctx.scratch        # the layer's persistent zeroed scratch (forward statistics kernel): no memset node per launch
+        have_sc = sc is not None and sc.numel() >= 2 + 2 * C
+        # GELU layers: the reduce pass keeps dz = dy*gelu'(z) so the apply pass does not pay for the derivative a second time
+        dz = torch.empty_like(x, memory_format=CL) if (ctx.act == _lib.ACT_GELU and BN_KEEP_DZ["on"]) else None
+        check(lib.rss_bn_bwd_reduce_ws(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(sums),
+                                       _p(sc[2:]) if have_sc else None, _p(sc) if have_sc else None, _p(dz),
+                                       rows, C, ctx.act, dt, st), "rss_bn_bwd_reduce")
         local = sums
         if ctx.training:
             red = sums
@@ -317,9 +323,13 @@ class BNAct(torch.autograd.Function):
         else:                       # eval-mode BN is a fixed affine map: no batch-statistic terms
             red = torch.zeros_like(sums)
             inv_count = 0.0
-        check(lib.rss_bn_bwd_apply(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(red), inv_count,
-                                   _p(dx), _p(dres), rows, C, ctx.act, dt, _p(local), _p(sg) if direct else None,
-                                   _p(sb) if direct else None, st), "rss_bn_bwd_apply")
+        if dz is not None:
+            check(lib.rss_bn_bwd_apply_dz(_p(x), _p(dz), _p(aff[2]), _p(aff[0]), _p(aff[1]), _p(red), inv_count, _p(dx), rows, C, dt,
+                                          _p(local), _p(sg) if direct else None, _p(sb) if direct else None, st), "rss_bn_bwd_apply_dz")
+        else:
+            check(lib.rss_bn_bwd_apply(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(red), inv_count,
+                                       _p(dx), _p(dres), rows, C, ctx.act, dt, _p(local), _p(sg) if direct else None,
+                                       _p(sb) if direct else None, st), "rss_bn_bwd_apply")
         if direct:
             return (dx, dres) + (None,) * 12
         return (dx, dres, local[C:], local[:C]) + (None,) * 10
@@ -515,3 +525,8 @@ def grad_sumsq(flat_grad, grad_scale, out):
 def sgd_step(flat_p, flat_g, flat_m, sumsq, grad_scale, max_norm, lr_dev, momentum, weight_decay, zero_grad, shadow=None):
     check(_lib.load().rss_sgd_step(_p(flat_p), _p(flat_g), _p(flat_m), flat_p.numel(), _p(sumsq), grad_scale, max_norm, _p(lr_dev),
                                    momentum, weight_decay, int(zero_grad), _p(shadow), _st()), "rss_sgd_step")
+
+
+def shadow_cl_refresh(flat_p, shadow_cl, table, row_start, n_entries, max_row_floats):
+    check(_lib.load().rss_shadow_cl_refresh(_p(flat_p), _p(shadow_cl), _p(table), _p(row_start), n_entries, max_row_floats, _st()),
+          "rss_shadow_cl_refresh")

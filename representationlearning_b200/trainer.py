@@ -57,10 +57,43 @@ class FlatSGD:
                 conv.register_shadow(p, self.shadow[o:o + n].view(p.shape))
         if self.shadow is not None:
             self.shadow.copy_(self.flat_p)
+        self._build_cl_shadow(dev)
         self.iteration = 0
         from .modules import FusedBNAct
         self._bn_counters = [m.num_batches_tracked for m in model.modules() if isinstance(m, FusedBNAct)]
         FusedBNAct.defer_counter = True
+
+    def _build_cl_shadow(self, dev):
+        """channels-last bf16 copies of every k x k (k > 1) convolution weight, refreshed by ONE kernel per step
+        (rss_shadow_cl_refresh) instead of one permute kernel in front of each library convolution"""
+        self.shadow_cl = None
+        if self.shadow is None or dev.type != "cuda":
+            return
+        table, rows, total, nrow, max_row = [], [0], 0, 0, 1
+        views = []
+        for p, o in zip(self.params, self.offsets):
+            if p.dim() != 4 or p.shape[2] * p.shape[3] == 1:
+                continue
+            cout, cin, kh, kw = p.shape
+            table.append([o, total, cin, kh * kw])
+            views.append((p, total, (cout, kh, kw, cin)))
+            total += (p.numel() + 7) // 8 * 8                 # 16-byte aligned copies
+            nrow += cout
+            rows.append(nrow)
+            max_row = max(max_row, cin * kh * kw)
+        if not table:
+            return
+        self.shadow_cl = torch.zeros(total, device=dev, dtype=torch.bfloat16)
+        self._cl_table = torch.tensor(table, dtype=torch.int64).to(dev)
+        self._cl_rows = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self._cl_meta = (len(table), max_row)
+        for p, o, shp in views:
+            conv.register_shadow_cl(p, self.shadow_cl[o:o + p.numel()].view(shp).permute(0, 3, 1, 2))
+        self.refresh_cl_shadow()
+
+    def refresh_cl_shadow(self):
+        if self.shadow_cl is not None:
+            ops.shadow_cl_refresh(self.flat_p, self.shadow_cl, self._cl_table, self._cl_rows, *self._cl_meta)
 
     def lr(self):
         return poly_lr(self.iteration, self.hp["base_lr"], self.hp["power"], self.hp["max_iters"])
@@ -92,6 +125,7 @@ class FlatSGD:
         ops.grad_sumsq(self.flat_g, grad_scale, self.sumsq)
         ops.sgd_step(self.flat_p, self.flat_g, self.flat_m, self.sumsq, grad_scale, hp["max_norm"], self.lr_dev, hp["momentum"],
                      hp["weight_decay"], True, self.shadow)
+        self.refresh_cl_shadow()
         if self._bn_counters and self.model.training:
             torch._foreach_add_(self._bn_counters, 1)       # num_batches_tracked of all 330 BN layers in one multi-tensor op
 
