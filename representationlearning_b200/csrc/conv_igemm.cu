@@ -15,6 +15,7 @@
 // (cta_group::1, M=128, kind::f16, bf16 x bf16 -> fp32) accumulates in TMEM, and a 4-warp epilogue drains
 // TMEM with tcgen05.ld (+bias, ->bf16) while the MMA warp already works on the next tile (2 TMEM stages).
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.  Persistent: one CTA per SM.
+#include <stdlib.h>
 #include "tc05.cuh"
 
 namespace rss {
@@ -32,6 +33,9 @@ struct ConvGeom {
     int tiles_x, tiles_y, m_tiles, n_tiles, block_n;
     int kchunks;                 // ceil(Cin / 64)
     int stages;
+    int mm;                      // 128-row M sub-tiles per CTA tile (1 or 2): with 2, one B (weight) stage feeds two A tiles, i.e. the
+                                 // weight traffic L2 -> shared memory per output pixel halves (the 17-tap FFN GEMM streams its
+                                 // 557 KB of weights once per tile: ncu had the 1-sub-tile version pinned on the L2 -> SM fabric)
 };
 
 // K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B; 8-row groups of 1024 B): cute::UMMA::SmemDescriptor
@@ -55,14 +59,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, ConvGeom g, ConvTaps taps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t b_tile_bytes = (uint32_t)g.block_n * kBlockK * 2;
-    const uint32_t stage_bytes = kATileBytes + b_tile_bytes;               // multiple of 1024 (block_n % 16 == 0 -> N*128 B % 2048)
+    const uint32_t a_bytes = (uint32_t)g.mm * kATileBytes;                 // mm sub-tiles of 128 rows, one TMA box (BH*mm image rows)
+    const uint32_t stage_bytes = a_bytes + b_tile_bytes;                   // multiple of 1024 (block_n % 16 == 0 -> N*128 B % 2048)
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
     // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty ; then the TMEM base address
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * g.stages + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tmem_cols = (2 * g.block_n <= 32) ? 32 : (2 * g.block_n <= 64) ? 64 : (2 * g.block_n <= 128) ? 128
-                               : (2 * g.block_n <= 256) ? 256 : 512;
+    const int acc_cols = g.mm * g.block_n;                                 // TMEM columns of one accumulator stage
+    const uint32_t tmem_cols = (2 * acc_cols <= 32) ? 32 : (2 * acc_cols <= 64) ? 64 : (2 * acc_cols <= 128) ? 128
+                               : (2 * acc_cols <= 256) ? 256 : 512;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + g.stages + s), 1); }
@@ -87,7 +93,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
                 const int tx = mt % g.tiles_x, ty = (mt / g.tiles_x) % g.tiles_y, b = mt / (g.tiles_x * g.tiles_y);
-                const int x0 = tx * g.BW, y0 = ty * g.BH, n0 = nt * g.block_n;
+                const int x0 = tx * g.BW, y0 = ty * g.BH * g.mm, n0 = nt * g.block_n;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     const int tap = kb / g.kchunks, kc = kb % g.kchunks;
                     mbar_wait(smem_u32(bars + g.stages + stage), phase ^ 1);           // slot free?
@@ -95,7 +101,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     const uint32_t a_dst = smem_u32(smem + (size_t)stage * stage_bytes);
                     mbar_expect_tx(full, stage_bytes);
                     tma_load_4d(a_dst, &tmap_a, full, kc * kBlockK, x0 + taps.dx[tap], y0 + taps.dy[tap], b);
-                    tma_load_2d(a_dst + kATileBytes, &tmap_b, full, kc * kBlockK, tap * g.Cout + n0);
+                    tma_load_2d(a_dst + a_bytes, &tmap_b, full, kc * kBlockK, tap * g.Cout + n0);
                     if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -113,7 +119,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(smem_u32(bars + 2 * g.stages + 2 + acc), acc_phase ^ 1);       // epilogue drained this TMEM stage?
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_u + acc * g.block_n;
+                const uint32_t d_tmem = tmem_u + acc * acc_cols;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     const int kc = kb % g.kchunks;
                     int ksteps = (g.Cin - kc * kBlockK + kUmmaK - 1) / kUmmaK;            // skip zero-filled tail channels
@@ -121,12 +127,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     mbar_wait(smem_u32(bars + stage), phase);                             // TMA landed?
                     tc_fence_after();
                     const uint32_t a_lo = smem_u32(smem + (size_t)stage * stage_bytes) >> 4;
-                    const uint32_t b_lo = a_lo + (kATileBytes >> 4);
+                    const uint32_t b_lo = a_lo + (a_bytes >> 4);
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k)     // +32 B (2 units of 16 B) per K=16 step inside the 128 B swizzle atom
-                        if (k < ksteps)
+                        if (k < ksteps) {
                             umma_bf16_elect(leader, d_tmem, desc_hi | (uint64_t)(a_lo + k * 2), desc_hi | (uint64_t)(b_lo + k * 2), idesc,
                                             (kb | k) != 0);
+                            if (g.mm == 2)                         // second 128-row sub-tile: same weights, next 16 KB of A, next N columns
+                                umma_bf16_elect(leader, d_tmem + g.block_n, desc_hi | (uint64_t)(a_lo + (kATileBytes >> 4) + k * 2),
+                                                desc_hi | (uint64_t)(b_lo + k * 2), idesc, (kb | k) != 0);
+                        }
                     umma_commit_elect(leader, smem_u32(bars + g.stages + stage));        // frees the smem slot when MMAs finish
                     if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
                 }
@@ -142,22 +152,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
             const int tx = mt % g.tiles_x, ty = (mt / g.tiles_x) % g.tiles_y, b = mt / (g.tiles_x * g.tiles_y);
-            const int x = tx * g.BW + row % g.BW, y = ty * g.BH + row / g.BW, n0 = nt * g.block_n;
-            const bool live = x < g.W && y < g.H;
-            __nv_bfloat16* dst = out + (((size_t)b * g.H + y) * g.W + x) * g.Cout + n0;
+            const int n0 = nt * g.block_n;
             mbar_wait(smem_u32(bars + 2 * g.stages + acc), acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * g.block_n;
-            for (int c0 = 0; c0 < g.block_n; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(t_row + c0, r);
-                tmem_ld_wait();
-                if (live) {
-                    float v[16];
+            for (int m = 0; m < g.mm; ++m) {
+                const int x = tx * g.BW + row % g.BW, y = (ty * g.mm + m) * g.BH + row / g.BW;
+                const bool live = x < g.W && y < g.H;
+                __nv_bfloat16* dst = out + (((size_t)b * g.H + y) * g.W + x) * g.Cout + n0;
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols + m * g.block_n;
+                for (int c0 = 0; c0 < g.block_n; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(t_row + c0, r);
+                    tmem_ld_wait();
+                    if (live) {
+                        float v[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (bias ? bias[n0 + c0 + i] : 0.f);
-                    store8(dst + c0, v);
-                    store8(dst + c0 + 8, v + 8);
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (bias ? bias[n0 + c0 + i] : 0.f);
+                        store8(dst + c0, v);
+                        store8(dst + c0 + 8, v + 8);
+                    }
                 }
             }
             tc_fence_before();
@@ -265,7 +278,7 @@ static int make_maps(const void* x, const void* wp, const ConvGeom& g, int n_tap
     {
         cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
         cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.W * g.Cin * 2, (cuuint64_t)g.H * g.W * g.Cin * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)g.BW, (cuuint32_t)g.BH, 1};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)g.BW, (cuuint32_t)(g.BH * g.mm), 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = cuTensorMapEncodeTiled(ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -328,13 +341,20 @@ extern "C" int rss_conv_igemm(const void* x, const void* w_packed, const float* 
     ConvGeom g;
     g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
     g.BW = W >= 128 ? 128 : W; g.BH = kBlockM / g.BW;
-    g.tiles_x = (W + g.BW - 1) / g.BW; g.tiles_y = (H + g.BH - 1) / g.BH;
-    g.m_tiles = B * g.tiles_x * g.tiles_y;
     g.n_tiles = (Cout + 255) / 256;
     if (Cout % g.n_tiles || (Cout / g.n_tiles) % 16) return RSS_ERR_SHAPE;
     g.block_n = Cout / g.n_tiles;
+    // two M sub-tiles per CTA tile when both accumulator stages still fit in TMEM (2 * 2 * N <= 512 columns), the image rows pair
+    // up, and the launch still has at least 64 tiles; RSS_IGEMM_MM=1 keeps the single sub-tile version (A/B measurements)
+    static const int mm_env = getenv("RSS_IGEMM_MM") ? atoi(getenv("RSS_IGEMM_MM")) : 2;
+    g.mm = 1;
+    if (mm_env >= 2 && g.block_n <= 128 && g.BH * 2 <= 256 && H % (2 * g.BH) == 0 &&
+        (int64_t)B * ((W + g.BW - 1) / g.BW) * (H / (2 * g.BH)) * g.n_tiles >= 64)
+        g.mm = 2;
+    g.tiles_x = (W + g.BW - 1) / g.BW; g.tiles_y = (H + g.BH * g.mm - 1) / (g.BH * g.mm);
+    g.m_tiles = B * g.tiles_x * g.tiles_y;
     g.kchunks = (Cin + kBlockK - 1) / kBlockK;
-    const size_t stage_bytes = kATileBytes + (size_t)g.block_n * kBlockK * 2;
+    const size_t stage_bytes = (size_t)g.mm * kATileBytes + (size_t)g.block_n * kBlockK * 2;
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return RSS_ERR_SHAPE;

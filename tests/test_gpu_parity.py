@@ -439,6 +439,7 @@ IGEMM_CASES = [
     (3, 8, 8, 256, 256, [(3, 1)]),
     (1, 128, 128, 32, 32, [(3, 1)]),
     (2, 64, 64, 64, 64, [(3, 1)]),
+    (4, 64, 64, 128, 128, [(3, 1)]),       # two M sub-tiles per CTA tile with 2-row sub-tiles (BW = 64)
 ]
 
 
