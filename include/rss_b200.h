@@ -113,11 +113,29 @@ int rss_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float*
                       cudaStream_t stream);
 /* same, without the memset node in front of the kernel: accum_scratch (float[2C]) + ticket (one counter) are a persistent
  * per-layer scratch, zero on entry and left zero (the last block to arrive publishes the totals into `sums`); both may be
- * NULL (then `sums` is cleared by a memset node first). */
+ * NULL (then `sums` is cleared by a memset node first); accum_scratch without ticket = "raw" protocol (totals stay in the scratch,
+ * `sums` is not written, see rss_bn_bwd_apply_raw). */
 int rss_bn_bwd_reduce_ws(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
                          const float* mean, const float* invstd, float* sums, float* accum_scratch, unsigned int* ticket,
                          void* dz_out /*may be NULL: [rows][C] activation dtype, receives dz for rss_bn_bwd_apply_dz*/,
                          int64_t rows, int C, int act, int dtype, cudaStream_t stream);
+/* "Raw" protocol of the single-rank training path: rss_bn_stats_raw only adds per-block sums of (x-K), (x-K)^2 (K = running
+ * mean - pre_bias) into the layer's persistent zeroed scratch; rss_bn_act_fwd_raw derives scale/shift from those totals in its
+ * prologue, and its last block writes mean/invstd/scale/shift, updates the running statistics and clears the scratch + ticket.
+ * Same results as rss_bn_stats_fused + rss_bn_act_fwd with three dependent global round trips less per layer.
+ * Backward: rss_bn_bwd_reduce_ws(accum_scratch, ticket = NULL) + rss_bn_bwd_apply_raw (reads the totals from the scratch; its last
+ * block publishes sums_out (optional), accumulates dgamma/dbeta and clears the scratch). */
+int rss_bn_stats_raw(const void* x, float* accum_scratch, int64_t rows, int C, int dtype,
+                     const float* running_mean /*may be NULL*/, const float* pre_bias /*may be NULL*/, cudaStream_t stream);
+int rss_bn_act_fwd_raw(const void* x, const void* residual /*may be NULL*/, void* y, float* accum_scratch, unsigned int* ticket,
+                       int64_t rows, int C, int act, int dtype, const float* gamma, const float* beta,
+                       float* running_mean /*may be NULL*/, float* running_var, float momentum, float eps,
+                       float* mean_out, float* invstd_out, float* scale, float* shift, const float* pre_bias /*may be NULL*/,
+                       cudaStream_t stream);
+int rss_bn_bwd_apply_raw(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, float* accum_scratch, unsigned int* ticket,
+                         float inv_count, void* dx, void* dresidual /*may be NULL*/, int64_t rows, int C, int act, int dtype,
+                         float* sums_out /*may be NULL*/, float* dgamma_acc /*may be NULL*/, float* dbeta_acc, cudaStream_t stream);
 /* second pass from the stored dz (used for the GELU layers, whose derivative is too expensive to recompute in both passes) */
 int rss_bn_bwd_apply_dz(const void* x, const void* dz, const float* scale, const float* mean, const float* invstd,
                         const float* sums, float inv_count, void* dx, int64_t rows, int C, int dtype,

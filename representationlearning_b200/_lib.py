@@ -52,6 +52,9 @@ SIGNATURES = {
     "rss_bn_act_fwd": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
     "rss_bn_bwd_reduce": (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
     "rss_bn_bwd_reduce_ws": (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P]),
+    "rss_bn_stats_raw": (c_int, [P, P, c_int64, c_int, c_int, P, P, P]),
+    "rss_bn_act_fwd_raw": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P, c_float, c_float, P, P, P, P, P, P]),
+    "rss_bn_bwd_apply_raw": (c_int, [P, P, P, P, P, P, P, P, P, c_float, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
     "rss_bn_bwd_apply_dz": (c_int, [P, P, P, P, P, P, c_float, P, c_int64, c_int, c_int, P, P, P, P]),
     "rss_bn_bwd_apply": (c_int, [P, P, P, P, P, P, P, P, c_float, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
     "rss_bn_fused_supported": (c_int, [c_int64, c_int, c_int, c_int]),

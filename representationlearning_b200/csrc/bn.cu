@@ -184,6 +184,7 @@ __global__ void bn_stats_fused_kernel(const T* __restrict__ x, float* __restrict
         for (int rr = 0; rr < rpb; ++rr) t += sm[((size_t)rr * 2 + which) * C + ch];
         atomicAdd(accum + which * C + ch, t);
     }
+    if (!ticket) return;                // "raw" protocol: the consumer (bn_act_fwd_kernel, BnFin) finalises and clears the totals
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
@@ -254,14 +255,44 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
 }
 
 // ---------------------------------------------------------------------------------------------
+// "Raw" protocol of the single-rank training path (accum != NULL): the statistics kernel only adds its per-block sums into the
+// layer's persistent scratch and exits -- no fence, no ticket, no finalize block, i.e. three dependent global round trips less on
+// every one of the 330 layers -- and THIS kernel turns the raw totals into scale/shift in its prologue (a handful of flops per
+// thread).  The bookkeeping that must happen exactly once (saved mean/invstd/scale/shift for the backward pass, running
+// statistics, clearing the scratch) is done by whichever block finishes LAST (ticket taken after the block's work, nobody waits).
+struct BnFin {
+    float* accum;                       // [2C] sum (x-K), sum (x-K)^2 ; NULL = legacy mode (scale/shift come in precomputed)
+    unsigned int* ticket;
+    const float* gamma; const float* beta;
+    float* running_mean; float* running_var;      // may be NULL
+    float momentum, eps;
+    float* mean_out; float* invstd_out; float* scale_out; float* shift_out;
+    const float* pre_bias;              // may be NULL
+    float n;                            // rows
+};
+
 template <typename T, int ACT, bool RES>   // ACT: 0 none, 1 relu, 2 gelu
 __global__ void bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
                                   const float* __restrict__ scale, const float* __restrict__ shift,
-                                  int64_t rows, int C, int cg, int rpb) {
+                                  int64_t rows, int C, int cg, int rpb, const BnFin fin) {
     const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
     float sc[8], sh[8];
+    if (fin.accum) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { sc[i] = scale[sub * 8 + i]; sh[i] = shift[sub * 8 + i]; }
+        for (int i = 0; i < 8; ++i) {
+            const int c = sub * 8 + i;
+            const float K = fin.running_mean ? fin.running_mean[c] - (fin.pre_bias ? fin.pre_bias[c] : 0.f) : 0.f;
+            const float S = __ldcg(fin.accum + c), Q = __ldcg(fin.accum + C + c);
+            const float md = S / fin.n;
+            const float m2 = fmaxf(Q - S * md, 0.f);
+            const float invstd = rsqrtf(m2 / fin.n + fin.eps);
+            sc[i] = fin.gamma[c] * invstd;
+            sh[i] = fin.beta[c] - (K + md) * sc[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sc[i] = scale[sub * 8 + i]; sh[i] = shift[sub * 8 + i]; }
+    }
     const int64_t stride = (int64_t)gridDim.x * rpb;
     int64_t row = (int64_t)blockIdx.x * rpb + r;
     constexpr int U = 4;
@@ -301,6 +332,24 @@ __global__ void bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__
         if (RES) ldraw(res + off, rr);
         one(rx, rr, off);
     }
+    if (!fin.accum) return;
+    __shared__ bool is_last;
+    __syncthreads();                     // every thread of the block has consumed its totals
+    if (threadIdx.x == 0) { __threadfence(); is_last = (atomicAdd(fin.ticket, 1u) == gridDim.x - 1); }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();                     // all other blocks are past their reads of accum / running_mean
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float S = __ldcg(fin.accum + c), Q = __ldcg(fin.accum + C + c);
+        const float md = S / fin.n;
+        const float m2 = fmaxf(Q - S * md, 0.f);
+        const float k = fin.running_mean ? fin.running_mean[c] - (fin.pre_bias ? fin.pre_bias[c] : 0.f) : 0.f;
+        bn_finalize_channel(fin.n, k + md, m2, c, fin.gamma, fin.beta, fin.running_mean, fin.running_var, fin.momentum, fin.eps,
+                            fin.mean_out, fin.invstd_out, fin.scale_out, fin.shift_out, fin.pre_bias);
+        fin.accum[c] = 0.f;
+        fin.accum[C + c] = 0.f;
+    }
+    if (threadIdx.x == 0) *fin.ticket = 0u;
 }
 
 // dz = dy * act'(z).  relu: mask from the saved output y (>0) when HAS_Y (residual layers), else recomputed from x; gelu: z
@@ -393,7 +442,7 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
         for (int rr = 0; rr < rpb; ++rr) s += sm[((size_t)rr * 2 + which) * C + ch];
         atomicAdd((accum ? accum : sums) + which * C + ch, s);
     }
-    if (!accum) return;
+    if (!accum || !ticket) return;       // (accum without ticket: "raw" protocol, bn_bwd_apply_kernel publishes and clears the totals)
     // no memset node in front of the kernel (one launch + one dependency edge less per layer on a latency-bound chain): the
     // totals are built in a persistent scratch that every launch leaves zeroed; the last block to arrive publishes them
     __threadfence();
@@ -415,16 +464,22 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ sums, float inv_count,
                                     T* __restrict__ dx, T* __restrict__ dres, int64_t rows, int C, int cg, int rpb,
-                                    const float* __restrict__ local_sums, float* __restrict__ dgamma_acc, float* __restrict__ dbeta_acc) {
+                                    const float* __restrict__ local_sums, float* __restrict__ dgamma_acc, float* __restrict__ dbeta_acc,
+                                    float* __restrict__ raw_accum /*NULL, or the scratch bn_bwd_reduce_kernel added into ("raw" protocol)*/,
+                                    unsigned int* __restrict__ raw_ticket, float* __restrict__ sums_out /*NULL or [2C]*/) {
     const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
-    if (dgamma_acc && blockIdx.x == 0) {      // parameter gradients straight into the caller's (flat) grad buffer
+    if (!raw_accum && dgamma_acc && blockIdx.x == 0) {      // parameter gradients straight into the caller's (flat) grad buffer
         for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta_acc[c] += local_sums[c]; dgamma_acc[c] += local_sums[C + c]; }
     }
     float sc[8], sh[8], mu[8], is[8], m0[8], m1[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         sc[i] = scale[sub * 8 + i]; sh[i] = shift[sub * 8 + i]; mu[i] = mean[sub * 8 + i]; is[i] = invstd[sub * 8 + i];
-        m0[i] = sums[sub * 8 + i] * inv_count; m1[i] = sums[C + sub * 8 + i] * inv_count;
+        if (raw_accum) {
+            m0[i] = __ldcg(raw_accum + sub * 8 + i) * inv_count; m1[i] = __ldcg(raw_accum + C + sub * 8 + i) * inv_count;
+        } else {
+            m0[i] = sums[sub * 8 + i] * inv_count; m1[i] = sums[C + sub * 8 + i] * inv_count;
+        }
     }
     const int64_t stride = (int64_t)gridDim.x * rpb;
     int64_t row = (int64_t)blockIdx.x * rpb + r;
@@ -457,6 +512,21 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
         if (HAS_Y) ldraw(y + off, ry);
         one(rx, ry, rd, off);
     }
+    if (!raw_accum) return;
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); is_last = (atomicAdd(raw_ticket, 1u) == gridDim.x - 1); }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {      // once per launch: publish, accumulate dgamma/dbeta, clear the scratch
+        const float S0 = __ldcg(raw_accum + c), S1 = __ldcg(raw_accum + C + c);
+        if (sums_out) { sums_out[c] = S0; sums_out[C + c] = S1; }
+        if (dgamma_acc) { dbeta_acc[c] += S0; dgamma_acc[c] += S1; }
+        raw_accum[c] = 0.f;
+        raw_accum[C + c] = 0.f;
+    }
+    if (threadIdx.x == 0) *raw_ticket = 0u;
 }
 
 // apply pass when the reduce pass kept dz = dy*act'(z) (GELU layers: the derivative costs ~30 instructions and two MUFU ops per
@@ -829,7 +899,36 @@ extern "C" int rss_bn_act_fwd(const void* x, const void* residual, void* y, cons
     if (residual && act == RSS_ACT_GELU) return RSS_ERR_SHAPE;   // not a pattern of the reference (backward would need the residual)
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 4, 8);
-    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_act_fwd_kernel, residual != nullptr, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, rows, C, g.cg, g.rpb)));
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_act_fwd_kernel, residual != nullptr, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, rows, C, g.cg, g.rpb, BnFin{})));
+    return check_launch();
+}
+
+// ---- "raw" protocol (single-rank training path): statistics kernel = sums only; the apply kernel finalises (see BnFin) ----
+extern "C" int rss_bn_stats_raw(const void* x, float* accum_scratch, int64_t rows, int C, int dtype,
+                                const float* running_mean, const float* pre_bias, cudaStream_t st) {
+    if (C <= 0 || C % 8 || C > 2048 || rows <= 0 || !accum_scratch) return RSS_ERR_SHAPE;
+    const BnGeom g = bn_geom(C);
+    const int grid = bn_grid(rows, g.rpb * 8, 4);
+    const size_t smem = (size_t)g.rpb * C * 2 * sizeof(float);
+    RSS_DISPATCH_DTYPE(dtype, bn_stats_fused_kernel<T><<<grid, g.threads, smem, st>>>((const T*)x, accum_scratch, nullptr, rows, C, g.cg, g.rpb,
+                       nullptr, nullptr, const_cast<float*>(running_mean), nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, pre_bias));
+    return check_launch();
+}
+
+extern "C" int rss_bn_act_fwd_raw(const void* x, const void* residual, void* y, float* accum_scratch, unsigned int* ticket,
+                                  int64_t rows, int C, int act, int dtype, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, float momentum, float eps,
+                                  float* mean_out, float* invstd_out, float* scale, float* shift, const float* pre_bias,
+                                  cudaStream_t st) {
+    if (C <= 0 || C % 8 || rows <= 0 || !accum_scratch || !ticket) return RSS_ERR_SHAPE;
+    if (residual && act == RSS_ACT_GELU) return RSS_ERR_SHAPE;
+    const BnGeom g = bn_geom(C);
+    const int grid = bn_grid(rows, g.rpb * 4, 8);
+    BnFin fin;
+    fin.accum = accum_scratch; fin.ticket = ticket; fin.gamma = gamma; fin.beta = beta; fin.running_mean = running_mean;
+    fin.running_var = running_var; fin.momentum = momentum; fin.eps = eps; fin.mean_out = mean_out; fin.invstd_out = invstd_out;
+    fin.scale_out = scale; fin.shift_out = shift; fin.pre_bias = pre_bias; fin.n = (float)rows;
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_act_fwd_kernel, residual != nullptr, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, nullptr, nullptr, rows, C, g.cg, g.rpb, fin)));
     return check_launch();
 }
 
@@ -838,7 +937,7 @@ extern "C" int rss_bn_act_fwd(const void* x, const void* residual, void* y, cons
 extern "C" int rss_bn_bwd_reduce_ws(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
                                     const float* mean, const float* invstd, float* sums, float* accum_scratch, unsigned int* ticket,
                                     void* dz_out, int64_t rows, int C, int act, int dtype, cudaStream_t st) {
-    if (C <= 0 || C % 8 || rows <= 0 || (accum_scratch == nullptr) != (ticket == nullptr)) return RSS_ERR_SHAPE;
+    if (C <= 0 || C % 8 || rows <= 0 || (ticket && !accum_scratch)) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 8, 4);
     const size_t smem = (size_t)g.rpb * 2 * C * sizeof(float);
@@ -865,7 +964,22 @@ extern "C" int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, co
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 4, 8);
     RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
-                                                                                                           local_sums, dgamma_acc, dbeta_acc)));
+                                                                                                           local_sums, dgamma_acc, dbeta_acc, nullptr, nullptr, nullptr)));
+    return check_launch();
+}
+
+// "raw" protocol backward: rss_bn_bwd_reduce_ws(accum_scratch, ticket = NULL) only adds the per-block sums into the scratch;
+// this apply pass reads them there, and its last block publishes sums_out (optional), accumulates dgamma/dbeta and clears the scratch
+extern "C" int rss_bn_bwd_apply_raw(const void* x, const void* y, const void* dy, const float* scale, const float* shift,
+                                    const float* mean, const float* invstd, float* accum_scratch, unsigned int* ticket,
+                                    float inv_count, void* dx, void* dres, int64_t rows, int C, int act, int dtype,
+                                    float* sums_out, float* dgamma_acc, float* dbeta_acc, cudaStream_t st) {
+    if (C <= 0 || C % 8 || rows <= 0 || !accum_scratch || !ticket) return RSS_ERR_SHAPE;
+    if (act == RSS_ACT_RELU && dres && !y) return RSS_ERR_SHAPE;
+    const BnGeom g = bn_geom(C);
+    const int grid = bn_grid(rows, g.rpb * 4, 8);
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, nullptr, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
+                                                                                                           nullptr, dgamma_acc, dbeta_acc, accum_scratch, ticket, sums_out)));
     return check_launch();
 }
 

@@ -43,8 +43,12 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
     __shared__ float T[kTile][kFoot][kNC];          // after the x pass: [output row][low-res column][class]
     __shared__ float red[3][kTile * kTile / 32];
     __shared__ int flags[2];
-    __shared__ int cx0[kTile], cx1[kTile], cy0[kTile], cy1[kTile];     // footprint-relative source indices per output column / row
-    __shared__ float clx[kTile], cly[kTile];
+    // per output column / row: footprint-relative low source index (kBig outside the image), weight of the low and of the high
+    // source cell (the high weight is folded into the low one where align_corners clamps both onto the last cell)
+    __shared__ int cx0[kTile], cy0[kTile];
+    __shared__ float wx0[kTile], wx1[kTile], wy0[kTile], wy1[kTile];
+    __shared__ int fx[kFoot + 2], fy[kFoot + 2];     // fx[r] = number of columns with cx0 < r: columns [fx[r], fx[r+1]) have cx0 == r
+    constexpr int kBig = 1 << 20;
     const int tiles_x = (W + kTile - 1) / kTile;
     const int ty0 = (blockIdx.x / tiles_x) * kTile, tx0 = (blockIdx.x % tiles_x) * kTile;
     const int b = blockIdx.y;
@@ -63,8 +67,8 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
         int y0, y1, x0, x1; float ly, lx;
         bilinear_src_l(oy < H ? oy : H - 1, sy, h, y0, y1, ly);
         bilinear_src_l(ox < W ? ox : W - 1, sx, w, x0, x1, lx);
-        if (r == 0) { cx0[c] = ox < W ? x0 - fx0 : -1; cx1[c] = ox < W ? x1 - fx0 : -1; clx[c] = lx; }
-        if (c == 0) { cy0[r] = oy < H ? y0 - fy0 : -1; cy1[r] = oy < H ? y1 - fy0 : -1; cly[r] = ly; }
+        if (r == 0) { cx0[c] = ox < W ? x0 - fx0 : kBig; wx0[c] = x1 == x0 ? 1.f : 1.f - lx; wx1[c] = x1 == x0 ? 0.f : lx; }
+        if (c == 0) { cy0[r] = oy < H ? y0 - fy0 : kBig; wy0[r] = y1 == y0 ? 1.f : 1.f - ly; wy1[r] = y1 == y0 ? 0.f : ly; }
         if (oy < H && ox < W) {
             const float* base = logits + (int64_t)b * h * w * kNCP;
             const float4* p00 = reinterpret_cast<const float4*>(base + ((int64_t)y0 * w + x0) * kNCP);
@@ -86,20 +90,20 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
             float e[kNC], s = 0.f;
 #pragma unroll
             for (int k = 0; k < kNC; ++k) { e[k] = expf(z[k] - mx); s += e[k]; }
-            const float lse = mx + logf(s);
+            const float lse = mx + logf(s), inv_s = 1.f / s;
             const int64_t lbl = labels[((int64_t)b * H + oy) * W + ox];
             const bool valid = lbl != (int64_t)ignore_index;
             const int t = valid ? (int)lbl : 0;
-            float zt = 0.f;
+            float zt = 0.f, et = 0.f;
 #pragma unroll
-            for (int k = 0; k < kNC; ++k) zt = (k == t) ? z[k] : zt;
-            A = 1.f - expf(zt - lse);
+            for (int k = 0; k < kNC; ++k) { zt = (k == t) ? z[k] : zt; et = (k == t) ? e[k] : et; }
+            A = 1.f - et * inv_s;
             if (lbl > 0) flags[0] = 1; else flags[1] = 1;          // benign race: all writers store 1
             if (valid) {
                 ce = lse - zt;
                 nv = 1.f;
 #pragma unroll
-                for (int k = 0; k < kNC; ++k) gk[k] = expf(z[k] - lse) - (k == t ? 1.f : 0.f);
+                for (int k = 0; k < kNC; ++k) gk[k] = e[k] * inv_s - (k == t ? 1.f : 0.f);
             }
         }
     }
@@ -109,6 +113,13 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
     ce = warp_sum(ce); nv = warp_sum(nv); A = warp_sum(A);
     if (lane == 0) { red[0][warp] = ce; red[1][warp] = nv; red[2][warp] = A; }
     __syncthreads();
+    if (threadIdx.x < 2 * (kFoot + 2)) {               // range tables (cx0 / cy0 are monotone along the tile)
+        const int which = threadIdx.x / (kFoot + 2), rr = threadIdx.x % (kFoot + 2);
+        const int* src = which ? cy0 : cx0;
+        int n = 0;
+        for (int i = 0; i < kTile; ++i) n += src[i] < rr ? 1 : 0;
+        (which ? fy : fx)[rr] = n;
+    }
     if (threadIdx.x < 3) {
         float s = 0.f;
         for (int i = 0; i < kTile * kTile / 32; ++i) s += red[threadIdx.x][i];
@@ -116,43 +127,25 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
     }
     if (threadIdx.x == 3 && flags[0]) atomicOr(reinterpret_cast<int*>(acc + 2 + B) + b, 1);
     if (threadIdx.x == 4 && flags[1]) atomicOr(reinterpret_cast<int*>(acc + 2 + 2 * B) + b, 1);
-    // ---- x pass: T[row][rx][k] = sum over the output columns whose bilinear footprint contains low-res column fx0 + rx
+    __syncthreads();
+    // ---- x pass: T[row][rx][k] = sum over the output columns whose bilinear footprint contains low-res column fx0 + rx:
+    //      columns with x0 == rx (low weight) and columns with x0 == rx - 1 (high weight)
     for (int i = threadIdx.x; i < kTile * kFoot * kNC; i += blockDim.x) {
         const int k = i % kNC, rx = (i / kNC) % kFoot, row = i / (kNC * kFoot);
-        int lo = 0, hi = kTile - 1;
-        if (sx > 0.f) {                      // columns with scale*ox in (xx - 1, xx + 1), padded by one against rounding
-            const float xx = (float)(fx0 + rx);
-            lo = (int)((xx - 1.f) / sx) - 1 - tx0;
-            hi = (int)((xx + 1.f) / sx) + 1 - tx0;
-            lo = lo < 0 ? 0 : lo;
-            hi = hi > kTile - 1 ? kTile - 1 : hi;
-        }
         float s = 0.f;
-        for (int cc = lo; cc <= hi; ++cc) {
-            const float v = G[row][cc][k], l = clx[cc];
-            if (cx0[cc] == rx) s += (1.f - l) * v;
-            if (cx1[cc] == rx) s += l * v;
-        }
+        for (int cc = fx[rx]; cc < fx[rx + 1]; ++cc) s += wx0[cc] * G[row][cc][k];
+        if (rx > 0)
+            for (int cc = fx[rx - 1]; cc < fx[rx]; ++cc) s += wx1[cc] * G[row][cc][k];
         T[row][rx][k] = s;
     }
     __syncthreads();
     // ---- y pass, straight into the global low-resolution gradient (cells on tile borders are shared with the neighbours)
     for (int i = threadIdx.x; i < kFoot * kFoot * kNC; i += blockDim.x) {
         const int k = i % kNC, rx = (i / kNC) % kFoot, ry = i / (kNC * kFoot);
-        int lo = 0, hi = kTile - 1;
-        if (sy > 0.f) {
-            const float yy = (float)(fy0 + ry);
-            lo = (int)((yy - 1.f) / sy) - 1 - ty0;
-            hi = (int)((yy + 1.f) / sy) + 1 - ty0;
-            lo = lo < 0 ? 0 : lo;
-            hi = hi > kTile - 1 ? kTile - 1 : hi;
-        }
         float vsum = 0.f;
-        for (int rr = lo; rr <= hi; ++rr) {
-            const float v = T[rr][rx][k], l = cly[rr];
-            if (cy0[rr] == ry) vsum += (1.f - l) * v;
-            if (cy1[rr] == ry) vsum += l * v;
-        }
+        for (int rr = fy[ry]; rr < fy[ry + 1]; ++rr) vsum += wy0[rr] * T[rr][rx][k];
+        if (ry > 0)
+            for (int rr = fy[ry - 1]; rr < fy[ry]; ++rr) vsum += wy1[rr] * T[rr][rx][k];
         const int yy = fy0 + ry, xx = fx0 + rx;
         if (vsum != 0.f && yy < h && xx < w) atomicAdd(gdir + (((int64_t)b * h + yy) * w + xx) * kNCP + k, vsum);
     }

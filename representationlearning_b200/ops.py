@@ -97,6 +97,9 @@ import os
 # split kernels, 382 vs 418 img/s -- so it is OFF by default; the kernels stay in the library (tests run them) for round 2.
 BN_FUSED = {"on": os.environ.get("RSS_BN_FUSED", "0") != "0"}
 BN_KEEP_DZ = {"on": os.environ.get("RSS_BN_KEEP_DZ", "1") != "0"}
+# "raw" BatchNorm protocol (csrc/bn.cu BnFin): the statistics / reduce kernels only add their sums into the layer's scratch and
+# the apply kernels finalise -- fewer dependent global round trips per layer
+BN_RAW = {"on": os.environ.get("RSS_BN_RAW", "1") != "0"}
 
 
 def _world(group):
@@ -244,6 +247,7 @@ class BNAct(torch.autograd.Function):
         if fused and (scratch is None or scratch.numel() < 2 + 2 * C):
             scratch = torch.zeros(2 + 2 * C, device=dev, dtype=torch.float32)   # [0:2] barrier counters, [2:] accumulators; left zeroed
         y = torch.empty_like(x, memory_format=CL)
+        raw = False
         if fused and not have_aff:          # statistics + apply in ONE launch (device-wide barrier in between)
             check(lib.rss_bn_fwd_fused(_p(x), _p(residual), _p(y), _p(scratch[2:]), _p(scratch), rows, C, act, dt, _p(g), _p(b),
                                        _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
@@ -254,6 +258,17 @@ class BNAct(torch.autograd.Function):
             elif training and world == 1:
                 if scratch is None or scratch.numel() < 2 + 2 * C:      # [0] last-block ticket, [2:] accumulators; kernel leaves zeros
                     scratch = torch.zeros(2 + 2 * C, device=dev, dtype=torch.float32)
+                raw = BN_RAW["on"]
+                if raw:
+                    check(lib.rss_bn_stats_raw(_p(x), _p(scratch[2:]), rows, C, dt, _p(running_mean), _p(pre_bias), st), "rss_bn_stats_raw")
+                    check(lib.rss_bn_act_fwd_raw(_p(x), _p(residual), _p(y), _p(scratch[2:]), _p(scratch), rows, C, act, dt, _p(g), _p(b),
+                                                 _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
+                                                 _p(aff[3]), _p(pre_bias), st), "rss_bn_act_fwd_raw")
+            if raw:
+                pass
+            elif have_aff:
+                pass
+            elif training and world == 1:
                 check(lib.rss_bn_stats_fused(_p(x), _p(scratch[2:]), _p(scratch), rows, C, dt, _p(g), _p(b),
                                              _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
                                              _p(aff[3]), _p(pre_bias), st), "rss_bn_stats_fused")
@@ -275,7 +290,8 @@ class BNAct(torch.autograd.Function):
             else:
                 check(lib.rss_bn_eval_affine(_p(g), _p(b), _p(running_mean), _p(running_var), eps, C,
                                              _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), st), "rss_bn_eval_affine")
-            check(lib.rss_bn_act_fwd(_p(x), _p(residual), _p(y), _p(aff[2]), _p(aff[3]), rows, C, act, dt, st), "rss_bn_act_fwd")
+            if not raw:
+                check(lib.rss_bn_act_fwd(_p(x), _p(residual), _p(y), _p(aff[2]), _p(aff[3]), rows, C, act, dt, st), "rss_bn_act_fwd")
         ctx.fused, ctx.scratch = fused, scratch
         ctx.save_for_backward(x, y if (act == _lib.ACT_RELU and residual is not None) else None, aff)
         ctx.act, ctx.training, ctx.group, ctx.world, ctx.has_res = act, training, group, world, residual is not None
@@ -310,6 +326,16 @@ class BNAct(torch.autograd.Function):
         have_sc = sc is not None and sc.numel() >= 2 + 2 * C
         # GELU layers: the reduce pass keeps dz = dy*gelu'(z) so the apply pass does not pay for the derivative a second time
         dz = torch.empty_like(x, memory_format=CL) if (ctx.act == _lib.ACT_GELU and BN_KEEP_DZ["on"]) else None
+        if BN_RAW["on"] and have_sc and dz is None and ctx.training and ctx.world == 1:
+            # raw protocol: totals stay in the scratch, the apply kernel reads them there and its last block does the bookkeeping
+            check(lib.rss_bn_bwd_reduce_ws(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), None,
+                                           _p(sc[2:]), None, None, rows, C, ctx.act, dt, st), "rss_bn_bwd_reduce")
+            check(lib.rss_bn_bwd_apply_raw(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(sc[2:]), _p(sc),
+                                           1.0 / rows, _p(dx), _p(dres), rows, C, ctx.act, dt, None if direct else _p(sums),
+                                           _p(sg) if direct else None, _p(sb) if direct else None, st), "rss_bn_bwd_apply")
+            if direct:
+                return (dx, dres) + (None,) * 12
+            return (dx, dres, sums[C:], sums[:C]) + (None,) * 10
         check(lib.rss_bn_bwd_reduce_ws(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(sums),
                                        _p(sc[2:]) if have_sc else None, _p(sc) if have_sc else None, _p(dz),
                                        rows, C, ctx.act, dt, st), "rss_bn_bwd_reduce")
