@@ -9,6 +9,7 @@
 //   backward : dz = dy*act'(.), sums (sum dz, sum dz*xhat)                -> rss_bn_bwd_reduce
 //              dx = gamma*invstd*(dz - sum_dz/n - xhat*sum_dzxhat/n)      -> rss_bn_bwd_apply
 // All kernels are HBM-bound: each thread owns 8 consecutive channels (one 16/32-byte vector).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace rss {
@@ -16,6 +17,13 @@ namespace rss {
 struct BnGeom { int cg; int rpb; int threads; };
 static inline BnGeom bn_geom(int C) {
     BnGeom g; g.cg = C / 8; g.rpb = 256 / g.cg; if (g.rpb < 1) g.rpb = 1; g.threads = g.cg * g.rpb; return g;
+}
+// blocks per SM of the kernels that end in a device-wide ticket (statistics, backward reduce): every block pays one same-address
+// atomic round trip at its end, so fewer, fatter blocks shorten the tail (RSS_BN_TICKET_BPSM, default 4)
+static inline int bn_ticket_bpsm() {
+    static int v = 0;
+    if (v == 0) { const char* e = getenv("RSS_BN_TICKET_BPSM"); v = e ? atoi(e) : 4; if (v < 1 || v > 8) v = 4; }
+    return v;
 }
 static inline int bn_grid(int64_t rows, int rpb, int per_sm) {
     int64_t g = (rows + rpb - 1) / rpb;
@@ -282,7 +290,10 @@ __global__ void bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__
         for (int i = 0; i < 8; ++i) {
             const int c = sub * 8 + i;
             const float K = fin.running_mean ? fin.running_mean[c] - (fin.pre_bias ? fin.pre_bias[c] : 0.f) : 0.f;
-            const float S = __ldcg(fin.accum + c), Q = __ldcg(fin.accum + C + c);
+            // plain (L1-cached) loads on purpose: every thread of up to 1184 blocks reads the same 2C floats, and L1-bypassing
+            // __ldcg turned that into a hot spot on ONE L2 slice (measured: 51 us instead of 10 for the whole kernel); the
+            // totals were written by the previous kernel, so L1 cannot hold a stale copy
+            const float S = fin.accum[c], Q = fin.accum[C + c];
             const float md = S / fin.n;
             const float m2 = fmaxf(Q - S * md, 0.f);
             const float invstd = rsqrtf(m2 / fin.n + fin.eps);
@@ -335,7 +346,10 @@ __global__ void bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__
     if (!fin.accum) return;
     __shared__ bool is_last;
     __syncthreads();                     // every thread of the block has consumed its totals
-    if (threadIdx.x == 0) { __threadfence(); is_last = (atomicAdd(fin.ticket, 1u) == gridDim.x - 1); }
+    // (no fence in front of the ticket: the block's reads of the totals completed long ago -- their values fed the main loop --
+    //  and nothing this block wrote is read by the last block; a __threadfence() here, behind the block's burst of stores, made
+    //  the kernel 4-5x slower on the 1184-block grids: measured 51 vs 10 us)
+    if (threadIdx.x == 0) is_last = (atomicAdd(fin.ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!is_last) return;
     __threadfence();                     // all other blocks are past their reads of accum / running_mean
@@ -476,7 +490,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
     for (int i = 0; i < 8; ++i) {
         sc[i] = scale[sub * 8 + i]; sh[i] = shift[sub * 8 + i]; mu[i] = mean[sub * 8 + i]; is[i] = invstd[sub * 8 + i];
         if (raw_accum) {
-            m0[i] = __ldcg(raw_accum + sub * 8 + i) * inv_count; m1[i] = __ldcg(raw_accum + C + sub * 8 + i) * inv_count;
+            m0[i] = raw_accum[sub * 8 + i] * inv_count; m1[i] = raw_accum[C + sub * 8 + i] * inv_count;   // L1-cached on purpose, see BnFin
         } else {
             m0[i] = sums[sub * 8 + i] * inv_count; m1[i] = sums[C + sub * 8 + i] * inv_count;
         }
@@ -515,7 +529,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
     if (!raw_accum) return;
     __shared__ bool is_last;
     __syncthreads();
-    if (threadIdx.x == 0) { __threadfence(); is_last = (atomicAdd(raw_ticket, 1u) == gridDim.x - 1); }
+    if (threadIdx.x == 0) is_last = (atomicAdd(raw_ticket, 1u) == gridDim.x - 1);      // no fence needed, see bn_act_fwd_kernel
     __syncthreads();
     if (!is_last) return;
     __threadfence();
@@ -855,7 +869,7 @@ extern "C" int rss_bn_stats_fused(const void* x, float* accum_scratch, unsigned 
                                   const float* pre_bias, cudaStream_t st) {
     if (C <= 0 || C % 8 || C > 2048 || rows <= 0 || !ticket || !accum_scratch) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 8, 4);
+    const int grid = bn_grid(rows, g.rpb * 8, bn_ticket_bpsm());
     const size_t smem = (size_t)g.rpb * C * 2 * sizeof(float);
     RSS_DISPATCH_DTYPE(dtype, bn_stats_fused_kernel<T><<<grid, g.threads, smem, st>>>((const T*)x, accum_scratch, ticket, rows, C, g.cg, g.rpb,
                        gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out, scale, shift, pre_bias));
@@ -908,7 +922,7 @@ extern "C" int rss_bn_stats_raw(const void* x, float* accum_scratch, int64_t row
                                 const float* running_mean, const float* pre_bias, cudaStream_t st) {
     if (C <= 0 || C % 8 || C > 2048 || rows <= 0 || !accum_scratch) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 8, 4);
+    const int grid = bn_grid(rows, g.rpb * 8, bn_ticket_bpsm());
     const size_t smem = (size_t)g.rpb * C * 2 * sizeof(float);
     RSS_DISPATCH_DTYPE(dtype, bn_stats_fused_kernel<T><<<grid, g.threads, smem, st>>>((const T*)x, accum_scratch, nullptr, rows, C, g.cg, g.rpb,
                        nullptr, nullptr, const_cast<float*>(running_mean), nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, pre_bias));
@@ -939,7 +953,7 @@ extern "C" int rss_bn_bwd_reduce_ws(const void* x, const void* y, const void* dy
                                     void* dz_out, int64_t rows, int C, int act, int dtype, cudaStream_t st) {
     if (C <= 0 || C % 8 || rows <= 0 || (ticket && !accum_scratch)) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 8, 4);
+    const int grid = bn_grid(rows, g.rpb * 8, bn_ticket_bpsm());
     const size_t smem = (size_t)g.rpb * 2 * C * sizeof(float);
     if (!accum_scratch) {
         cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st);

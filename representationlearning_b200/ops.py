@@ -99,7 +99,9 @@ BN_FUSED = {"on": os.environ.get("RSS_BN_FUSED", "0") != "0"}
 BN_KEEP_DZ = {"on": os.environ.get("RSS_BN_KEEP_DZ", "1") != "0"}
 # "raw" BatchNorm protocol (csrc/bn.cu BnFin): the statistics / reduce kernels only add their sums into the layer's scratch and
 # the apply kernels finalise -- fewer dependent global round trips per layer
-BN_RAW = {"on": os.environ.get("RSS_BN_RAW", "1") != "0"}
+# Measured on the B=16 step (gpurun 2026-10-17, timeline_s3f): statistics -3.3 us and reduce -2.1 us per layer, but the "last block
+# finished" ticket costs more on the 1184-block apply grids (+6.9 / +3.2 us), 453 vs 458 img/s -> OFF by default.
+BN_RAW = {"on": os.environ.get("RSS_BN_RAW", "0") != "0"}
 
 
 def _world(group):
