@@ -19,10 +19,17 @@ static inline BnGeom bn_geom(int C) {
     BnGeom g; g.cg = C / 8; g.rpb = 256 / g.cg; if (g.rpb < 1) g.rpb = 1; g.threads = g.cg * g.rpb; return g;
 }
 // blocks per SM of the kernels that end in a device-wide ticket (statistics, backward reduce): every block pays one same-address
-// atomic round trip at its end, so fewer, fatter blocks shorten the tail (RSS_BN_TICKET_BPSM, default 4)
+// atomic round trip at its end, so fewer, fatter blocks shorten the tail (RSS_BN_TICKET_BPSM; measured on the B=16 step:
+// 1 -> 457, 2 -> 465, 4 -> 459, 8 -> 456 img/s; default 2)
 static inline int bn_ticket_bpsm() {
     static int v = 0;
-    if (v == 0) { const char* e = getenv("RSS_BN_TICKET_BPSM"); v = e ? atoi(e) : 4; if (v < 1 || v > 8) v = 4; }
+    if (v == 0) { const char* e = getenv("RSS_BN_TICKET_BPSM"); v = e ? atoi(e) : 2; if (v < 1 || v > 8) v = 2; }
+    return v;
+}
+// blocks per SM of the streaming apply kernels (RSS_BN_APPLY_BPSM, default 8)
+static inline int bn_apply_bpsm() {
+    static int v = 0;
+    if (v == 0) { const char* e = getenv("RSS_BN_APPLY_BPSM"); v = e ? atoi(e) : 8; if (v < 1 || v > 16) v = 8; }
     return v;
 }
 static inline int bn_grid(int64_t rows, int rpb, int per_sm) {
@@ -912,7 +919,7 @@ extern "C" int rss_bn_act_fwd(const void* x, const void* residual, void* y, cons
     if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
     if (residual && act == RSS_ACT_GELU) return RSS_ERR_SHAPE;   // not a pattern of the reference (backward would need the residual)
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 4, 8);
+    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
     RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_act_fwd_kernel, residual != nullptr, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, rows, C, g.cg, g.rpb, BnFin{})));
     return check_launch();
 }
@@ -937,7 +944,7 @@ extern "C" int rss_bn_act_fwd_raw(const void* x, const void* residual, void* y, 
     if (C <= 0 || C % 8 || rows <= 0 || !accum_scratch || !ticket) return RSS_ERR_SHAPE;
     if (residual && act == RSS_ACT_GELU) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 4, 8);
+    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
     BnFin fin;
     fin.accum = accum_scratch; fin.ticket = ticket; fin.gamma = gamma; fin.beta = beta; fin.running_mean = running_mean;
     fin.running_var = running_var; fin.momentum = momentum; fin.eps = eps; fin.mean_out = mean_out; fin.invstd_out = invstd_out;
@@ -976,7 +983,7 @@ extern "C" int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, co
     if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
     if (act == RSS_ACT_RELU && dres && !y) return RSS_ERR_SHAPE;     // residual layers must pass the saved output
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 4, 8);
+    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
     RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
                                                                                                            local_sums, dgamma_acc, dbeta_acc, nullptr, nullptr, nullptr)));
     return check_launch();
@@ -991,7 +998,7 @@ extern "C" int rss_bn_bwd_apply_raw(const void* x, const void* y, const void* dy
     if (C <= 0 || C % 8 || rows <= 0 || !accum_scratch || !ticket) return RSS_ERR_SHAPE;
     if (act == RSS_ACT_RELU && dres && !y) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 4, 8);
+    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
     RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, nullptr, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
                                                                                                            nullptr, dgamma_acc, dbeta_acc, accum_scratch, ticket, sums_out)));
     return check_launch();
@@ -1003,7 +1010,7 @@ extern "C" int rss_bn_bwd_apply_dz(const void* x, const void* dz, const float* s
                                    const float* local_sums, float* dgamma_acc, float* dbeta_acc, cudaStream_t st) {
     if (C <= 0 || C % 8 || rows <= 0 || !dz) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 4, 8);
+    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
     RSS_DISPATCH_DTYPE(dtype, bn_bwd_apply_dz_kernel<T><<<grid, g.threads, 0, st>>>((const T*)x, (const T*)dz, scale, mean, invstd, sums,
                        inv_count, (T*)dx, rows, C, g.cg, g.rpb, local_sums, dgamma_acc, dbeta_acc));
     return check_launch();
