@@ -30,10 +30,17 @@ BRANCH_STREAMS = {"on": os.environ.get("RSS_BRANCH_STREAMS", "2") != "0", "flow"
 _SIDE = {}
 
 
+# The forward/backward chains (this module's streams, trainer.GraphedTrainStep's capture stream) run at HIGH stream priority and
+# the weight-gradient side streams (conv.py) at the default one: the weight gradients are only needed by the optimiser, but their
+# long library kernels were occupying the SMs whenever a chain kernel became ready (10-25 us start gaps on almost every kernel of
+# the backward chain, tools/timeline.py).  Stream capture carries the priority into the graph's kernel nodes.
+CHAIN_PRIORITY = -1 if os.environ.get("RSS_PRIORITY", "1") != "0" else 0
+
+
 def _side_streams(dev, n):
     lst = _SIDE.setdefault(dev, [])
     while len(lst) < n:
-        lst.append(torch.cuda.Stream(dev))
+        lst.append(torch.cuda.Stream(dev, priority=CHAIN_PRIORITY))
     return lst
 
 

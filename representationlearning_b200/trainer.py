@@ -164,7 +164,8 @@ class GraphedTrainStep:
         self.model, self.opt, self.group = model, opt, group
         self.img = img.clone()
         self.labels = labels.clone()
-        side = torch.cuda.Stream(img.device)
+        from .hrnet import CHAIN_PRIORITY
+        side = self.stream = torch.cuda.Stream(img.device, priority=CHAIN_PRIORITY)     # chain streams outrank the wgrad streams
         side.wait_stream(torch.cuda.current_stream())
         self.warmup_losses = []
         with torch.cuda.stream(side):
@@ -175,7 +176,7 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         opt.push_lr()
         # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures (DDP all-reduce / SyncBN inside the graph)
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+        with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="thread_local"):
             self.loss = _device_train_step(model, opt, self.img, self.labels, group)   # capture records, does not run
 
     def load(self, img, labels, non_blocking=True):
