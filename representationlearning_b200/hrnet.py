@@ -30,11 +30,12 @@ BRANCH_STREAMS = {"on": os.environ.get("RSS_BRANCH_STREAMS", "2") != "0", "flow"
 _SIDE = {}
 
 
-# The forward/backward chains (this module's streams, trainer.GraphedTrainStep's capture stream) run at HIGH stream priority and
-# the weight-gradient side streams (conv.py) at the default one: the weight gradients are only needed by the optimiser, but their
-# long library kernels were occupying the SMs whenever a chain kernel became ready (10-25 us start gaps on almost every kernel of
-# the backward chain, tools/timeline.py).  Stream capture carries the priority into the graph's kernel nodes.
-CHAIN_PRIORITY = -1 if os.environ.get("RSS_PRIORITY", "1") != "0" else 0
+# RSS_PRIORITY=1: the forward/backward chains (this module's streams, trainer.GraphedTrainStep's capture stream) run at HIGH stream
+# priority and the weight-gradient side streams (conv.py) at the default one.  Motivation: the long library wgrad kernels occupy the
+# SMs whenever a chain kernel becomes ready (10-25 us start gaps on almost every kernel of the backward chain, tools/timeline.py).
+# Measured on the B=16 step: 479 img/s with priorities vs 490 without -- the weight gradients pile up behind the chain and the
+# step ends with a serial tail -- so it is OFF by default.
+CHAIN_PRIORITY = -1 if os.environ.get("RSS_PRIORITY", "0") != "0" else 0
 
 
 def _side_streams(dev, n):
