@@ -12,6 +12,11 @@ from . import _lib  # noqa: F401
 # strict fp32 parity runs must not silently drop to TF32 inside library convolutions
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
+# RSS_CUDNN_BENCHMARK=1: let the library pick its convolution engines by measurement during the eager warm-up steps (every shape of
+# the step is static, and the warm-up runs before the CUDA-graph capture) instead of by heuristic
+import os as _os
+if _os.environ.get("RSS_CUDNN_BENCHMARK", "0") != "0":
+    torch.backends.cudnn.benchmark = True
 from .model import HRNetFusion, MODEL, RSSFORMER_CONFIG, build_rssformer  # noqa: F401
 from .modules import (FusedBNAct, GeneralTransformerBlock, InterlacedPoolAttention2, Mhca, MlpDWBN,  # noqa: F401
                       SimpleFusion8, SpatialAttention)

@@ -27,6 +27,9 @@ WGRAD = {"async": os.environ.get("RSS_WGRAD_STREAM", "1") != "0", "streams": {},
 # side streams used round-robin (measured on the B=16 step: 1 -> 464, 2 -> 493, 3 -> 492 img/s: one stream serialised the weight
 # gradients into the longest chain of the backward pass)
 WGRAD["n"] = max(1, int(os.environ.get("RSS_WGRAD_STREAMS", "2")))
+# RSS_WGRAD_AFTER_DGRAD=1: issue the data gradient (on the critical chain) before forking the weight gradient, so the side stream
+# waits for it instead of competing with it for SMs
+WGRAD["after_dgrad"] = os.environ.get("RSS_WGRAD_AFTER_DGRAD", "0") != "0"
 
 
 def wgrad_stream(dev):
@@ -182,11 +185,14 @@ class _ConvLib(torch.autograd.Function):
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
         dx = dw = db = None
-        if ctx.needs_input_grad[1]:
+        first = ctx.needs_input_grad[1] and not WGRAD["after_dgrad"]
+        if first:
             dw, db = _wgrad(dy, x, w, ctx.refs[0], ctx.refs[1], has_bias and ctx.needs_input_grad[2], stride, padding, dilation, wdtype)
         if ctx.needs_input_grad[0]:
             dx = torch.ops.aten.convolution_backward(dy, x, w, None, [stride, stride], [padding, padding], [dilation, dilation],
                                                      False, [0, 0], 1, [True, False, False])[0]
+        if ctx.needs_input_grad[1] and not first:
+            dw, db = _wgrad(dy, x, w, ctx.refs[0], ctx.refs[1], has_bias and ctx.needs_input_grad[2], stride, padding, dilation, wdtype)
         return dx, dw, db, None, None, None, None
 
 
