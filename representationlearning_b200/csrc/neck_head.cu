@@ -114,9 +114,10 @@ __global__ void neck_gather_bwd_kernel(const T* __restrict__ dcat, T* __restrict
 // ---------------------------------------------------------------------------------------------
 constexpr int kNC = 7, kNCP = 8;
 
+// General-C version: one warp per pixel, weights in shared memory (14 LDS.128 per 16-byte activation chunk: shared-memory bound).
 template <typename T>
-__global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                                       float* __restrict__ logits, int64_t pixels, int C) {
+__global__ void __launch_bounds__(256) head_fwd_smem_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                            float* __restrict__ logits, int64_t pixels, int C) {
     extern __shared__ float wsm[];                    // [7][C]
     for (int i = threadIdx.x; i < kNC * C; i += blockDim.x) wsm[i] = w[i];
     __syncthreads();
@@ -147,6 +148,73 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ x, 
     }
 }
 
+// C <= 512 (RSSFormer: 480): one warp per pixel, lane L owns the FIXED channel chunks L and L + 32 of every pixel, so its 2 x 7 x 8
+// weights live in registers for the whole kernel (the shared-memory version above spends 14 LDS.128 per loaded chunk and ran at
+// 0.15 of the HBM roofline).  kHeadU pixels per warp iteration keep 2 * kHeadU 16-byte loads in flight per lane.
+constexpr int kHeadU = 4;
+template <typename T>
+__global__ void __launch_bounds__(128) head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ logits, int64_t pixels, int C) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int chunks = C / 8;
+    const bool has0 = lane < chunks, has1 = lane + 32 < chunks;
+    float wr0[kNC][8], wr1[kNC][8];
+#pragma unroll
+    for (int o = 0; o < kNC; ++o)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            wr0[o][i] = has0 ? w[o * C + lane * 8 + i] : 0.f;
+            wr1[o][i] = has1 ? w[o * C + (lane + 32) * 8 + i] : 0.f;
+        }
+    const float bl = lane < kNC ? bias[lane] : 0.f;
+    const int64_t stride = (int64_t)gridDim.x * wpb;
+    for (int64_t pix0 = (int64_t)blockIdx.x * wpb + warp; pix0 < pixels; pix0 += kHeadU * stride) {
+        Raw8<T> r0[kHeadU], r1[kHeadU];
+#pragma unroll
+        for (int u = 0; u < kHeadU; ++u) {
+            const int64_t pix = pix0 + u * stride;
+            if (pix < pixels) {
+                if (has0) ldraw(x + pix * C + lane * 8, r0[u]);
+                if (has1) ldraw(x + pix * C + (lane + 32) * 8, r1[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kHeadU; ++u) {
+            const int64_t pix = pix0 + u * stride;
+            if (pix >= pixels) break;                  // warp-uniform
+            float acc[kNC];
+#pragma unroll
+            for (int o = 0; o < kNC; ++o) acc[o] = 0.f;
+            if (has0) {
+                float v[8];
+                unpack8(r0[u], v);
+#pragma unroll
+                for (int o = 0; o < kNC; ++o)
+                    acc[o] += v[0] * wr0[o][0] + v[1] * wr0[o][1] + v[2] * wr0[o][2] + v[3] * wr0[o][3] + v[4] * wr0[o][4] + v[5] * wr0[o][5] +
+                              v[6] * wr0[o][6] + v[7] * wr0[o][7];
+            }
+            if (has1) {
+                float v[8];
+                unpack8(r1[u], v);
+#pragma unroll
+                for (int o = 0; o < kNC; ++o)
+                    acc[o] += v[0] * wr1[o][0] + v[1] * wr1[o][1] + v[2] * wr1[o][2] + v[3] * wr1[o][3] + v[4] * wr1[o][4] + v[5] * wr1[o][5] +
+                              v[6] * wr1[o][6] + v[7] * wr1[o][7];
+            }
+#pragma unroll
+            for (int o = 0; o < kNC; ++o) acc[o] = warp_sum(acc[o]);
+            if (lane < kNCP) {
+                float r = 0.f;
+#pragma unroll
+                for (int o = 0; o < kNC; ++o) if (lane == o) r = acc[o] + bl;
+                logits[pix * kNCP + lane] = r;
+            }
+        }
+    }
+}
+
+// (A split into a dx pass and a dW pass with ~56 state registers each was measured slower on B200 -- 105 + 160 us vs 218 us for
+//  this fused kernel: both passes stayed latency-bound on their one-pixel-per-iteration loops -- so the fused kernel stays.)
 // dx[pix][c] = sum_o dl[pix][o] W[o][c];  dW[o][c] += sum_pix dl[pix][o] x[pix][c];  db[o] += sum_pix dl[pix][o]
 template <typename T>
 __global__ void head_bwd_kernel(const T* __restrict__ x, const float* __restrict__ dl, const float* __restrict__ w,
@@ -307,9 +375,15 @@ extern "C" int rss_neck_gather_bwd(const void* dcat, void* d0, void* d1, void* d
 extern "C" int rss_head_fwd(const void* x, const float* w, const float* bias, float* logits_lr, int64_t pixels, int C,
                             int dtype, cudaStream_t st) {
     if (pixels <= 0 || C <= 0 || C % 8 || (size_t)kNC * C * sizeof(float) > 48 * 1024) return RSS_ERR_SHAPE;
+    if (C <= 512) {                                   // weights in registers (2 chunks per lane)
+        int grid = (int)((pixels + 3) / 4);
+        if (grid > num_sms() * 2) grid = num_sms() * 2;      // 181 registers x 128 threads: two resident blocks per SM
+        RSS_DISPATCH_DTYPE(dtype, head_fwd_kernel<T><<<grid, 128, 0, st>>>((const T*)x, w, bias, logits_lr, pixels, C));
+        return check_launch();
+    }
     int grid = (int)((pixels + 7) / 8);
     if (grid > num_sms() * 8) grid = num_sms() * 8;
-    RSS_DISPATCH_DTYPE(dtype, head_fwd_kernel<T><<<grid, 256, kNC * C * sizeof(float), st>>>((const T*)x, w, bias, logits_lr, pixels, C));
+    RSS_DISPATCH_DTYPE(dtype, head_fwd_smem_kernel<T><<<grid, 256, kNC * C * sizeof(float), st>>>((const T*)x, w, bias, logits_lr, pixels, C));
     return check_launch();
 }
 
