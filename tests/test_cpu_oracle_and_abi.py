@@ -166,3 +166,29 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), fn
+
+
+def test_channels_last_weight_shadow_view_is_used_without_a_copy():
+    """conv._lowp(channels_last=True) hands the library convolution the per-step (Cout,kh,kw,Cin) bf16 shadow as a
+    channels_last-strided (Cout,Cin,kh,kw) view: `.contiguous(memory_format=channels_last)` must be a no-op on it."""
+    from representationlearning_b200 import conv
+    w = torch.nn.Parameter(torch.randn(8, 4, 3, 3))
+    store = torch.empty(8 * 3 * 3 * 4, dtype=torch.bfloat16)
+    view = store.view(8, 3, 3, 4).permute(0, 3, 1, 2)
+    view.copy_(w.detach())                                   # what rss_shadow_cl_refresh writes: (co, kh, kw, ci) memory order
+    conv.register_shadow_cl(w, view)
+    got = conv._lowp(w, torch.bfloat16, channels_last=True)
+    assert got.shape == w.shape and got.data_ptr() == store.data_ptr()
+    assert got.contiguous(memory_format=torch.channels_last).data_ptr() == store.data_ptr()
+    assert torch.equal(got.float(), w.detach().bfloat16().float())
+    assert store.view(8, 3, 3, 4)[2, 1, 2, 3] == w.detach()[2, 3, 1, 2].bfloat16()
+    # without a registered shadow the plain cast path is taken
+    w2 = torch.nn.Parameter(torch.randn(8, 4, 3, 3))
+    assert conv._lowp(w2, torch.bfloat16, channels_last=True).dtype == torch.bfloat16
+
+
+def test_stream_schedule_switches_are_inert_on_cpu():
+    from representationlearning_b200 import hrnet
+    assert not hrnet._dataflow(torch.zeros(1))               # the data-flow schedule only engages for CUDA tensors
+    t = [torch.zeros(2), torch.zeros(2)]
+    assert not hasattr(t[0], "_rss_home")
