@@ -211,7 +211,7 @@ __device__ __forceinline__ void load_window(const T* __restrict__ src, const LnR
                 for (int i = 0; i < 8; ++i) v[i] = (v[i] - mu) * rs * ln.gamma[part * 8 + i] + ln.beta[part * 8 + i];
             }
             if (gate_b) {
-                int gi = (int)(((int64_t)n * kC + part * 8) % g.HW);
+                int gi = (int)(((uint32_t)n * kC + part * 8) % (uint32_t)g.HW);      // n < HW <= 2^26: 32-bit modulo
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { v[i] *= gate_b[gi]; if (++gi == g.HW) gi = 0; }
             }
@@ -455,7 +455,7 @@ __device__ __forceinline__ void load_window_bf16(const T* __restrict__ src, cons
                 for (int i = 0; i < 8; ++i) v[i] = (v[i] - mu) * rs * ln.gamma[part * 8 + i] + ln.beta[part * 8 + i];
             }
             if (gate_b) {
-                int gi = (int)(((int64_t)n * kC + part * 8) % g.HW);
+                int gi = (int)(((uint32_t)n * kC + part * 8) % (uint32_t)g.HW);      // n < HW <= 2^26: 32-bit modulo
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { v[i] *= gate_b[gi]; if (++gi == g.HW) gi = 0; }
             }
@@ -1367,7 +1367,9 @@ __global__ void gate_bwd_apply_kernel(const float* __restrict__ dxg, const float
         const int64_t f0 = i8 * 8;
         float v[8];
         load8(src + f0, v);
-        int j = (int)(f0 % HW), kk = (int)(f0 / HW);
+        // f0 < HW*kC: 32-bit division whenever that fits (always, for any image this path sees)
+        int kk = (int64_t)HW * kC < 0x7fffffffLL ? (int)((uint32_t)f0 / (uint32_t)HW) : (int)(f0 / HW);
+        int j = (int)(f0 - (int64_t)kk * HW);
         if ((HW & 7) == 0) {                 // the 8 positions stay inside one row k of the flat view: vector loads of the maps
             float g8[8], a8[8], m8[8];
             load8(gm + j, g8);
@@ -1521,7 +1523,7 @@ extern "C" int rss_attn_fwd(const void* x, const void* y, const rss_attn_params*
                             void* out, cudaStream_t stream) {
     if (B <= 0 || H <= 0 || W <= 0 || !p) return RSS_ERR_SHAPE;
     if (p->C != kC || p->num_heads != 2 || p->window != kWS) return RSS_ERR_SHAPE;
-    if (((int64_t)H * W * kC) % 8) return RSS_ERR_SHAPE;
+    if (((int64_t)H * W * kC) % 8 || (int64_t)H * W * kC >= 0x7fffffffLL) return RSS_ERR_SHAPE;     // 32-bit per-image index math
     RSS_DISPATCH_DTYPE(dtype, return attn_fwd_impl<T>(x, y, p, B, H, W, flags, ln_stats, pooled, amax, smap, gmap, out, stream));
 }
 
@@ -1531,6 +1533,7 @@ extern "C" int rss_attn_bwd(const void* dout, const void* x, const void* y, cons
                             void* dx, void* dy, const rss_attn_grads* grads, cudaStream_t stream) {
     if (B <= 0 || H <= 0 || W <= 0 || !p || !grads) return RSS_ERR_SHAPE;
     if (p->C != kC || p->num_heads != 2 || p->window != kWS) return RSS_ERR_SHAPE;
+    if ((int64_t)H * W * kC >= 0x7fffffffLL) return RSS_ERR_SHAPE;
     if (workspace_bytes < rss_attn_bwd_workspace_bytes(B, H, W, dtype)) return RSS_ERR_WORKSPACE;
     RSS_DISPATCH_DTYPE(dtype, return attn_bwd_impl<T>(dout, x, y, p, B, H, W, flags, ln_stats, pooled, amax, smap, gmap,
                                                         workspace, dx, dy, grads, stream));

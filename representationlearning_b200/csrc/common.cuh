@@ -124,6 +124,29 @@ template <> __device__ __forceinline__ float gelu_grad_t<__nv_bfloat16>(float z)
 }
 __device__ __forceinline__ float sigmoid_f(float z) { return 1.0f / (1.0f + __expf(-z)); }
 
+// (group, x, y, b) of a flat index over [b][y][x][group].  The element counts of this path fit 32 bits (B=16 x 128^2 x 60 groups =
+// 15.7 M), and five 64-bit divisions per 16 bytes of output were most of the instructions of the gather / fuse kernels, so the
+// 32-bit path is taken whenever the launch is small enough (`small` is launch-uniform).
+struct PixIdx { int grp, x, y, b; int64_t pix; };
+__device__ __forceinline__ PixIdx split_pix(int64_t idx, int groups, int W, int H, bool small) {
+    PixIdx r;
+    if (small) {
+        const uint32_t i = (uint32_t)idx, pix = i / (uint32_t)groups, t = pix / (uint32_t)W;
+        r.grp = (int)(i - pix * (uint32_t)groups);
+        r.x = (int)(pix - t * (uint32_t)W);
+        r.b = (int)(t / (uint32_t)H);
+        r.y = (int)(t - (uint32_t)r.b * (uint32_t)H);
+        r.pix = pix;
+    } else {
+        r.grp = (int)(idx % groups);
+        r.pix = idx / groups;
+        r.x = (int)(r.pix % W);
+        r.y = (int)((r.pix / W) % H);
+        r.b = (int)(r.pix / ((int64_t)W * H));
+    }
+    return r;
+}
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {

@@ -12,10 +12,11 @@ template <typename T>
 __global__ void fuse_sum_fwd_kernel(FuseTerms t, T* __restrict__ out, int B, int H, int W, int C, int relu) {
     const int groups = C / 8;
     const int64_t total = (int64_t)B * H * W * groups;
+    const bool small = total < 0x7fffffffLL;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int grp = (int)(idx % groups);
-        const int64_t pix = idx / groups;
-        const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((int64_t)W * H));
+        const PixIdx q = split_pix(idx, groups, W, H, small);
+        const int grp = q.grp, x = q.x, y = q.y, b = q.b;
+        const int64_t pix = q.pix;
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -43,10 +44,11 @@ __global__ void fuse_sum_bwd_kernel(const T* __restrict__ dout, const T* __restr
                                     int B, int H, int W, int C, int k, int relu) {
     const int groups = C / 8, h = H >> k, w = W >> k, s = 1 << k;
     const int64_t total = (int64_t)B * h * w * groups;
+    const bool small = total < 0x7fffffffLL;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int grp = (int)(idx % groups);
-        const int64_t pix = idx / groups;
-        const int x = (int)(pix % w), y = (int)((pix / w) % h), b = (int)(pix / ((int64_t)w * h));
+        const PixIdx q = split_pix(idx, groups, w, h, small);
+        const int grp = q.grp, x = q.x, y = q.y, b = q.b;
+        const int64_t pix = q.pix;
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;

@@ -34,10 +34,11 @@ __global__ void neck_gather_fwd_kernel(const T* __restrict__ f0, const T* __rest
                                        const T* __restrict__ f3, T* __restrict__ out, NeckGeom g) {
     const int groups = g.Ctot / 8;
     const int64_t total = (int64_t)g.B * g.H * g.W * groups;
+    const bool small = total < 0x7fffffffLL;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int grp = (int)(idx % groups);
-        const int64_t pix = idx / groups;
-        const int ox = (int)(pix % g.W), oy = (int)((pix / g.W) % g.H), b = (int)(pix / ((int64_t)g.W * g.H));
+        const PixIdx q = split_pix(idx, groups, g.W, g.H, small);
+        const int grp = q.grp, ox = q.x, oy = q.y, b = q.b;
+        const int64_t pix = q.pix;
         const int ch = grp * 8;
         int l = 0;
         if (ch >= g.coff[3]) l = 3; else if (ch >= g.coff[2]) l = 2; else if (ch >= g.coff[1]) l = 1;
@@ -71,10 +72,11 @@ __global__ void neck_gather_bwd_kernel(const T* __restrict__ dcat, T* __restrict
     const int l = level, Cl = g.C[l], hl = g.h[l], wl = g.w[l], groups = Cl / 8;
     T* dst = l == 0 ? d0 : (l == 1 ? d1 : (l == 2 ? d2 : d3));
     const int64_t total = (int64_t)g.B * hl * wl * groups;
+    const bool small = total < 0x7fffffffLL;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int grp = (int)(idx % groups);
-        const int64_t pix = idx / groups;
-        const int ix = (int)(pix % wl), iy = (int)((pix / wl) % hl), b = (int)(pix / ((int64_t)wl * hl));
+        const PixIdx q = split_pix(idx, groups, wl, hl, small);
+        const int grp = q.grp, ix = q.x, iy = q.y, b = q.b;
+        const int64_t pix = q.pix;
         const T* src = dcat + (int64_t)b * g.H * g.W * g.Ctot + g.coff[l] + grp * 8;
         float acc[8];
 #pragma unroll
