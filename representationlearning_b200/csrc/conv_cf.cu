@@ -397,6 +397,13 @@ static CfEncodeTiledFn cf_encode_tiled() {
     return fn;
 }
 
+// conv_c32.cu
+int conv_c32_launch(const void* x, const void* w_packed, void* y, int B, int H, int W, const int* taps_dy, const int* taps_dx,
+                    const float* in_scale, const float* in_shift, int in_relu,
+                    float* stat_accum, unsigned int* stat_ticket, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps,
+                    float* mean_out, float* invstd_out, float* scale_out, float* shift_out, cudaStream_t stream);
+
 }  // namespace rss
 
 using namespace rss;
@@ -441,6 +448,14 @@ extern "C" int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, 
         st.accum = stat_accum; st.ticket = stat_ticket; st.gamma = gamma; st.beta = beta; st.running_mean = running_mean;
         st.running_var = running_var; st.momentum = momentum; st.eps = eps; st.mean_out = mean_out; st.invstd_out = invstd_out;
         st.scale_out = scale_out; st.shift_out = shift_out; st.count = (float)((double)B * H * W);
+    }
+    {
+        // EXPERIMENTAL (RSS_CF_MMA=1): the 32 -> 32 channel 3x3 layers go to the flat mma.sync kernel of conv_c32.cu
+        static const int use_mma = getenv("RSS_CF_MMA") ? atoi(getenv("RSS_CF_MMA")) : 0;
+        if (use_mma && Cin == 32 && Cout == 32 && n_taps == 9)
+            return conv_c32_launch(x, w_packed, y, B, H, W, taps_dy, taps_dx, in_scale, in_shift, in_relu,
+                                   stats ? stat_accum : nullptr, stat_ticket, gamma, beta, running_mean, running_var, momentum, eps,
+                                   mean_out, invstd_out, scale_out, shift_out, stream);
     }
     CUtensorMap tm;
     {
