@@ -283,10 +283,17 @@ ENGINE["cf"] = os.environ.get("RSS_CONV_CF", "0") != "0"      # fused tcgen05 co
 # (bit-correct, but its cp.async producer is still slower than the library conv + separate statistics kernel: off by default)
 
 
+# RSS_CF_MMA=1 (experimental, csrc/conv_c32.cu): with RSS_CONV_CF=1 only the 32 -> 32 channel 3x3 layers (HRNet branch 0, the
+# critical stream) take the hand-written path -- the library keeps every other shape
+ENGINE["cf_c32_only"] = os.environ.get("RSS_CF_MMA", "0") != "0"
+
+
 def _cf_ok(x, Cout, k, with_stats):
     if not ENGINE["cf"] or x.dtype != torch.bfloat16 or not x.is_cuda:
         return False
     B, Cin, H, W = x.shape
+    if ENGINE["cf_c32_only"] and not (Cin == 32 and Cout == 32 and k == 3):
+        return False
     return bool(_lib.load().rss_conv_cf_supported(B, H, W, Cin, Cout, k, int(with_stats)))
 
 
