@@ -91,6 +91,13 @@ class FlatSGD:
             conv.register_shadow_cl(p, self.shadow_cl[o:o + p.numel()].view(shp).permute(0, 3, 1, 2))
         self.refresh_cl_shadow()
 
+    def sync_shadows(self):
+        """call after writing parameters from outside the optimiser (e.g. load_state_dict on resume): refreshes the bf16 copies
+        the convolution kernels read"""
+        if self.shadow is not None:
+            self.shadow.copy_(self.flat_p)
+        self.refresh_cl_shadow()
+
     def refresh_cl_shadow(self):
         if self.shadow_cl is not None:
             ops.shadow_cl_refresh(self.flat_p, self.shadow_cl, self._cl_table, self._cl_rows, *self._cl_meta)
