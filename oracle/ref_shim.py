@@ -12,8 +12,10 @@ minimal stand-ins are registered in `sys.modules` *before* the reference is
 imported.  Nothing in here does arithmetic: the numerics that come out of
 `load_reference()` are 100 % the reference's own code on torch CPU.
 
-`/root/reference` does not exist on the GPU box; this module must only be used
-from `oracle/gen_golden.py` and from tests that skip when the tree is absent.
+`/root/reference` does not exist on the GPU box.  There the same unmodified sources are imported from the
+travelling archive `oracle/_ref/rssformer_reference.zip` (zipimport; built by `oracle/build_ref.py`, git-ignored).
+This module must only be used from `oracle/gen_golden.py`, `bench.py`'s reference / baseline legs and tests that
+skip when neither the tree nor the archive is present.
 """
 import os
 import sys
@@ -21,10 +23,20 @@ import types
 import logging
 
 REFERENCE_ROOT = os.environ.get("RSS_REFERENCE_ROOT", "/root/reference/RSSFormer-TIP2023")
+REFERENCE_ZIP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "rssformer_reference.zip")
+
+
+def reference_tree_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "module", "baseline"))
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "module", "baseline"))
+    """the unmodified reference can be imported: from its tree (authoring container) or from the travelling archive"""
+    return reference_tree_available() or os.path.exists(REFERENCE_ZIP)
+
+
+def reference_path():
+    return REFERENCE_ROOT if reference_tree_available() else REFERENCE_ZIP
 
 
 class _AttrDict(dict):
@@ -140,10 +152,10 @@ RSSFORMER_PARAMS = dict(  # restated from configs/baseline/hrnetw32.py:7-33 (pre
 def load_reference():
     """Returns the reference's python modules (hrnet_aux, MTFM, ...) imported from REFERENCE_ROOT."""
     if not reference_available():
-        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+        raise RuntimeError("reference not present at %s or %s" % (REFERENCE_ROOT, REFERENCE_ZIP))
     _install_fakes()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if reference_path() not in sys.path:
+        sys.path.insert(0, reference_path())
     import importlib
     ns = types.SimpleNamespace()
     ns.hrnet_aux = importlib.import_module("module.baseline.hrnet_aux")

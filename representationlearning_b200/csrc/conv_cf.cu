@@ -48,7 +48,9 @@ struct CfGeom {
     int in_relu;
     int desc_swap;                       // debugging aid (RSS_CF_DESC_SWAP=1): base-offset field = (start >> 7) & 7 (measured WRONG)
     int dbg;                             // profiling aid (RSS_CF_DBG bits): 1 no epilogue stores/stats, 2 no TMA after the first S tiles, 4 no MMAs
+    long long* trace;                    // profiling aid (RSS_CF_TRACE_PTR): CTA 0 records clock64() per role/tile/event, [4 roles][16 tiles][8]
 };
+#define CF_TRACE(role, i, k) do { if (g.trace && blockIdx.x == 0 && (i) < 16) g.trace[((role) * 16 + (i)) * 8 + (k)] = clock64(); } while (0)
 
 struct CfStats {                         // all NULL when no statistics are wanted (data gradients)
     float* accum;                        // [2*Cout] persistent, zero between launches
@@ -127,7 +129,9 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
             int i = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++i) {
                 const int si = i % S, use = i / S;
+                CF_TRACE(0, i, 0);
                 if (use > 0) mbar_wait(smem_u32(bar_empty + si), (use - 1) & 1);         // MMAs that read this stage retired
+                CF_TRACE(0, i, 1);
                 const int b = tile / g.tiles_per_img, t = tile % g.tiles_per_img;
                 const int r_lo = cf_row_lo(t * g.MT, g.halo, g.Wp);
                 const uint32_t full = smem_u32(bar_landed + si);
@@ -135,6 +139,7 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                 mbar_expect_tx(full, tx_bytes);
                 for (int pl = 0; pl < g.KC; ++pl)
                     tma_load_4d(a_s + si * stage_bytes + (uint32_t)(pl * g.P) * 128, &tmap_x, full, pl * 64, -g.halo, r_lo, b);
+                CF_TRACE(0, i, 2);
             }
         }
     } else if (warp < 4) {
@@ -149,7 +154,9 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
             int i = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++i) {
                 const int si = i % S;
+                if (ht == 0) CF_TRACE(1, i, 0);
                 mbar_wait(smem_u32(bar_landed + si), (i / S) & 1);
+                if (ht == 0) CF_TRACE(1, i, 1);
                 const int t = tile % g.tiles_per_img;
                 const int r_lo = cf_row_lo(t * g.MT, g.halo, g.Wp);
                 uint8_t* base = smem + w_bytes + (size_t)si * stage_bytes + (size_t)((ch >> 3) * g.P) * 128;
@@ -174,6 +181,7 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(bar_ready + si));
+                if (ht == 0) CF_TRACE(1, i, 2);
             }
         }
     } else if (warp == 4) {
@@ -191,7 +199,9 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++i) {
                 const int si = i % S;
+                if (lane == 0) CF_TRACE(2, i, 0);
                 mbar_wait(smem_u32(bar_in + si), (i / S) & 1);             // tile staged (and transformed)
+                if (lane == 0) CF_TRACE(2, i, 1);
                 fence_proxy_async_smem();
                 tc_fence_after();
                 const int t = tile % g.tiles_per_img;
@@ -202,6 +212,7 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                 const uint32_t a_lo0 = ((a_s + si * stage_bytes) >> 4) + (uint32_t)pbase * 8;
                 for (int mm = 0; mm < g.MM; ++mm) {
                     mbar_wait(smem_u32(bar_tempty + acc), acc_phase ^ 1);                // epilogue drained this accumulator
+                    if (lane == 0) CF_TRACE(2, i, 2 + 2 * mm);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_u + acc * g.Cout;
                     const uint32_t a_lo1 = a_lo0 + (uint32_t)mm * 128 * 8;
@@ -222,6 +233,7 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                         }
                     }
                     umma_commit_elect(leader, smem_u32(bar_tfull + acc));                        // accumulator complete -> epilogue
+                    if (lane == 0) CF_TRACE(2, i, 3 + 2 * mm);
                     if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
                 }
                 umma_commit_elect(leader, smem_u32(bar_empty + si));                              // stage free once these MMAs retire
@@ -242,14 +254,17 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
         }
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++ti) {
             const int b = tile / g.tiles_per_img, t = tile % g.tiles_per_img;
             for (int mm = 0; mm < g.MM; ++mm) {
                 const int q = t * g.MT + mm * 128 + m;
                 const int r = q / g.Wp, c = q - r * g.Wp - g.halo;
                 const bool live = q < g.Q && c >= 0 && c < g.W && !(g.dbg & 1);
                 __nv_bfloat16* dst = y + (((size_t)b * g.H + r) * g.W + c) * g.Cout;
+                if (m == 0) CF_TRACE(3, ti, 4 * mm);
                 mbar_wait(smem_u32(bar_tfull + acc), acc_phase);
+                if (m == 0) CF_TRACE(3, ti, 4 * mm + 1);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * g.Cout;
                 if (COUT_S > 0) {
@@ -291,6 +306,7 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(bar_tempty + acc));
+                if (m == 0) CF_TRACE(3, ti, 4 * mm + 2);
                 if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -346,7 +362,7 @@ static int cf_plan(int B, int H, int W, int Cin, int Cout, int n_taps, const int
     if (Cin != 32 && Cin != 64 && Cin != 128) return RSS_ERR_SHAPE;          // 96 helper threads / (Cin/8) chunks; 64-channel planes
     if (Cout < 16 || Cout % 16 || Cout > 128) return RSS_ERR_SHAPE;
     CfGeom& g = pl->g;
-    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.n_taps = n_taps; g.in_relu = 0; g.desc_swap = 0; g.dbg = 0;
+    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.n_taps = n_taps; g.in_relu = 0; g.desc_swap = 0; g.dbg = 0; g.trace = nullptr;
     int halo = 0;
     for (int t = 0; t < n_taps; ++t) {
         const int a = dy[t] < 0 ? -dy[t] : dy[t], b = dx[t] < 0 ? -dx[t] : dx[t];
@@ -439,6 +455,8 @@ extern "C" int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, 
         pl.g.desc_swap = (sw && sw[0] == '1') ? 1 : 0;
         const char* dbg = getenv("RSS_CF_DBG");
         pl.g.dbg = dbg ? atoi(dbg) : 0;
+        const char* tr = getenv("RSS_CF_TRACE_PTR");
+        pl.g.trace = tr ? (long long*)strtoull(tr, nullptr, 16) : nullptr;
     }
     CfStats st{};
     const bool stats = stat_accum != nullptr;
@@ -451,7 +469,7 @@ extern "C" int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, 
     }
     {
         // EXPERIMENTAL (RSS_CF_MMA=1): the 32 -> 32 channel 3x3 layers go to the flat mma.sync kernel of conv_c32.cu
-        static const int use_mma = getenv("RSS_CF_MMA") ? atoi(getenv("RSS_CF_MMA")) : 0;
+        const char* um = getenv("RSS_CF_MMA"); const int use_mma = um ? atoi(um) : 0;
         if (use_mma && Cin == 32 && Cout == 32 && n_taps == 9)
             return conv_c32_launch(x, w_packed, y, B, H, W, taps_dy, taps_dx, in_scale, in_shift, in_relu,
                                    stats ? stat_accum : nullptr, stat_ticket, gamma, beta, running_mean, running_var, momentum, eps,
