@@ -185,19 +185,40 @@ int rss_conv_igemm(const void* x, const void* w_packed, const float* bias /*may 
                    int Cin, int Cout, int n_taps, const int* taps_dy, const int* taps_dx, cudaStream_t stream);
 
 /* ---- fused tcgen05 convolution of the HRNet family (BasicBlock/Bottleneck 3x3 and 1x1 stride-1 convs and their data gradients:
- *      _hrnet_rssformer.py:209-287): y = conv(T(x)), T = identity or relu(x*in_scale + in_shift) (the previous layer's
- *      BatchNorm+ReLU applied on load), plus -- when stat_accum != NULL -- the training-mode BatchNorm statistics of y with the
- *      contract of rss_bn_stats_fused (persistent zeroed accum[2*Cout] + ticket; outputs mean/invstd/scale/shift; running stats
- *      updated).  Every input pixel is staged in shared memory once per tile ([channel chunk][position][8 ch] = no-swizzle UMMA
- *      layout) and all taps read it at shifted descriptor addresses.  w_packed: bf16 [tap][Cout][Cin] from
+ *      _hrnet_rssformer.py:209-287):  y = E(conv(T(x)) + add)
+ *        T = identity or relu(x*in_scale + in_shift): the previous layer's BatchNorm(+ReLU) applied to the staged tile;
+ *        E = RSS_CF_PLAIN  identity
+ *            RSS_CF_STATS  + training-mode BatchNorm statistics of y with the contract of rss_bn_stats_fused (persistent zeroed
+ *                          accum[2*Cout] + ticket; outputs mean/invstd/scale/shift; running statistics updated)
+ *            RSS_CF_BNRED  y is the gradient w.r.t. the output of a BatchNorm(+ReLU) with input bn_z: stores g = y * relu_mask
+ *                          (mask = bn_out > 0 when bn_out is given, else bn_scale*bn_z + bn_shift > 0 when bn_relu, else 1)
+ *                          and sums_out[0:Cout] = sum g, sums_out[Cout:2*Cout] = sum g * (bn_z - bn_mean) * bn_invstd
+ *                          (what rss_bn_bwd_apply needs; same accum/ticket contract).
+ *      Every input pixel is staged in shared memory once per tile (TMA box of whole zero-padded rows, 128B-swizzled K-major
+ *      UMMA layout) and all taps read it at shifted descriptor addresses.  w_packed: bf16 [tap][Cout][Cin] from
  *      rss_conv_pack_weights (transpose=1 pack with Cin/Cout swapped gives the data gradient). ---- */
-int rss_conv_cf_supported(int B, int H, int W, int Cin, int Cout, int ksize, int with_stats);
+#define RSS_CF_PLAIN 0
+#define RSS_CF_STATS 1
+#define RSS_CF_BNRED 2
+typedef struct {
+    int mode;                          /* RSS_CF_* */
+    const void* add;                   /* bf16 (B,H,W,Cout) added before E, or NULL (residual gradient / residual) */
+    float* accum;                      /* STATS, BNRED: persistent zeroed [2*Cout] */
+    unsigned int* ticket;              /* STATS, BNRED: persistent zeroed */
+    const float* gamma; const float* beta;             /* STATS */
+    float* running_mean; float* running_var;           /* STATS, may be NULL */
+    float momentum, eps;                               /* STATS */
+    float* mean_out; float* invstd_out; float* scale_out; float* shift_out;   /* STATS */
+    const void* bn_z; const void* bn_out;              /* BNRED (bn_out may be NULL) */
+    const float* bn_mean; const float* bn_invstd; const float* bn_scale; const float* bn_shift;   /* BNRED */
+    int bn_relu;                                       /* BNRED */
+    float* sums_out;                                   /* BNRED: [2*Cout] */
+} RssConvCfEpilogue;
+int rss_conv_cf_supported(int B, int H, int W, int Cin, int Cout, int ksize, int mode);
 int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, int H, int W, int Cin, int Cout,
                 int n_taps, const int* taps_dy, const int* taps_dx,
                 const float* in_scale /*[Cin] or NULL*/, const float* in_shift, int in_relu,
-                float* stat_accum /*NULL: no statistics*/, unsigned int* stat_ticket, const float* gamma, const float* beta,
-                float* running_mean /*may be NULL*/, float* running_var, float momentum, float eps,
-                float* mean_out, float* invstd_out, float* scale_out, float* shift_out, cudaStream_t stream);
+                const RssConvCfEpilogue* epilogue /*NULL = plain*/, cudaStream_t stream);
 
 /* ---- weight gradient of the HRNet-family convolutions (BasicBlock/Bottleneck 3x3, stride-2 3x3 of the transition/fuse layers,
  *      small 1x1 convs: _hrnet_rssformer.py:209-287,361-405,512-546; FFN fc1/fc2: ffn_block.py:219,232).  Replaces the

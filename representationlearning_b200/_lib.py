@@ -31,6 +31,16 @@ class AttnGrads(Structure):
                                         "q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w", "o_b")]
 
 
+class ConvCfEpilogue(Structure):
+    """RssConvCfEpilogue of include/rss_b200.h"""
+    _fields_ = [("mode", c_int), ("add", c_void_p), ("accum", c_void_p), ("ticket", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+                ("running_mean", c_void_p), ("running_var", c_void_p), ("momentum", c_float), ("eps", c_float),
+                ("mean_out", c_void_p), ("invstd_out", c_void_p), ("scale_out", c_void_p), ("shift_out", c_void_p),
+                ("bn_z", c_void_p), ("bn_out", c_void_p), ("bn_mean", c_void_p), ("bn_invstd", c_void_p), ("bn_scale", c_void_p),
+                ("bn_shift", c_void_p), ("bn_relu", c_int), ("sums_out", c_void_p)]
+
+
+CF_PLAIN, CF_STATS, CF_BNRED = 0, 1, 2
 P = c_void_p
 # name -> (restype, argtypes); must list every symbol include/rss_b200.h declares (tests check this)
 SIGNATURES = {
@@ -69,7 +79,7 @@ SIGNATURES = {
     "rss_conv_igemm": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P]),
     "rss_conv_cf_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "rss_conv_cf": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P, P, c_int,
-                            P, P, P, P, P, P, c_float, c_float, P, P, P, P, P]),
+                            POINTER(ConvCfEpilogue), P]),
     "rss_conv_wgrad_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "rss_conv_wgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "rss_conv_wgrad_tc_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),

@@ -283,42 +283,61 @@ ENGINE["cf"] = os.environ.get("RSS_CONV_CF", "0") != "0"      # fused tcgen05 co
 # (bit-correct, but its cp.async producer is still slower than the library conv + separate statistics kernel: off by default)
 
 
-# RSS_CF_MMA=1 (experimental, csrc/conv_c32.cu): with RSS_CONV_CF=1 only the 32 -> 32 channel 3x3 layers (HRNet branch 0, the
-# critical stream) take the hand-written path -- the library keeps every other shape
-ENGINE["cf_c32_only"] = os.environ.get("RSS_CF_MMA", "0") != "0"
-
-
-def _cf_ok(x, Cout, k, with_stats):
+def _cf_ok(x, Cout, k, mode):
+    """mode: False/True (plain / statistics epilogue, as conv_bn_stats passes it) or one of _lib.CF_*"""
     if not ENGINE["cf"] or x.dtype != torch.bfloat16 or not x.is_cuda:
         return False
     B, Cin, H, W = x.shape
-    if ENGINE["cf_c32_only"] and not (Cin == 32 and Cout == 32 and k == 3):
-        return False
-    return bool(_lib.load().rss_conv_cf_supported(B, H, W, Cin, Cout, k, int(with_stats)))
+    return bool(_lib.load().rss_conv_cf_supported(B, H, W, Cin, Cout, k, int(mode)))
 
 
-def _cf_launch(x, packed, nt, tdy, tdx, Cin, Cout, in_aff, in_relu, stats):
-    """one rss_conv_cf launch; stats = None or (gamma, beta, running_mean, running_var, momentum, eps, scratch) -> (y, aff)"""
+def _cf_launch(x, packed, nt, tdy, tdx, Cin, Cout, in_aff, in_relu, stats, add=None, bnred=None):
+    """one rss_conv_cf launch -> (y, extra).
+    in_aff: (4,Cin) mean/invstd/scale/shift of the BatchNorm whose (+ReLU) output this conv consumes (applied on load) or None
+    stats = (gamma, beta, running_mean, running_var, momentum, eps, scratch): statistics epilogue, extra = (4,Cout) affine
+    add: tensor of y's shape added in the epilogue (residual / residual-path gradient)
+    bnred = (z, out_or_None, aff(4,Cout), relu, scratch): BatchNorm-backward reduction epilogue, y = masked gradient,
+            extra = sums (2*Cout)"""
     lib = _lib.load()
     B, _, H, W = x.shape
     y = torch.empty((B, Cout, H, W), device=x.device, dtype=x.dtype, memory_format=CL)
-    aff = None
-    sp = [None] * 10
-    mom = eps = 0.0
-    if stats is not None:
-        gamma, beta, rm, rv, mom, eps, scratch = stats
-        aff = torch.empty(4, Cout, device=x.device, dtype=torch.float32)
-        g, b = ops._f32(gamma), ops._f32(beta)
-        sp = [scratch[2:].data_ptr(), scratch.data_ptr(), g.data_ptr(), b.data_ptr(), ops._p(rm), ops._p(rv),
-              aff[0].data_ptr(), aff[1].data_ptr(), aff[2].data_ptr(), aff[3].data_ptr()]
+    extra = None
+    ep = None
+    keep = []
+    if stats is not None or add is not None or bnred is not None:
+        ep = _lib.ConvCfEpilogue()
+        ep.mode = _lib.CF_PLAIN
+        if add is not None:
+            add = ops.nhwc(add)
+            assert add.shape == y.shape and add.dtype == y.dtype
+            ep.add = add.data_ptr()
+        if stats is not None:
+            gamma, beta, rm, rv, mom, eps, scratch = stats
+            extra = torch.empty(4, Cout, device=x.device, dtype=torch.float32)
+            g, b = ops._f32(gamma), ops._f32(beta)
+            keep += [g, b]
+            ep.mode = _lib.CF_STATS
+            ep.accum, ep.ticket = scratch[2:].data_ptr(), scratch.data_ptr()
+            ep.gamma, ep.beta, ep.running_mean, ep.running_var = g.data_ptr(), b.data_ptr(), ops._p(rm), ops._p(rv)
+            ep.momentum, ep.eps = float(mom), float(eps)
+            ep.mean_out, ep.invstd_out, ep.scale_out, ep.shift_out = (extra[i].data_ptr() for i in range(4))
+        elif bnred is not None:
+            z, out, aff, relu, scratch = bnred
+            assert z.shape == y.shape and z.dtype == y.dtype and z.is_contiguous(memory_format=CL)
+            extra = torch.empty(2 * Cout, device=x.device, dtype=torch.float32)
+            ep.mode = _lib.CF_BNRED
+            ep.accum, ep.ticket = scratch[2:].data_ptr(), scratch.data_ptr()
+            ep.bn_z, ep.bn_out = z.data_ptr(), ops._p(out)
+            ep.bn_mean, ep.bn_invstd, ep.bn_scale, ep.bn_shift = (aff[i].data_ptr() for i in range(4))
+            ep.bn_relu = int(relu)
+            ep.sums_out = extra.data_ptr()
     isc = ish = None
     if in_aff is not None:
         isc, ish = in_aff[2].data_ptr(), in_aff[3].data_ptr()
     with ops.timed("rss_conv_cf"):
         ops.check(lib.rss_conv_cf(x.data_ptr(), packed.data_ptr(), y.data_ptr(), B, H, W, Cin, Cout, nt, tdy, tdx, isc, ish,
-                                  int(in_relu), sp[0], sp[1], sp[2], sp[3], sp[4], sp[5], float(mom), float(eps), sp[6], sp[7], sp[8],
-                                  sp[9], ops._st()), "rss_conv_cf")
-    return y, aff
+                                  int(in_relu), None if ep is None else ctypes.byref(ep), ops._st()), "rss_conv_cf")
+    return y, extra
 
 
 class _ConvCF(torch.autograd.Function):

@@ -581,9 +581,10 @@ CF_CASES = [
     (2, 20, 128, 64, 64, 3, True, False),      # layer1 geometry (wide, 64 channels)
     (2, 24, 24, 64, 32, 1, True, False),       # 1x1 (fuse layers)
     (2, 12, 20, 128, 32, 1, True, True),
-    (2, 16, 16, 32, 128, 3, False, False),     # no statistics, wide N (data-gradient shape)
-    (2, 16, 16, 64, 128, 3, False, False),
+    (2, 16, 16, 32, 128, 1, False, False),     # FFN fc1 geometry (wide N, no statistics)
     (2, 12, 20, 128, 64, 1, False, True),
+    (16, 128, 128, 32, 32, 3, True, True),     # the benched branch-0 layer: 1040 tiles over 148 persistent CTAs, 2-stage ring wraps
+    (16, 64, 64, 64, 64, 3, True, True),       # the benched branch-1 layer
 ]
 
 
@@ -607,7 +608,7 @@ def _cf_call(lib, x, w, k, stats, in_aff, in_relu, rm=None, rv=None, gamma=None,
 def test_conv_cf(P, report, case):
     lib = P._lib.load()
     B, H, W, Cin, Cout, k, stats, xform = case
-    assert lib.rss_conv_cf_supported(B, H, W, Cin, Cout, k, int(stats)) == 1
+    assert lib.rss_conv_cf_supported(B, H, W, Cin, Cout, k, int(stats)) == 1, "geometry not instantiated"
     torch.manual_seed(3)
     x = torch.randn(B, Cin, H, W, device=DEV).bfloat16()
     w = (torch.randn(Cout, Cin, k, k, device=DEV) / (Cin * k * k) ** 0.5).bfloat16().float()
@@ -638,6 +639,71 @@ def test_conv_cf(P, report, case):
     report["cf_%s" % "_".join(map(str, case))] = errs
     assert errs["y"] < 6e-3, errs                         # bf16 output rounding (2^-9 of max) dominates
     assert max(v for kk, v in errs.items() if kk != "y") < TOL_F32 if stats else True, errs
+
+
+CF_EPI_CASES = [
+    # B, H, W, C, k, add, bn_out given, bn_relu, xform
+    (2, 19, 23, 32, 3, True, True, True, False),       # residual block: mask from the stored output, + residual-path gradient
+    (2, 19, 23, 32, 3, False, False, True, False),     # plain BN+ReLU: mask recomputed from z and the affine
+    (2, 16, 16, 64, 3, True, False, False, True),      # BN without activation (fuse/downsample layers)
+    (16, 128, 128, 32, 3, True, True, True, False),    # benched geometry
+    (4, 64, 64, 64, 3, False, False, True, False),
+]
+
+
+@pytest.mark.parametrize("case", CF_EPI_CASES)
+def test_conv_cf_bn_backward_epilogue(P, report, case):
+    """rss_conv_cf with RSS_CF_BNRED (+add): the data-gradient conv whose epilogue masks the gradient with the ReLU of the
+    BatchNorm it flows into and reduces sum(g), sum(g*xhat) -- against conv2d + the same arithmetic in torch fp32."""
+    from representationlearning_b200 import conv
+    B, H, W, C, k, with_add, with_out, relu, xform = case
+    lib = P._lib.load()
+    assert lib.rss_conv_cf_supported(B, H, W, C, C, k, P._lib.CF_BNRED) == 1
+    torch.manual_seed(11)
+    x = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    w = (torch.randn(C, C, k, k, device=DEV) / (C * k * k) ** 0.5).bfloat16().float()
+    z = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    add = torch.randn(B, C, H, W, device=DEV).bfloat16() if with_add else None
+    aff = torch.zeros(4, C, device=DEV)
+    aff[0] = torch.randn(C, device=DEV) * 0.2
+    aff[1] = torch.rand(C, device=DEV) + 0.5
+    gamma = torch.rand(C, device=DEV) + 0.5
+    aff[2] = gamma * aff[1]
+    aff[3] = torch.randn(C, device=DEV) * 0.3 - aff[0] * aff[2]
+    v = lambda t: t.view(1, -1, 1, 1)
+    act = z.float() * v(aff[2]) + v(aff[3])
+    out = None
+    if with_out:       # residual block: the mask comes from relu(bn(z) + residual), which the affine alone cannot reproduce
+        out = torch.relu(act + torch.randn_like(act)).bfloat16()
+    in_aff, xin = None, x.float()
+    if xform:
+        in_aff = torch.zeros(4, C, device=DEV)
+        in_aff[2] = torch.rand(C, device=DEV) + 0.5
+        in_aff[3] = torch.randn(C, device=DEV) * 0.3
+        xin = torch.relu(x.float() * v(in_aff[2]) + v(in_aff[3])).bfloat16().float()
+    ref = torch.nn.functional.conv2d(xin, w, None, 1, k // 2)
+    if with_add:
+        ref = ref + add.float()
+    mask = (out.float() > 0) if with_out else ((act > 0) if relu else torch.ones_like(act, dtype=torch.bool))
+    g_ref = ref * mask
+    xh = (z.float() - v(aff[0])) * v(aff[1])
+    sums_ref = torch.cat([g_ref.sum(dim=(0, 2, 3)), (g_ref * xh).sum(dim=(0, 2, 3))])
+    packed, _, nt, tdy, tdx, keep = conv._pack([w], [None], [k], [1], C, C, False, x.device)
+    scratch = torch.zeros(2 + 2 * C, device=DEV)
+    g, sums = conv._cf_launch(nchw_from(x), packed, nt, tdy, tdx, C, C, in_aff, xform, None,
+                              add=None if add is None else nchw_from(add),
+                              bnred=(nchw_from(z), None if out is None else nchw_from(out), aff, relu, scratch))
+    torch.cuda.synchronize()
+    assert float(scratch.abs().max()) == 0.0, "the kernel must leave its scratch zeroed"
+    errs = dict(g=rel(g.float(), g_ref), sums=float((sums - sums_ref).abs().max() / sums_ref.abs().max()))
+    report["cf_bnred_%s" % "_".join(map(str, case))] = errs
+    assert errs["g"] < 6e-3, errs
+    assert errs["sums"] < 2e-3, errs        # fp32 atomics over <= 262144 terms of mixed sign
+    # the add-only plain epilogue
+    if with_add:
+        y2, _ = conv._cf_launch(nchw_from(x), packed, nt, tdy, tdx, C, C, in_aff, xform, None, add=nchw_from(add))
+        torch.cuda.synchronize()
+        assert rel(y2.float(), ref) < 6e-3
 
 
 def test_conv_cf_block_through_autograd(P, report):
