@@ -196,7 +196,9 @@ int rss_conv_igemm(const void* x, const void* w_packed, const float* bias /*may 
  *                          (what rss_bn_bwd_apply needs; same accum/ticket contract).
  *      Every input pixel is staged in shared memory once per tile (TMA box of whole zero-padded rows, 128B-swizzled K-major
  *      UMMA layout) and all taps read it at shifted descriptor addresses.  w_packed: bf16 [tap][Cout][Cin] from
- *      rss_conv_pack_weights (transpose=1 pack with Cin/Cout swapped gives the data gradient). ---- */
+ *      rss_conv_pack_weights (transpose=1 pack with Cin/Cout swapped gives the data gradient), or any layout with contiguous
+ *      input channels described by the two strides -- e.g. the per-step channels-last / transposed shadows of
+ *      rss_shadow_cl_refresh / rss_shadow_t_refresh, so no pack kernel runs per call. ---- */
 #define RSS_CF_PLAIN 0
 #define RSS_CF_STATS 1
 #define RSS_CF_BNRED 2
@@ -217,6 +219,7 @@ typedef struct {
 int rss_conv_cf_supported(int B, int H, int W, int Cin, int Cout, int ksize, int mode);
 int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, int H, int W, int Cin, int Cout,
                 int n_taps, const int* taps_dy, const int* taps_dx,
+                int w_row_stride, int w_tap_stride /* elements; weight (tap,co,ci) at co*row + tap*tap_stride + ci; 0,0 = packed */,
                 const float* in_scale /*[Cin] or NULL*/, const float* in_shift, int in_relu,
                 const RssConvCfEpilogue* epilogue /*NULL = plain*/, cudaStream_t stream);
 
@@ -273,6 +276,9 @@ int rss_sgd_step(float* params, float* grads, float* momentum_buf, int64_t n, co
  * Cout over the entries before e, row_start[n_entries] = total (int64, device memory); max_row_floats = max Cin*kh*kw. */
 int rss_shadow_cl_refresh(const float* params, void* shadow_cl, const int64_t* table, const int64_t* row_start,
                           int n_entries, int max_row_floats, cudaStream_t stream);
+/* transposed bf16 copies for the data-gradient operand of rss_conv_cf: weight e = fp32 (Cout,Cin,kh,kw) at params + table[e][0]
+ * -> bf16 [Cin][kh*kw][Cout] at shadow_t + table[e][1]; table[e] = {src offset, dst offset, Cout, Cin, kh*kw} (int64). */
+int rss_shadow_t_refresh(const float* params, void* shadow_t, const int64_t* table, int n_entries, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

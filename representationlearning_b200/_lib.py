@@ -78,8 +78,8 @@ SIGNATURES = {
                                       P, P, POINTER(c_int), POINTER(c_int), POINTER(c_int), P]),
     "rss_conv_igemm": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P]),
     "rss_conv_cf_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
-    "rss_conv_cf": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P, P, c_int,
-                            POINTER(ConvCfEpilogue), P]),
+    "rss_conv_cf": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int, c_int,
+                            P, P, c_int, POINTER(ConvCfEpilogue), P]),
     "rss_conv_wgrad_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "rss_conv_wgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "rss_conv_wgrad_tc_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
@@ -96,6 +96,7 @@ SIGNATURES = {
     "rss_grad_sumsq": (c_int, [P, c_int64, c_float, P, P]),
     "rss_sgd_step": (c_int, [P, P, P, c_int64, P, c_float, c_float, P, c_float, c_float, c_int, P, P]),
     "rss_shadow_cl_refresh": (c_int, [P, P, P, P, c_int, c_int, P]),
+    "rss_shadow_t_refresh": (c_int, [P, P, P, c_int, P]),
 }
 
 _lib = None

@@ -291,7 +291,7 @@ def _cf_ok(x, Cout, k, mode):
     return bool(_lib.load().rss_conv_cf_supported(B, H, W, Cin, Cout, k, int(mode)))
 
 
-def _cf_launch(x, packed, nt, tdy, tdx, Cin, Cout, in_aff, in_relu, stats, add=None, bnred=None):
+def _cf_launch(x, packed, nt, tdy, tdx, Cin, Cout, in_aff, in_relu, stats, add=None, bnred=None, wstrides=(0, 0)):
     """one rss_conv_cf launch -> (y, extra).
     in_aff: (4,Cin) mean/invstd/scale/shift of the BatchNorm whose (+ReLU) output this conv consumes (applied on load) or None
     stats = (gamma, beta, running_mean, running_var, momentum, eps, scratch): statistics epilogue, extra = (4,Cout) affine
@@ -335,9 +335,42 @@ def _cf_launch(x, packed, nt, tdy, tdx, Cin, Cout, in_aff, in_relu, stats, add=N
     if in_aff is not None:
         isc, ish = in_aff[2].data_ptr(), in_aff[3].data_ptr()
     with ops.timed("rss_conv_cf"):
-        ops.check(lib.rss_conv_cf(x.data_ptr(), packed.data_ptr(), y.data_ptr(), B, H, W, Cin, Cout, nt, tdy, tdx, isc, ish,
+        ops.check(lib.rss_conv_cf(x.data_ptr(), packed.data_ptr(), y.data_ptr(), B, H, W, Cin, Cout, nt, tdy, tdx,
+                                  int(wstrides[0]), int(wstrides[1]), isc, ish,
                                   int(in_relu), None if ep is None else ctypes.byref(ep), ops._st()), "rss_conv_cf")
     return y, extra
+
+
+CF_SQUARE_3X3 = (32, 64)         # channel counts of the C -> C 3x3 layers conv_cf.cu instantiates with all three epilogues
+_TAPS3 = {}
+
+
+def _taps3(sign):
+    """ctypes (dy[], dx[]) of the 3x3 taps in natural order t = ky*3 + kx; sign = -1: the data-gradient offsets"""
+    if sign not in _TAPS3:
+        _TAPS3[sign] = ((ctypes.c_int * 9)(*[sign * (t // 3 - 1) for t in range(9)]), (ctypes.c_int * 9)(*[sign * (t % 3 - 1) for t in range(9)]))
+    return _TAPS3[sign]
+
+
+def cf_weight(weight, transpose):
+    """weight operand of rss_conv_cf for a (C,C,3,3) parameter -> (tensor, n_taps, dy[], dx[], (row_stride, tap_stride), keepalive).
+    With trainer.FlatSGD the per-step shadows are used in place (channels-last copy for the forward operand, transposed copy for
+    the data gradient); otherwise the weight is packed on the fly."""
+    Cout, Cin, k, _ = weight.shape
+    if k == 3:
+        if not transpose:
+            s = getattr(weight, "_rss_shadow_cl", None)
+            if s is not None and s.dtype == torch.bfloat16:       # memory [Cout][tap][Cin]
+                return s, 9, *_taps3(1), (9 * Cin, Cin), None
+        else:
+            s = getattr(weight, "_rss_shadow_t", None)
+            if s is not None:                                     # memory [Cin][tap][Cout]: N = Cin rows, K = Cout contiguous
+                return s, 9, *_taps3(-1), (9 * Cout, Cout), None
+    if transpose:
+        packed, _, nt, tdy, tdx, keep = _pack([weight], [None], [k], [1], Cout, Cin, True, weight.device)
+    else:
+        packed, _, nt, tdy, tdx, keep = _pack([weight], [None], [k], [1], Cout, Cin, False, weight.device)
+    return packed, nt, tdy, tdx, (0, 0), keep
 
 
 class _ConvCF(torch.autograd.Function):

@@ -256,9 +256,27 @@ __global__ void shadow_cl_kernel(const float* __restrict__ p, __nv_bfloat16* __r
     }
 }
 
+// transposed copies for the data-gradient operand of the fused conv: out[(ci*kk + t)*Cout + co] = w[(co*Cin + ci)*kk + t]
+__global__ void shadow_t_kernel(const float* __restrict__ p, __nv_bfloat16* __restrict__ out, const int64_t* __restrict__ table) {
+    const int64_t* e = table + (int64_t)blockIdx.y * 5;
+    const int cout = (int)e[2], cin = (int)e[3], kk = (int)e[4], n = cout * cin * kk;
+    const float* src = p + e[0];
+    __nv_bfloat16* dst = out + e[1];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int co = j % cout, r = j / cout, t = r % kk, ci = r / kk;
+        dst[j] = __float2bfloat16_rn(src[((int64_t)co * cin + ci) * kk + t]);
+    }
+}
+
 }  // namespace rss
 
 using namespace rss;
+
+extern "C" int rss_shadow_t_refresh(const float* params, void* shadow_t, const int64_t* table, int n_entries, cudaStream_t st) {
+    if (n_entries <= 0 || n_entries > 65535) return RSS_ERR_SHAPE;
+    shadow_t_kernel<<<dim3(8, n_entries), 256, 0, st>>>(params, (__nv_bfloat16*)shadow_t, table);
+    return check_launch();
+}
 
 extern "C" int rss_shadow_cl_refresh(const float* params, void* shadow_cl, const int64_t* table, const int64_t* row_start,
                                      int n_entries, int max_row_floats, cudaStream_t st) {

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib, ops
+from . import _lib, conv as convmod, ops
 from .conv import conv2d, conv_bn_stats
 from .modules import FusedBNAct, GeneralTransformerBlock, BN_MOMENTUM
 
@@ -56,6 +56,99 @@ def _run(conv, bn, x, residual=None):
     return bn(y, residual, aff=aff)
 
 
+# RSS_BLOCK_FUSED (default on): stride-1 BasicBlocks without downsample whose geometry csrc/conv_cf.cu instantiates (C -> C 3x3, C in
+# RSS_BLOCK_FUSED_C, default 32 = HRNet branch 0, the critical stream) run as ONE autograd node built from the fused tcgen05 conv:
+#   forward   conv1 (+ bn1 statistics in the epilogue) -> bn1+ReLU -> conv2 (+ bn2 statistics) -> bn2 + residual + ReLU
+#   backward  bn2 backward (reduce, apply) -> conv2 data gradient whose epilogue masks with bn1's ReLU and reduces bn1's backward sums
+#             -> bn1 backward apply -> conv1 data gradient whose epilogue adds the residual-path gradient; weight gradients on the
+#             side streams.  7 chain kernels -> 5, no library conv, no autograd accumulation kernel.
+BLOCK_FUSED = {"on": os.environ.get("RSS_BLOCK_FUSED", "1") != "0",
+               "channels": tuple(int(c) for c in os.environ.get("RSS_BLOCK_FUSED_C", "32").split(",") if c)}
+
+
+class _BasicBlockFn(torch.autograd.Function):
+    """relu(bn2(conv2(relu(bn1(conv1(x))))) + x) for a training-mode block owned by trainer.FlatSGD (parameter gradients are
+    accumulated straight into the flat gradient buffer, so the parameters are not autograd inputs).  _hrnet_rssformer.py:230-246"""
+
+    @staticmethod
+    def forward(ctx, x, blk):
+        lib = _lib.load()
+        x = ops.nhwc(x)
+        B, C, H, W = x.shape
+        rows, dt, st = B * H * W, _lib.RSS_BF16, ops._st()
+        w1, n1, dy1, dx1, ws1, k1 = convmod.cf_weight(blk.conv1.weight, False)
+        z1, aff1 = convmod._cf_launch(x, w1, n1, dy1, dx1, C, C, None, False, blk.bn1.stats_args(), wstrides=ws1)
+        a1 = torch.empty_like(x, memory_format=ops.CL)
+        ops.check(lib.rss_bn_act_fwd(z1.data_ptr(), None, a1.data_ptr(), aff1[2].data_ptr(), aff1[3].data_ptr(), rows, C, _lib.ACT_RELU,
+                                     dt, st), "rss_bn_act_fwd")
+        w2, n2, dy2, dx2, ws2, k2 = convmod.cf_weight(blk.conv2.weight, False)
+        z2, aff2 = convmod._cf_launch(a1, w2, n2, dy2, dx2, C, C, None, False, blk.bn2.stats_args(), wstrides=ws2)
+        out = torch.empty_like(x, memory_format=ops.CL)
+        ops.check(lib.rss_bn_act_fwd(z2.data_ptr(), x.data_ptr(), out.data_ptr(), aff2[2].data_ptr(), aff2[3].data_ptr(), rows, C,
+                                     _lib.ACT_RELU, dt, st), "rss_bn_act_fwd")
+        if not FusedBNAct.defer_counter:
+            blk.bn1.num_batches_tracked += 1
+            blk.bn2.num_batches_tracked += 1
+        ctx.save_for_backward(x, z1, a1, z2, out, aff1, aff2)
+        ctx.blk = blk
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x, z1, a1, z2, out, aff1, aff2 = ctx.saved_tensors
+        blk = ctx.blk
+        dout = ops.nhwc(dout)
+        if dout.dtype != x.dtype:
+            dout = dout.to(x.dtype)
+        B, C, H, W = x.shape
+        rows, dt, st = B * H * W, _lib.RSS_BF16, ops._st()
+        p = ops._p
+        relu = _lib.ACT_RELU
+        # bn2 backward (residual layer: the ReLU mask comes from the stored block output)
+        sc2 = blk.bn2._scratch
+        sums2 = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+        ops.check(lib.rss_bn_bwd_reduce_ws(p(z2), p(out), p(dout), p(aff2[2]), p(aff2[3]), p(aff2[0]), p(aff2[1]), p(sums2), p(sc2[2:]),
+                                           p(sc2), None, rows, C, relu, dt, st), "rss_bn_bwd_reduce")
+        dz2 = torch.empty_like(x, memory_format=ops.CL)
+        dres = torch.empty_like(x, memory_format=ops.CL)
+        ops.check(lib.rss_bn_bwd_apply(p(z2), p(out), p(dout), p(aff2[2]), p(aff2[3]), p(aff2[0]), p(aff2[1]), p(sums2), 1.0 / rows,
+                                       p(dz2), p(dres), rows, C, relu, dt, p(sums2), p(blk.bn2.weight.grad), p(blk.bn2.bias.grad), st),
+                  "rss_bn_bwd_apply")
+        convmod._wgrad(dz2, a1, a1, blk.conv2.weight, None, False, 1, 1, 1, blk.conv2.weight.dtype)
+        # conv2 data gradient; its epilogue applies bn1's ReLU mask and reduces bn1's backward sums
+        w2, n2, dy2, dx2, ws2, k2 = convmod.cf_weight(blk.conv2.weight, True)
+        g1, sums1 = convmod._cf_launch(dz2, w2, n2, dy2, dx2, C, C, None, False, None, bnred=(z1, None, aff1, True, blk.bn1._scratch),
+                                       wstrides=ws2)
+        dz1 = torch.empty_like(x, memory_format=ops.CL)
+        ops.check(lib.rss_bn_bwd_apply(p(z1), None, p(g1), p(aff1[2]), p(aff1[3]), p(aff1[0]), p(aff1[1]), p(sums1), 1.0 / rows,
+                                       p(dz1), None, rows, C, relu, dt, p(sums1), p(blk.bn1.weight.grad), p(blk.bn1.bias.grad), st),
+                  "rss_bn_bwd_apply")
+        convmod._wgrad(dz1, x, x, blk.conv1.weight, None, False, 1, 1, 1, blk.conv1.weight.dtype)
+        # conv1 data gradient + the residual-path gradient in the epilogue
+        w1, n1, dy1, dx1, ws1, k1 = convmod.cf_weight(blk.conv1.weight, True)
+        dx, _ = convmod._cf_launch(dz1, w1, n1, dy1, dx1, C, C, None, False, None, add=dres, wstrides=ws1)
+        return dx, None
+
+
+def _block_fused_ok(blk, x):
+    if not (BLOCK_FUSED["on"] and blk.training and blk.downsample is None and blk.stride == 1 and x.is_cuda
+            and x.dtype == torch.bfloat16 and torch.is_grad_enabled() and x.requires_grad):
+        return False
+    C = x.shape[1]
+    if C not in BLOCK_FUSED["channels"] or C not in convmod.CF_SQUARE_3X3:
+        return False
+    for bn in (blk.bn1, blk.bn2):
+        if not bn.training or bn.stats_args() is None:
+            return False
+    for prm in (blk.conv1.weight, blk.conv2.weight, blk.bn1.weight, blk.bn1.bias, blk.bn2.weight, blk.bn2.bias):
+        if not getattr(prm, "_rss_flat", False) or ops.grad_sink(prm) is None:      # direct accumulation needs trainer.FlatSGD
+            return False
+    B, _, H, W = x.shape
+    lib = _lib.load()
+    return bool(lib.rss_conv_cf_supported(B, H, W, C, C, 3, _lib.CF_STATS)) and bool(lib.rss_conv_cf_supported(B, H, W, C, C, 3, _lib.CF_BNRED))
+
+
 class BasicBlock(nn.Module):
     """_hrnet_rssformer.py:216-246"""
     expansion = 1
@@ -70,6 +163,8 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
+        if _block_fused_ok(self, x):
+            return _BasicBlockFn.apply(x, self)
         residual = x if self.downsample is None else _run(self.downsample[0], self.downsample[1], x)
         out = _run(self.conv1, self.bn1, x)
         return _run(self.conv2, self.bn2, out, residual)

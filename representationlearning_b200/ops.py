@@ -20,7 +20,7 @@ KERNELS_PER_CALL = {
     "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1, "rss_bn_fwd_fused": 1, "rss_bn_bwd_fused": 1,
     "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 4, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
     "rss_headaux_fwd": 2, "rss_seg_loss_fwd": 2, "rss_seg_loss_bwd": 1, "rss_grad_sumsq": 1, "rss_sgd_step": 1,
-    "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_conv_wgrad": 1, "rss_conv_wgrad_tc": 1, "rss_conv_cf": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
+    "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_conv_wgrad": 1, "rss_conv_wgrad_tc": 1, "rss_conv_cf": 1, "rss_shadow_t_refresh": 1, "rss_shadow_cl_refresh": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
 }
 COUNTERS = {"launches": 0, "calls": 0}
 TIMED = {}            # op name -> list of (start_event, end_event), filled only while bench.py enables it
@@ -558,3 +558,7 @@ def sgd_step(flat_p, flat_g, flat_m, sumsq, grad_scale, max_norm, lr_dev, moment
 def shadow_cl_refresh(flat_p, shadow_cl, table, row_start, n_entries, max_row_floats):
     check(_lib.load().rss_shadow_cl_refresh(_p(flat_p), _p(shadow_cl), _p(table), _p(row_start), n_entries, max_row_floats, _st()),
           "rss_shadow_cl_refresh")
+
+
+def shadow_t_refresh(flat_p, shadow_t, table, n_entries):
+    check(_lib.load().rss_shadow_t_refresh(_p(flat_p), _p(shadow_t), _p(table), n_entries, _st()), "rss_shadow_t_refresh")

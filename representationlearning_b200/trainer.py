@@ -58,6 +58,7 @@ class FlatSGD:
         if self.shadow is not None:
             self.shadow.copy_(self.flat_p)
         self._build_cl_shadow(dev)
+        self._build_t_shadow(dev)
         self.iteration = 0
         from .modules import FusedBNAct
         self._bn_counters = [m.num_batches_tracked for m in model.modules() if isinstance(m, FusedBNAct)]
@@ -91,12 +92,39 @@ class FlatSGD:
             conv.register_shadow_cl(p, self.shadow_cl[o:o + p.numel()].view(shp).permute(0, 3, 1, 2))
         self.refresh_cl_shadow()
 
+    def _build_t_shadow(self, dev):
+        """transposed bf16 copies ([Cin][kh*kw][Cout]) of the 3x3 weights the fused conv (csrc/conv_cf.cu) differentiates: the
+        data-gradient operand, refreshed by ONE kernel per step (rss_shadow_t_refresh) instead of a pack kernel per call"""
+        self.shadow_t = None
+        if self.shadow is None or dev.type != "cuda":
+            return
+        table, views, total = [], [], 0
+        for p, o in zip(self.params, self.offsets):
+            if p.dim() != 4 or tuple(p.shape[2:]) != (3, 3) or p.shape[0] != p.shape[1] or p.shape[0] not in conv.CF_SQUARE_3X3:
+                continue
+            cout, cin, kh, kw = p.shape
+            table.append([o, total, cout, cin, kh * kw])
+            views.append((p, total))
+            total += p.numel()
+        if not table:
+            return
+        self.shadow_t = torch.zeros(total, device=dev, dtype=torch.bfloat16)
+        self._t_table = torch.tensor(table, dtype=torch.int64).to(dev)
+        for p, o in views:
+            p._rss_shadow_t = self.shadow_t[o:o + p.numel()]
+        self.refresh_t_shadow()
+
+    def refresh_t_shadow(self):
+        if self.shadow_t is not None:
+            ops.shadow_t_refresh(self.flat_p, self.shadow_t, self._t_table, self._t_table.shape[0])
+
     def sync_shadows(self):
         """call after writing parameters from outside the optimiser (e.g. load_state_dict on resume): refreshes the bf16 copies
         the convolution kernels read"""
         if self.shadow is not None:
             self.shadow.copy_(self.flat_p)
         self.refresh_cl_shadow()
+        self.refresh_t_shadow()
 
     def refresh_cl_shadow(self):
         if self.shadow_cl is not None:
@@ -133,6 +161,7 @@ class FlatSGD:
         ops.sgd_step(self.flat_p, self.flat_g, self.flat_m, self.sumsq, grad_scale, hp["max_norm"], self.lr_dev, hp["momentum"],
                      hp["weight_decay"], True, self.shadow)
         self.refresh_cl_shadow()
+        self.refresh_t_shadow()
         if self._bn_counters and self.model.training:
             torch._foreach_add_(self._bn_counters, 1)       # num_batches_tracked of all 330 BN layers in one multi-tensor op
 

@@ -578,7 +578,7 @@ CF_CASES = [
     (2, 19, 23, 32, 32, 3, True, True),        # ragged: tiles straddle rows, last tile partial
     (1, 128, 128, 32, 32, 3, True, False),     # branch-0 geometry: two 128-row blocks per tile
     (3, 64, 64, 64, 64, 3, True, True),        # branch-1 geometry
-    (2, 20, 128, 64, 64, 3, True, False),      # layer1 geometry (wide, 64 channels)
+    (2, 20, 72, 64, 64, 3, True, False),       # 64 channels, rows wider than one 128-position block
     (2, 24, 24, 64, 32, 1, True, False),       # 1x1 (fuse layers)
     (2, 12, 20, 128, 32, 1, True, True),
     (2, 16, 16, 32, 128, 1, False, False),     # FFN fc1 geometry (wide N, no statistics)
@@ -704,6 +704,56 @@ def test_conv_cf_bn_backward_epilogue(P, report, case):
         y2, _ = conv._cf_launch(nchw_from(x), packed, nt, tdy, tdx, C, C, in_aff, xform, None, add=nchw_from(add))
         torch.cuda.synchronize()
         assert rel(y2.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 24, 40), (16, 32, 128, 128), (3, 64, 32, 32)])
+def test_fused_basic_block_vs_unfused(P, report, shape):
+    """hrnet._BasicBlockFn (fused tcgen05 convs with statistics / BN-backward epilogues, residual gradient added in the last
+    epilogue, weight shadows read in place) against the same block run layer by layer through the library conv + BN kernels:
+    output, input gradient and all six parameter gradients.  _hrnet_rssformer.py:230-246"""
+    from representationlearning_b200 import hrnet, trainer
+    B, C, H, W = shape
+    torch.manual_seed(21)
+    x = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    dout = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    res = {}
+    saved = dict(hrnet.BLOCK_FUSED)
+    try:
+        for mode in ("fused", "unfused"):
+            torch.manual_seed(5)
+            blk = hrnet.BasicBlock(C, C).to(DEV).train()
+            with torch.no_grad():
+                for bn in (blk.bn1, blk.bn2):
+                    bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.3)
+            opt = trainer.FlatSGD(blk)
+            hrnet.BLOCK_FUSED.update(on=(mode == "fused"), channels=(32, 64))
+            xi = nchw_from(x).requires_grad_(True)
+            assert hrnet._block_fused_ok(blk, xi) == (mode == "fused")
+            out = blk(xi)
+            out.backward(nchw_from(dout))
+            from representationlearning_b200 import conv
+            conv.join_wgrad()
+            torch.cuda.synchronize()
+            res[mode] = dict(out=out.float(), dx=xi.grad.float(), rm1=blk.bn1.running_mean.clone(), rv2=blk.bn2.running_var.clone(),
+                             **{n: p.grad.clone() for n, p in blk.named_parameters()})
+            assert float(blk.bn1._scratch.abs().max()) == 0.0 and float(blk.bn2._scratch.abs().max()) == 0.0
+    finally:
+        hrnet.BLOCK_FUSED.update(saved)
+        P.FusedBNAct.defer_counter = False
+    # The two paths take bn1's statistics from different roundings of z1 (fp32 accumulators vs the stored bf16 tensor), so ~2 % of
+    # a1 differs by one bf16 ulp and a few ReLU masks flip: a flipped element changes a gradient by O(1) locally.  The comparison
+    # is therefore in the L2 norm (a wrong tap, stride or mask rule gives O(1) there) plus the fraction of visibly different elements.
+    def l2(a, b):
+        a, b = a.double(), b.double()
+        return float((a - b).norm() / (b.norm() + 1e-30))
+    errs = {k: l2(res["fused"][k], res["unfused"][k]) for k in res["fused"]}
+    d = (res["fused"]["dx"] - res["unfused"]["dx"]).abs()
+    errs["dx_frac_off"] = float((d > 0.05 * res["unfused"]["dx"].abs().max()).float().mean())
+    errs["out_max"] = rel(res["fused"]["out"], res["unfused"]["out"])
+    report["fused_block_%s" % "_".join(map(str, shape))] = errs
+    assert errs["out_max"] < 2e-2, errs
+    assert errs["dx"] < 5e-2 and errs["dx_frac_off"] < 2e-2, errs
+    assert max(v for k, v in errs.items() if k not in ("out", "dx", "dx_frac_off", "out_max")) < 5e-2, errs
 
 
 def test_conv_cf_block_through_autograd(P, report):
