@@ -126,15 +126,21 @@ def check(rc, what):
 
 
 _device_ok = False
+_device_index = None
 
 
 def require_device():
-    """The product path refuses to run anywhere but on an sm_100 GPU."""
-    global _device_ok
-    if _device_ok:
-        return
+    """The product path refuses to run anywhere but on an sm_100 GPU -- and on ONE GPU per process (the launch model of bench.py /
+    torchrun): the kernels cache per-device launch attributes (opt-in shared memory size, SM count) for the first device used."""
+    global _device_ok, _device_index
     import torch
+    if _device_ok:
+        if torch.cuda.current_device() != _device_index:
+            raise RssError("librss_b200 drives one GPU per process (first used cuda:%d, now cuda:%d): launch one process per GPU"
+                           % (_device_index, torch.cuda.current_device()))
+        return
     if not torch.cuda.is_available():
         raise RssError("no CUDA device: representationlearning_b200 has no CPU fallback")
     check(load().rss_check_device(), "rss_check_device")
+    _device_index = torch.cuda.current_device()
     _device_ok = True

@@ -36,8 +36,9 @@
 
 namespace rss {
 
-// warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 input transform, warps 6-13 epilogue, warp 14 copy warp (bulk stores/loads)
-constexpr int kCfThreads = 480;
+// warp 0 TMA producer, warps 1 and 15 MMA issuers (even / odd 128-row blocks), warps 2-5 input transform, warps 6-13 epilogue,
+// warp 14 copy warp (bulk stores/loads)
+constexpr int kCfThreads = 512;
 constexpr int kCfXfThreads = 128;
 constexpr int kCfEpiThreads = 256;
 constexpr int kCfMaxTaps = 9;
@@ -54,10 +55,16 @@ struct CfGeom {
     int tap_off[kCfMaxTaps];             // dy*Wp + dx (signed)
     int in_relu;
     int w_row_stride, w_tap_stride;      // weight operand: element (tap, n, k) at n*w_row_stride + tap*w_tap_stride + k (k contiguous)
+    unsigned int wp_magic;               // ceil(2^32 / Wp): q / Wp == __umulhi(q, wp_magic) for q < 2^32 / Wp (positions are < 2^17)
+    int dbg;                             // profiling aid (RSS_CF_DBG bits): 1 epilogue does no math / staging stores, 4 no MMAs issued
     int ops_staged;                      // epilogue operands (add / bn_z / bn_out) are staged in shared memory by the copy warp
     long long* trace;                    // profiling aid (RSS_CF_TRACE_PTR): CTA 0 records clock64() per role/tile/event, [4 roles][16 tiles][8]
 };
+#ifdef RSS_CF_TRACE_BUILD
 #define CF_TRACE(role, i, k) do { if (g.trace && blockIdx.x == 0 && (i) < 16) g.trace[((role) * 16 + (i)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define CF_TRACE(role, i, k) do { } while (0)
+#endif
 
 struct CfEpi {
     const __nv_bfloat16* add;            // [B,H,W,Cout] added to the accumulator before anything else (NULL: none)
@@ -121,7 +128,7 @@ __device__ __forceinline__ void cf_bulk_wait_read0() { asm volatile("cp.async.bu
 // Returns the number of live positions of that row segment (0: none); m0 = index of its first position within the block,
 // pix = (b*H + r)*W + c of its first pixel.
 __device__ __forceinline__ int cf_segment(const CfGeom& g, int b, int q0, int lane, int& m0, size_t& pix) {
-    const int r = q0 / g.Wp + lane;
+    const int r = (int)__umulhi((unsigned)q0, g.wp_magic) + lane;
     const int rs = r * g.Wp + g.halo;                   // first interior position of the row
     const int lo = max(q0, rs), hi = min(q0 + 128, rs + g.W);
     if (r >= g.H || hi <= lo) return 0;
@@ -144,15 +151,15 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
     constexpr int NC = COUT / 2;                                      // channels per epilogue thread
     constexpr uint32_t OUT_BYTES = 128u * COUT * 2;                   // one staged 128-position block of bf16 rows
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // barriers: [0,3) landed (TMA bytes), [3,6) ready (transformed), [6,9) empty, [9,13) tmem_full, [13,17) tmem_empty,
-    //           [17,19) out_full, [19,21) out_empty, [21,23) opnd_full
-    __shared__ __align__(8) uint64_t bars[23];
+    // barriers: [0,3) landed (TMA bytes), [3,6) ready (transformed), [6,9) empty, [9,17) tmem_full, [17,25) tmem_empty,
+    //           [25,27) out_full, [27,29) out_empty, [29,31) opnd_full
+    __shared__ __align__(8) uint64_t bars[31];
     __shared__ uint32_t tmem_slot;
     __shared__ bool is_last;
     __shared__ __align__(16) float cst[MODE == kCfBnRed ? 4 * COUT : COUT];   // statistics: K; bn-backward: mean, invstd, scale, shift
     __shared__ float red[MODE == kCfPlain ? 1 : 8 * COUT];                    // [8 warps][2*NC]
-    uint64_t* bar_landed = bars, *bar_ready = bars + 3, *bar_empty = bars + 6, *bar_tfull = bars + 9, *bar_tempty = bars + 13;
-    uint64_t* bar_ofull = bars + 17, *bar_oempty = bars + 19, *bar_pfull = bars + 21;
+    uint64_t* bar_landed = bars, *bar_ready = bars + 3, *bar_empty = bars + 6, *bar_tfull = bars + 9, *bar_tempty = bars + 17;
+    uint64_t* bar_ofull = bars + 25, *bar_oempty = bars + 27, *bar_pfull = bars + 29;
 
     const int S = g.S, MM = g.MM, NACC = 2 * MM;
     const uint32_t stage_bytes = (uint32_t)KC * g.P * ROWB;           // [plane][position row]
@@ -175,9 +182,9 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kCfMaxStages; ++s) {
-            mbar_init(smem_u32(bar_landed + s), 1); mbar_init(smem_u32(bar_ready + s), kCfXfThreads / 32); mbar_init(smem_u32(bar_empty + s), 1);
+            mbar_init(smem_u32(bar_landed + s), 1); mbar_init(smem_u32(bar_ready + s), kCfXfThreads / 32); mbar_init(smem_u32(bar_empty + s), 2);
         }
-        for (int a = 0; a < 4; ++a) { mbar_init(smem_u32(bar_tfull + a), 1); mbar_init(smem_u32(bar_tempty + a), kCfEpiThreads / 32); }
+        for (int a = 0; a < 8; ++a) { mbar_init(smem_u32(bar_tfull + a), 1); mbar_init(smem_u32(bar_tempty + a), kCfEpiThreads / 32); }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(bar_ofull + a), kCfEpiThreads / 32); mbar_init(smem_u32(bar_oempty + a), 1); mbar_init(smem_u32(bar_pfull + a), 1);
         }
@@ -224,8 +231,12 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                 if (++si == S) { si = 0; ++use; }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =================
+    } else if (warp == 1 || warp == 15) {
+        // ================= MMA issuers: warp 1 issues the even 128-row blocks of every tile, warp 15 the odd ones.  One warp cannot
+        // keep the tensor pipe fed: it sits in back-pressure while its MMAs execute (32 cycles each: the 4 KB A operand at 128 B/clk)
+        // and only then does the bookkeeping of the next block (~450 cycles of barrier polls and descriptor arithmetic per block).
+        // The whole warp runs the (warp-uniform) loop, one elected lane issues. =================
+        const int who = warp == 1 ? 0 : 1;
         constexpr uint32_t idesc = cf_idesc(COUT);
         uint64_t* bar_in = xform ? bar_ready : bar_landed;
         constexpr uint64_t desc_hi = cf_desc_hi(ROWB);
@@ -233,45 +244,52 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
         const uint32_t leader = elect_one();
         const uint32_t w_lo = w_s >> 4;
         const int plane_a = g.P * RU;
+        const bool no_mma = (g.dbg & 4) != 0;
         int toff[NTAPS];
 #pragma unroll
         for (int t = 0; t < NTAPS; ++t) toff[t] = g.tap_off[t] * RU;
-        int si = 0, acc = 0, ti = 0;
-        uint32_t in_phase = 0, acc_phase = 0;
+        int si = 0, ti = 0;
+        uint32_t in_phase = 0;
+        // accumulator of block mm of the tile: (tile parity)*MM + mm; its phase flips every second tile
+        int tpar = 0;
+        uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++ti) {
-            const int t = tile % g.tiles_per_img;
-            const int q0 = t * g.MT;
+            const int b_ = tile / g.tiles_per_img;
+            const int q0 = (tile - b_ * g.tiles_per_img) * g.MT;
             const int pbase = q0 - cf_row_lo(q0, g.halo, g.Wp) * g.Wp;  // staged index of output position q0
             // descriptors differ only in their 14-bit start-address field (address >> 4): a K=16 step of 32 B = 2 units
             const int a_lo0 = (int)((a_s + si * stage_bytes) >> 4) + pbase * RU;
-            if (lane == 0) CF_TRACE(1, ti, 0);
+            if (lane == 0 && who == 0) CF_TRACE(1, ti, 0);
             mbar_wait(smem_u32(bar_in + si), in_phase);                // tile staged (and transformed)
-            if (lane == 0) CF_TRACE(1, ti, 1);
+            if (lane == 0 && who == 0) CF_TRACE(1, ti, 1);
             tc_fence_after();
-            for (int mm = 0; mm < MM; ++mm) {
+            for (int mm = who; mm < MM; mm += 2) {
+                const int acc = tpar * MM + mm;
                 mbar_wait(smem_u32(bar_tempty + acc), acc_phase ^ 1);  // epilogue drained this accumulator
-                if (lane == 0) CF_TRACE(1, ti, 2 + 2 * mm);
+                if (lane == 0 && mm < 2) CF_TRACE(1, ti, 2 + 2 * mm);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_u + acc * COUT;
                 const int a_lo1 = a_lo0 + mm * 128 * RU;
+                if (!no_mma) {
 #pragma unroll
-                for (int tp = 0; tp < NTAPS; ++tp) {
+                    for (int tp = 0; tp < NTAPS; ++tp) {
 #pragma unroll
-                    for (int pl = 0; pl < KC; ++pl) {
+                        for (int pl = 0; pl < KC; ++pl) {
 #pragma unroll
-                        for (int kk = 0; kk < KPP; ++kk) {
-                            const uint32_t a = (uint32_t)(a_lo1 + toff[tp] + pl * plane_a + kk * 2);
-                            const uint32_t b = w_lo + (uint32_t)((tp * KC + pl) * COUT * RU + kk * 2);
-                            umma_bf16_elect(leader, d_tmem, desc_hi | (uint64_t)a, desc_hi | (uint64_t)b, idesc, (tp | pl | kk) ? 1u : 0u);
+                            for (int kk = 0; kk < KPP; ++kk) {
+                                const uint32_t a = (uint32_t)(a_lo1 + toff[tp] + pl * plane_a + kk * 2);
+                                const uint32_t b = w_lo + (uint32_t)((tp * KC + pl) * COUT * RU + kk * 2);
+                                umma_bf16_elect(leader, d_tmem, desc_hi | (uint64_t)a, desc_hi | (uint64_t)b, idesc, (tp | pl | kk) ? 1u : 0u);
+                            }
                         }
                     }
                 }
                 umma_commit_elect(leader, smem_u32(bar_tfull + acc));  // accumulator complete -> epilogue
-                if (lane == 0) CF_TRACE(1, ti, 3 + 2 * mm);
-                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+                if (lane == 0 && mm < 2) CF_TRACE(1, ti, 3 + 2 * mm);
             }
-            umma_commit_elect(leader, smem_u32(bar_empty + si));        // stage free once these MMAs retire
+            umma_commit_elect(leader, smem_u32(bar_empty + si));        // stage free once both issuers' MMAs on it retire
             if (++si == S) { si = 0; in_phase ^= 1; }
+            if (++tpar == 2) { tpar = 0; acc_phase ^= 1; }
         }
     } else if (warp < 6) {
         // ================= transform warps: previous layer's BN(+ReLU) applied in place on the landed tile =================
@@ -337,18 +355,20 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
         for (int i = 0; i < NS; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
         const bool bn_relu = MODE == kCfBnRed && ep.bn_relu != 0;
         const uint32_t row_off = (uint32_t)m * COUT * 2 + (uint32_t)ch0 * 2;      // this thread's bytes within a staged block
-        int acc = 0, ti = 0, kb = 0;
+        int ti = 0, kb = 0, tpar = 0;
         uint32_t acc_phase = 0;
         const bool tracer = threadIdx.x == 192;
+        const bool no_epi = (g.dbg & 1) != 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++ti) {
             const int b = tile / g.tiles_per_img, t = tile - b * g.tiles_per_img;
             for (int mm = 0; mm < MM; ++mm, ++kb) {
-                if (tracer) CF_TRACE(3, ti, 4 * mm);
+                if (tracer && mm < 2) CF_TRACE(3, ti, 4 * mm);
                 const int ob = kb & 1;
                 const uint32_t ph = (uint32_t)(kb >> 1) & 1;
+                const int acc = tpar * MM + mm;
                 const int q = t * g.MT + mm * 128 + m;
-                const int r = q / g.Wp, c = q - r * g.Wp - g.halo;
-                const bool live = q < g.Q && c >= 0 && c < g.W;
+                const int r = (int)__umulhi((unsigned)q, g.wp_magic), c = q - r * g.Wp - g.halo;
+                const bool live = q < g.Q && c >= 0 && c < g.W && !no_epi;
                 uint4 av[NC / 8], zv[NC / 8], ov[NC / 8];
                 if (!staged && n_ops > 0 && live) {            // direct (strided) operand loads: in flight while the MMAs finish
                     const size_t off = (((size_t)b * g.H + r) * g.W + c) * COUT + ch0;
@@ -366,7 +386,7 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                     }
                 }
                 mbar_wait(smem_u32(bar_tfull + acc), acc_phase);
-                if (tracer) CF_TRACE(3, ti, 4 * mm + 1);
+                if (tracer && mm < 2) CF_TRACE(3, ti, 4 * mm + 1);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * COUT + ch0;
                 uint32_t rr[NC];
@@ -376,7 +396,6 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(bar_tempty + acc));      // the accumulator is in registers: hand TMEM back
-                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
                 if (staged) {                                  // operand rows brought in by the copy warp
                     mbar_wait(smem_u32(bar_pfull + ob), ph);
                     const uint8_t* pb = smem + (p_s - w_s) + (size_t)ob * OUT_BYTES + row_off;
@@ -393,7 +412,7 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                         }
                     }
                 }
-                if (tracer) CF_TRACE(3, ti, 4 * mm + 2);
+                if (tracer && mm < 2) CF_TRACE(3, ti, 4 * mm + 2);
                 uint4 pk[NC / 8];
                 const float livef = live ? 1.f : 0.f;          // everything below is branch-free (per-element branches diverge)
 #pragma unroll
@@ -444,15 +463,40 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(bar_ofull + ob));
-                if (tracer) CF_TRACE(3, ti, 4 * mm + 3);
+                if (tracer && mm < 2) CF_TRACE(3, ti, 4 * mm + 3);
             }
+            if (++tpar == 2) { tpar = 0; acc_phase ^= 1; }
         }
         if (MODE != kCfPlain) {
-            // per-channel totals: warp shuffle tree -> 8 warp partials in smem -> one atomicAdd per channel per CTA
+            // per-channel totals: recursive-halving butterfly (NS-1 shuffles per array instead of 5*NS: after the step with offset o
+            // a lane keeps the half of its values selected by its lane bit o) -> 8 warp partials in smem -> one atomicAdd per
+            // channel per CTA.  Lane l ends up with the warp total of value index bitrev-free: idx = sum of kept halves.
+            {
+                int idx = 0;                                   // value index this lane ends up owning
+                int n = NS;
 #pragma unroll
-            for (int i = 0; i < NS; ++i) {
-                const float a = warp_sum(s1[i]), b2 = warp_sum(s2[i]);
-                if (lane == 0) { red[ew * 2 * NC + i] = a; red[ew * 2 * NC + NC + i] = b2; }
+                for (int o = 16; o >= 1; o >>= 1) {
+                    if (n > 1) {
+                        n >>= 1;
+                        const bool up = (lane & o) != 0;       // upper lanes keep the upper half of the remaining values
+#pragma unroll
+                        for (int i = 0; i < NS / 2; ++i) {
+                            if (i < n) {
+                                const float keep1 = up ? s1[n + i] : s1[i], send1 = up ? s1[i] : s1[n + i];
+                                const float keep2 = up ? s2[n + i] : s2[i], send2 = up ? s2[i] : s2[n + i];
+                                s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, o);
+                                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, o);
+                            }
+                        }
+                        if (up) idx += n;
+                    } else {                                   // one value left: plain butterfly over the remaining lane bits
+                        s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], o);
+                        s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], o);
+                    }
+                }
+                // lanes that differ only in the bits consumed by the plain butterfly hold the same total: one of them writes
+                constexpr int LANES_PER_VAL = 32 / (NS < 32 ? NS : 32);
+                if ((lane & (LANES_PER_VAL - 1)) == 0) { red[ew * 2 * NC + idx] = s1[0]; red[ew * 2 * NC + NC + idx] = s2[0]; }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int et = threadIdx.x - 192;                  // 0..255 within the epilogue group
@@ -561,6 +605,8 @@ static int cf_plan(int B, int H, int W, int Cin, int Cout, int n_taps, const int
     }
     if (halo > 1) return RSS_ERR_SHAPE;
     g.halo = halo; g.Wp = W + 2 * halo; g.Q = H * g.Wp;
+    g.wp_magic = (unsigned int)((0x100000000ull + (unsigned)g.Wp - 1) / (unsigned)g.Wp);
+    g.dbg = 0;
     if (g.Wp > 256 || g.Wp < 8) return RSS_ERR_SHAPE;                         // TMA box dimension limit; <= 32 row segments per block
     for (int t = 0; t < kCfMaxTaps; ++t) g.tap_off[t] = t < n_taps ? dy[t] * g.Wp + dx[t] : 0;
     const int KC = (Cin + 63) / 64, rowb = Cin == 32 ? 64 : 128;
@@ -570,10 +616,11 @@ static int cf_plan(int B, int H, int W, int Cin, int Cout, int n_taps, const int
     // two 128-row blocks per tile halve the halo over-fetch; needs 4 accumulators in TMEM and a tile count that still fills the GPU.
     // Preference: staged epilogue operands > two blocks per tile > three ring stages.
     for (int staged = n_ops > 0 ? 1 : 0; staged >= 0; --staged) {
-        for (int mm = (4 * Cout <= 512) ? 2 : 1; mm >= 1; --mm) {
+        for (int mm = 4; mm >= 1; mm >>= 1) {
+            if (2 * mm * Cout > 512) continue;                                // 2*mm accumulators of Cout TMEM columns
             g.MM = mm; g.MT = 128 * mm;
             g.tiles_per_img = (g.Q + g.MT - 1) / g.MT;
-            if (mm == 2 && (int64_t)B * g.tiles_per_img < 2 * num_sms()) continue;
+            if (mm > 1 && (int64_t)B * g.tiles_per_img < 2 * num_sms()) continue;
             const int L = g.MT + 2 * halo;                                    // padded-linear span a tile reads within its own rows
             g.NR = (L + g.Wp - 2) / g.Wp + 1 + 2 * halo;                      // rows that span can touch, + halo rows above and below
             if (g.NR > 256) continue;
@@ -676,6 +723,8 @@ extern "C" int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, 
     if ((w_row_stride & 7) || (w_tap_stride & 7)) return RSS_ERR_SHAPE;                                // 16-byte chunks
     pl.g.w_row_stride = w_row_stride; pl.g.w_tap_stride = w_tap_stride;
     {
+        const char* dbg = getenv("RSS_CF_DBG");
+        pl.g.dbg = dbg ? atoi(dbg) : 0;
         const char* tr = getenv("RSS_CF_TRACE_PTR");
         pl.g.trace = tr ? (long long*)strtoull(tr, nullptr, 16) : nullptr;
     }

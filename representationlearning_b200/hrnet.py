@@ -86,9 +86,9 @@ class _BasicBlockFn(torch.autograd.Function):
         out = torch.empty_like(x, memory_format=ops.CL)
         ops.check(lib.rss_bn_act_fwd(z2.data_ptr(), x.data_ptr(), out.data_ptr(), aff2[2].data_ptr(), aff2[3].data_ptr(), rows, C,
                                      _lib.ACT_RELU, dt, st), "rss_bn_act_fwd")
-        if not FusedBNAct.defer_counter:
-            blk.bn1.num_batches_tracked += 1
-            blk.bn2.num_batches_tracked += 1
+        for bn in (blk.bn1, blk.bn2):
+            if not bn.defer_counter:
+                bn.num_batches_tracked += 1
         ctx.save_for_backward(x, z1, a1, z2, out, aff1, aff2)
         ctx.blk = blk
         return out

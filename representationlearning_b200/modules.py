@@ -36,12 +36,12 @@ class FusedBNAct(nn.Module):
         # One per layer: layers may run concurrently on different streams.  Not part of the state_dict.
         self.register_buffer("_scratch", torch.zeros(2 + 2 * num_features), persistent=False)
 
-    defer_counter = False      # trainer.FlatSGD bumps every num_batches_tracked with one foreach op per step instead
+    defer_counter = False      # set per INSTANCE by trainer.FlatSGD, which bumps the counters of the modules it owns with one foreach op per step
 
     def forward(self, x, residual=None, pre_bias=None, aff=None):
         """pre_bias (training mode only): bias of the conv that produced x, left out of x because BatchNorm cancels it.
         aff: statistics already produced by the conv kernel's epilogue (conv.conv_bn_stats)."""
-        if self.training and not FusedBNAct.defer_counter:
+        if self.training and not self.defer_counter:
             self.num_batches_tracked += 1
         return ops.BNAct.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
                                self.training, self.momentum, self.eps, self.act, True if self.sync else None, self._scratch,

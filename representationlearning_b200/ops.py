@@ -82,8 +82,10 @@ def nhwc(t):
 
 def grad_sink(p):
     """fp32 gradient buffer of a parameter that kernels may accumulate into directly (bypassing one AccumulateGrad
-    add kernel per parameter per step: ~1.4 k launches).  None -> return the gradient through autograd as usual."""
-    if p is None or not isinstance(p, torch.nn.Parameter):
+    add kernel per parameter per step: ~1.4 k launches).  None -> return the gradient through autograd as usual.
+    Only parameters owned by trainer.FlatSGD take the direct path: for anyone else (a plain torch optimiser, DDP's reducer
+    hooks, gradient accumulation with zero_grad(set_to_none=False)) AccumulateGrad and its hooks must run."""
+    if p is None or not isinstance(p, torch.nn.Parameter) or not getattr(p, "_rss_flat", False):
         return None
     g = p.grad
     if g is None or g.dtype != torch.float32 or not g.is_contiguous():

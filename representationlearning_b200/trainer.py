@@ -46,7 +46,10 @@ class FlatSGD:
         self.shadow = torch.zeros(total, device=dev, dtype=torch.bfloat16) if bf16_shadow else None
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.lr_dev = torch.zeros(1, device=dev, dtype=torch.float32)     # poly LR lives on the device (graph-replay safe)
-        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(1)
+        # ring of pinned slots: with graph replay the host runs ahead of the device, so a slot must not be rewritten before the
+        # copy that reads it has executed (8 steps of run-ahead are far more than the launch queue allows)
+        self._lr_host = torch.zeros(8, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(8)
+        self._lr_slot = 0
         for p, o in zip(self.params, offs):
             n = p.numel()
             self.flat_p[o:o + n].copy_(p.data.reshape(-1))
@@ -61,8 +64,29 @@ class FlatSGD:
         self._build_t_shadow(dev)
         self.iteration = 0
         from .modules import FusedBNAct
-        self._bn_counters = [m.num_batches_tracked for m in model.modules() if isinstance(m, FusedBNAct)]
-        FusedBNAct.defer_counter = True
+        self._bn_counters = []
+        for m in model.modules():
+            if isinstance(m, FusedBNAct):
+                m.defer_counter = True                      # instance attribute: other models in the process keep counting themselves
+                self._bn_counters.append(m.num_batches_tracked)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and dev.type == "cuda":
+            dist.broadcast(self.flat_p, src=0)              # replicas must start identical (DDP does this in its constructor)
+            self.sync_shadows()
+
+    def state_dict(self):
+        """momentum buffer, schedule position and hyper-parameters (the parameters themselves are the model's state_dict)"""
+        return {"momentum_buffer": self.flat_m.detach().clone(), "iteration": int(self.iteration), "hp": dict(self.hp),
+                "names": list(self.names), "offsets": list(self.offsets)}
+
+    def load_state_dict(self, state):
+        """restores what state_dict() saved and refreshes the bf16 / channels-last / transposed weight shadows from the (already
+        loaded) parameters: call AFTER model.load_state_dict()"""
+        if list(state["names"]) != list(self.names) or list(state["offsets"]) != list(self.offsets):
+            raise ValueError("optimizer state was saved for a different parameter layout")
+        self.flat_m.copy_(state["momentum_buffer"])
+        self.iteration = int(state["iteration"])
+        self.hp.update(state["hp"])
+        self.sync_shadows()
 
     def _build_cl_shadow(self, dev):
         """channels-last bf16 copies of every k x k (k > 1) convolution weight, refreshed by ONE kernel per step
@@ -151,8 +175,9 @@ class FlatSGD:
 
     def push_lr(self):
         """host side of the schedule: write lr(iteration) into the device scalar (async, pinned)"""
-        self._lr_host[0] = self.lr()
-        self.lr_dev.copy_(self._lr_host, non_blocking=True)
+        self._lr_slot = (self._lr_slot + 1) % self._lr_host.numel()
+        self._lr_host[self._lr_slot] = self.lr()
+        self.lr_dev.copy_(self._lr_host[self._lr_slot:self._lr_slot + 1], non_blocking=True)
 
     def device_step(self, grad_scale=1.0):
         """the two optimiser kernels only (capturable); the caller handles push_lr()/iteration"""
@@ -196,10 +221,16 @@ class GraphedTrainStep:
     launch-latency bound when issued from Python, and every shape in the step is static.  Inputs are copied into
     static device buffers; the poly LR is a device scalar refreshed by the host before each replay."""
 
-    def __init__(self, model, opt, img, labels, group=None, warmup=3):
+    def __init__(self, model, opt, img, labels, group=None, warmup=3, restore_after_warmup=False):
+        """warmup eager steps run first (one-time kernel attribute setup, allocator warm-up) and are REAL optimiser steps on the given
+        batch.  restore_after_warmup=True snapshots parameters, momentum, the schedule position and every module buffer (BatchNorm
+        running statistics, counters) before them and puts everything back afterwards, so the first replay is training step 0."""
         self.model, self.opt, self.group = model, opt, group
         self.img = img.clone()
         self.labels = labels.clone()
+        snap = None
+        if restore_after_warmup:
+            snap = (opt.flat_p.clone(), opt.flat_m.clone(), opt.iteration, [b.clone() for b in model.buffers()])
         from .hrnet import CHAIN_PRIORITY
         side = self.stream = torch.cuda.Stream(img.device, priority=CHAIN_PRIORITY)     # chain streams outrank the wgrad streams
         side.wait_stream(torch.cuda.current_stream())
@@ -209,6 +240,13 @@ class GraphedTrainStep:
                 self.warmup_losses.append(train_step(model, opt, self.img, self.labels, group))
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if snap is not None:
+            opt.flat_p.copy_(snap[0]); opt.flat_m.copy_(snap[1]); opt.flat_g.zero_()
+            opt.iteration = snap[2]
+            for b, v in zip(model.buffers(), snap[3]):
+                b.copy_(v)
+            opt.sync_shadows()
+            torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         opt.push_lr()
         # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures (DDP all-reduce / SyncBN inside the graph)

@@ -374,6 +374,109 @@ def test_model_S512_cfg1_argmax_vs_reference_golden(P, report):
     assert errs["probs_strided"] < TOL_F32 and errs["argmax_mismatch_decided"] == 0.0 and errs["loss"] < TOL_F32, errs
 
 
+def _envelope(g):
+    return json.loads(bytes(g["envelope_json"]).decode())
+
+
+def _eval_vs_golden(P, g, S, B, dtype):
+    img, lbl = R.synth_batch(B, S)
+    m = _model(P, dtype)
+    m.eval()
+    with torch.no_grad():
+        probs = m(img.to(DEV))
+    am = probs.argmax(1).cpu().numpy().astype(np.uint8)
+    gap = g["top2gap"].astype(np.float32)
+    ref_s = torch.as_tensor(g["probs_strided"])
+    e = dict(probs_max_abs=float((probs[:, :, ::8, ::8].float().cpu() - ref_s).abs().max()),
+             argmax_agree=float((am == g["argmax"]).mean()))
+    return m, img, lbl, am, gap, e
+
+
+def test_cfg2_bf16_graph_step_vs_reference_golden(P, report):
+    """The BENCHED configuration (BASELINE cfg2: 512x512 tiles, bf16 activations, whole step replayed from the CUDA graph with
+    the default side streams, fused BasicBlocks, async weight gradients; B reduced 16 -> 2 like the fixture) against vectors
+    the UNMODIFIED reference produced in fp32 (oracle/gen_golden_cfg.py).  Tolerances are the reference's OWN bf16-autocast
+    deviation from its fp32 run on the same inputs (the `envelope` stored in the fixture), times 2:
+      eval probabilities, arg-max on the pixels the reference decides by more than the probability tolerance, step-0 loss,
+      total gradient norm (read from the optimiser's clip kernel) and the first SGD update of two parameters.
+    Individual gradients carry no bf16 bound: the reference's own autocast gradients differ from its fp32 ones by 90-180 % in the
+    L2 norm at this size (ReLU/arg-max mask flips cascade through 140 layers), see ENVELOPE_REPORT.json; they are checked in
+    fp32 by test_cfg2_fp32_gradients_vs_reference_golden."""
+    g = np.load(os.path.join(GOLDEN, "model_S512_B2_cfg2.npz"))
+    env = _envelope(g)
+    m, img, lbl, am, gap, errs = _eval_vs_golden(P, g, 512, 2, torch.bfloat16)
+    tol_p = 2.0 * env["probs_max"]
+    decided = gap > tol_p
+    errs["argmax_mismatch_decided"] = float((am != g["argmax"])[decided].mean())
+    errs["tie_fraction"] = float(1 - decided.mean())
+    m.train()
+    opt = P.FlatSGD(m)
+    names = [k[7:] for k in g.files if k.startswith("update.")]
+    named = dict(m.named_parameters())
+    before = {k: named[k].detach().clone() for k in names}
+    step = P.GraphedTrainStep(m, opt, img.to(DEV), lbl.to(DEV), warmup=2, restore_after_warmup=True)
+    loss = float(step().item())                         # replay #1 == training step 0 (parameters were restored after the warm-up)
+    torch.cuda.synchronize()
+    errs["loss_rel"] = abs(loss - float(g["loss"])) / abs(float(g["loss"]))
+    errs["grad_norm_rel"] = abs(opt.grad_norm() - float(g["grad_norm"])) / float(g["grad_norm"])
+    for k in names:
+        errs["update_l2." + k] = float(((named[k].detach() - before[k]).double().cpu() - torch.as_tensor(g["update." + k]).double()).norm()
+                                       / torch.as_tensor(g["update." + k]).double().norm())
+    report["cfg2_bf16_graph"] = dict(errs, envelope={k: v for k, v in env.items() if not k.startswith("grad_")})
+    assert errs["probs_max_abs"] <= tol_p, (errs, env["probs_max"])
+    assert errs["argmax_mismatch_decided"] == 0.0 and errs["argmax_agree"] >= 1.0 - 2.0 * (1.0 - env["argmax_agree"]), errs
+    assert errs["loss_rel"] <= 2.0 * env["loss_rel"], (errs, env["loss_rel"])
+    assert errs["grad_norm_rel"] <= 2.0 * env["grad_norm_rel"], (errs, env["grad_norm_rel"])
+    for k in names:                                     # update = -lr (clip g + wd p): bounded by the gradient envelope of that tensor
+        assert errs["update_l2." + k] <= 2.0 * env["grad_l2." + k], (k, errs, env["grad_l2." + k])
+
+
+def test_cfg2_fp32_gradients_vs_reference_golden(P, report):
+    """Same geometry in fp32 (strict path: no bf16 kernels): loss, probabilities, arg-max and 15 parameter gradients spread over
+    stem / branches / transformer / neck / head against the reference's fp32 run."""
+    g = np.load(os.path.join(GOLDEN, "model_S512_B2_cfg2.npz"))
+    m, img, lbl, am, gap, errs = _eval_vs_golden(P, g, 512, 2, torch.float32)
+    errs["argmax_mismatch_decided"] = float((am != g["argmax"])[gap > 2e-3].mean())
+    m.train()
+    loss = sum(m(img.to(DEV), {"cls": lbl.to(DEV)}).values())
+    loss.backward()
+    from representationlearning_b200 import conv
+    conv.join_wgrad()
+    torch.cuda.synchronize()
+    errs["loss_rel"] = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
+    named = dict(m.named_parameters())
+    for k in g.files:
+        if k.startswith("grad."):
+            a, b = named[k[5:]].grad.double().cpu(), torch.as_tensor(g[k]).double()
+            errs["l2." + k[5:]] = float((a - b).norm() / b.norm())
+    report["cfg2_fp32"] = errs
+    assert errs["probs_max_abs"] < 1e-5 and errs["argmax_mismatch_decided"] == 0.0 and errs["loss_rel"] < TOL_F32, errs
+    # two fp32 implementations with different summation orders: the same mask-flip mechanism as above at the 1e-7 level
+    assert max(v for k, v in errs.items() if k.startswith("l2.")) < 2e-2, errs
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cfg5_1024_tile_vs_reference_golden(P, report, dtype):
+    """BASELINE cfg5 geometry: one 1024x1024 tile (branch 0 = 256x256, padded to 259 for the 7x7 windows; 1369 windows)."""
+    g = np.load(os.path.join(GOLDEN, "model_S1024_B1_cfg5.npz"))
+    env = _envelope(g)
+    m, img, lbl, am, gap, errs = _eval_vs_golden(P, g, 1024, 1, dtype)
+    bf = dtype == torch.bfloat16
+    tol_p = 2.0 * env["probs_max"] if bf else 1e-5
+    decided = gap > max(tol_p, 2e-3)
+    errs["argmax_mismatch_decided"] = float((am != g["argmax"])[decided].mean())
+    m.train()
+    loss = sum(m(img.to(DEV), {"cls": lbl.to(DEV)}).values())
+    loss.backward()
+    from representationlearning_b200 import conv
+    conv.join_wgrad()
+    torch.cuda.synchronize()
+    errs["loss_rel"] = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
+    report["cfg5_%s" % ("bf16" if bf else "fp32")] = dict(errs, envelope=env)
+    assert errs["probs_max_abs"] <= tol_p and errs["argmax_mismatch_decided"] == 0.0, (errs, env)
+    assert errs["loss_rel"] <= (2.0 * env["loss_rel"] if bf else TOL_F32), (errs, env)
+
+
 def test_flat_sgd_vs_oracle(P, report):
     torch.manual_seed(9)
     lin = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 5)).to(DEV)
@@ -706,7 +809,7 @@ def test_conv_cf_bn_backward_epilogue(P, report, case):
         assert rel(y2.float(), ref) < 6e-3
 
 
-@pytest.mark.parametrize("shape", [(2, 32, 24, 40), (16, 32, 128, 128), (3, 64, 32, 32)])
+@pytest.mark.parametrize("shape", [(2, 32, 24, 40), (16, 32, 128, 128), (4, 64, 32, 32)])
 def test_fused_basic_block_vs_unfused(P, report, shape):
     """hrnet._BasicBlockFn (fused tcgen05 convs with statistics / BN-backward epilogues, residual gradient added in the last
     epilogue, weight shadows read in place) against the same block run layer by layer through the library conv + BN kernels:
@@ -817,6 +920,38 @@ def test_fuse_sum(P, report, dtype, relu, ks):
         errs["d%d" % j] = rel(tc[j].grad.float(), tr[j].grad)
     report["fuse_sum_%s_%d_%s" % (str(dtype)[6:], relu, "".join(map(str, ks)))] = errs
     assert max(errs.values()) < (TOL_F32 if dtype == torch.float32 else TOL_BF16), errs
+
+
+def test_flat_sgd_state_dict_resume(P, report):
+    """optimizer checkpoint: momentum + schedule position survive a save / load, shadows are refreshed on load"""
+    torch.manual_seed(4)
+    from representationlearning_b200 import hrnet
+
+    def make():
+        torch.manual_seed(4)
+        return hrnet.BasicBlock(32, 32).to(DEV).train()
+    x = torch.randn(2, 32, 16, 16, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+
+    def one_step(blk, opt):
+        blk(x).float().square().mean().backward()
+        from representationlearning_b200 import conv
+        conv.join_wgrad()
+        opt.all_reduce_grads()
+        opt.step()
+    a = make(); oa = P.FlatSGD(a)
+    for _ in range(2):
+        one_step(a, oa)
+    sd_model, sd_opt = {k: v.clone() for k, v in a.state_dict().items()}, oa.state_dict()
+    one_step(a, oa)
+    b = make(); ob = P.FlatSGD(b)
+    b.load_state_dict(sd_model)
+    ob.load_state_dict(sd_opt)
+    assert ob.iteration == 2 and float((ob.shadow.float() - ob.flat_p).abs().max()) < 1e-2
+    one_step(b, ob)
+    torch.cuda.synchronize()
+    err = float((oa.flat_p - ob.flat_p).abs().max())
+    report["flat_sgd_resume"] = err
+    assert err < 1e-6, err
 
 
 def test_training_trajectory_graph_replay_vs_oracle(P, report):

@@ -50,8 +50,9 @@ def timeit(fn, reps=10):
 
 
 CL = torch.channels_last
+NSHAPES = int(os.environ.get("CF_BENCH_SHAPES", "99"))
 for H, Cin, Cout, k in ((128, 32, 32, 3), (64, 64, 64, 3), (128, 64, 64, 1), (128, 32, 128, 1), (128, 128, 32, 1),
-                        (64, 64, 32, 1)):
+                        (64, 64, 32, 1))[:NSHAPES]:
     x = torch.randn(B, Cin, H, H, device="cuda").bfloat16().contiguous(memory_format=CL)
     w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.05
     wl = w.bfloat16().contiguous(memory_format=CL)
