@@ -71,8 +71,13 @@ typedef struct {
  * pooled [B][4][HW] f32; amax [B][2][HW] u8; smap, gmap [B][2][HW] f32.  The normalised tokens are never materialised:
  * every consumer recomputes (x-mean)*rstd*gamma+beta in fp32 from x and ln_stats. */
 #define RSS_ATTN_SIMT 2          /* flags bit 1: force the fp32 SIMT kernels even for bf16 activations (A/B testing) */
+#define RSS_ATTN_NO_GATE 4       /* flags bit 2: no saliency gate (Mhca.forward alone, DAL.py:726-735): gmap is INPUT, filled by the caller */
 #define RSS_ATTN_NO_RESIDUAL 1   /* flags bit 0: out = Attn(...) without "+ x" (InterlacedPoolAttention2.forward alone) */
 /* p->ln_w == NULL skips norm1 (x, y are then the already-normalised tokens; ln_stats unused). */
+/* SpatialAttention.forward alone (multihead_isa_pool_attention.py:101-115): out (B,1,H,W) f32 = sigmoid(conv7x7([mean_c, max_c]))
+ * of an NCHW-contiguous (B,32,H,W) tensor.  Workspaces: pooled [B][4][HW] f32, amax [B][2][HW] u8, maps [2][B][2][HW] f32. */
+int rss_spatial_attention_fwd(const void* x_nchw, const float* conv_w, float* out, float* ws_pooled, uint8_t* ws_amax, float* ws_maps,
+                              int B, int H, int W, int dtype, cudaStream_t stream);
 int rss_attn_fwd(const void* x, const void* y, const rss_attn_params* p, int B, int H, int W, int dtype, int flags,
                  float* ln_stats, float* pooled, uint8_t* amax, float* smap, float* gmap,
                  void* out, cudaStream_t stream);

@@ -47,6 +47,7 @@ def _mx(a, b):
 
 def run(model, img, lbl, autocast):
     """eval probabilities, then one training forward/backward -> (probs, loss, {name: grad})"""
+    img = img.to(next(model.parameters()).dtype)
     ctx = torch.autocast("cpu", dtype=torch.bfloat16) if autocast else torch.autocast("cpu", enabled=False)
     model.eval()
     with torch.no_grad(), ctx:
@@ -76,6 +77,15 @@ def make(S, B, tag, with_grads):
     env = dict(loss_rel=abs(l16 - l32) / abs(l32), probs_max=float((p16 - p32).abs().max().item()),
                argmax_agree=float((p16.argmax(1) == p32.argmax(1)).float().mean().item()))
     if with_grads:
+        # fp64 run of the reference = the truth the gradients are stored from; its fp32 run's deviation = the fp32 envelope
+        m64 = build_reference_model().double()
+        m64.load_state_dict(R.synth_state_dict(2333, torch.float64))
+        _, l64, g64 = run(m64, img, lbl, False)
+        env["fp32_loss_rel"] = abs(l32 - l64) / abs(l64)
+        for k in KEEP:
+            env["fp32_grad_l2." + k] = _l2(g32[k], g64[k])
+            arrs["grad64." + k] = _np(g64[k])
+        del m64
         gn = torch.sqrt(sum(g.double().pow(2).sum() for g in g32.values()))
         gn16 = torch.sqrt(sum(g.double().pow(2).sum() for g in g16.values()))
         arrs["grad_norm"] = np.float64(gn.item())

@@ -50,6 +50,7 @@ SIGNATURES = {
     "rss_layernorm_fwd": (c_int, [P, P, P, P, P, P, c_float, c_int64, c_int, c_int, P]),
     "rss_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, P]),
     "rss_attn_fwd": (c_int, [P, P, POINTER(AttnParams), c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "rss_spatial_attention_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "rss_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "rss_attn_bwd": (c_int, [P, P, P, POINTER(AttnParams), c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_size_t,
                              P, P, POINTER(AttnGrads), P]),

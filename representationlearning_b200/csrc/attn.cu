@@ -1416,15 +1416,17 @@ static int attn_fwd_impl(const void* x, const void* y, const rss_attn_params* p,
     }
     const LnRef lx = ln_ref(p, ln_stats, rows, 0), ly = ln_ref(p, ln_stats, rows, 1);
     // (every pointer below is an allocation base + a multiple of HW elements: HW % 8 == 0 keeps the 16/32-byte vectors aligned)
-    if (g.HW % 8 == 0) {
-        dim3 pg((g.HW / 8 * 4 + 127) / 128, B, 2);
-        gate_pool_vec_kernel<T><<<pg, 128, 0, st>>>((const T*)x, (const T*)y, lx, ly, pooled, amax, g.HW);
-    } else {
-        dim3 pg((g.HW + 255) / 256, B, 2);
-        gate_pool_kernel<T><<<pg, 256, 0, st>>>((const T*)x, (const T*)y, lx, ly, pooled, amax, g.HW);
+    if (!(flags & RSS_ATTN_NO_GATE)) {      // NO_GATE: the caller filled gmap (Mhca.forward alone: all ones)
+        if (g.HW % 8 == 0) {
+            dim3 pg((g.HW / 8 * 4 + 127) / 128, B, 2);
+            gate_pool_vec_kernel<T><<<pg, 128, 0, st>>>((const T*)x, (const T*)y, lx, ly, pooled, amax, g.HW);
+        } else {
+            dim3 pg((g.HW + 255) / 256, B, 2);
+            gate_pool_kernel<T><<<pg, 256, 0, st>>>((const T*)x, (const T*)y, lx, ly, pooled, amax, g.HW);
+        }
+        dim3 mg(((W + kGmTW - 1) / kGmTW) * ((H + kGmTH - 1) / kGmTH), B);
+        gate_map_kernel<<<mg, kGmTW * kGmTH, 0, st>>>(pooled, p->sa1_w, p->sa2_w, p->lvl_w, p->lvl_b, smap, gmap, H, W);
     }
-    dim3 mg(((W + kGmTW - 1) / kGmTW) * ((H + kGmTH - 1) / kGmTH), B);
-    gate_map_kernel<<<mg, kGmTW * kGmTH, 0, st>>>(pooled, p->sa1_w, p->sa2_w, p->lvl_w, p->lvl_b, smap, gmap, H, W);
     const size_t smem = kFwdSmemFloats * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -1483,17 +1485,22 @@ static int attn_bwd_impl(const void* dout, const void* x, const void* y, const r
     } else {
         win_attn_bwd_kernel<T><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)y, lx, ly, gmap, (const T*)dout, dxg, dyg, *p, *gr, g);
     }
-    if (g.HW % 8 == 0) {
-        dim3 pg((g.HW / 8 * 4 + 127) / 128, B, 2);
-        gate_bwd_reduce_vec_kernel<T><<<pg, 128, 0, st>>>(dxg, dyg, (const T*)x, (const T*)y, lx, ly, dgmap, g.HW);
+    if (flags & RSS_ATTN_NO_GATE) {         // constant gate (ones): no gradient flows into the gate branch
+        cudaError_t e = cudaMemsetAsync(dpooled, 0, (size_t)B * 4 * g.HW * sizeof(float), st);
+        if (e != cudaSuccess) { g_last_cuda_error = (int)e; return RSS_ERR_CUDA; }
     } else {
-        dim3 pg((g.HW + 255) / 256, B, 2);
-        gate_bwd_reduce_kernel<T><<<pg, 256, 0, st>>>(dxg, dyg, (const T*)x, (const T*)y, lx, ly, dgmap, g.HW);
+        if (g.HW % 8 == 0) {
+            dim3 pg((g.HW / 8 * 4 + 127) / 128, B, 2);
+            gate_bwd_reduce_vec_kernel<T><<<pg, 128, 0, st>>>(dxg, dyg, (const T*)x, (const T*)y, lx, ly, dgmap, g.HW);
+        } else {
+            dim3 pg((g.HW + 255) / 256, B, 2);
+            gate_bwd_reduce_kernel<T><<<pg, 256, 0, st>>>(dxg, dyg, (const T*)x, (const T*)y, lx, ly, dgmap, g.HW);
+        }
+        dim3 mg((g.HW + 255) / 256, B);
+        gate_bwd_map_kernel<<<mg, 256, 0, st>>>(dgmap, gmap, smap, p->lvl_w, dpre, gr->lvl_w, gr->lvl_b, g.HW);
+        dim3 cg(((H + 31) / 32) * ((W + 31) / 32), B, 2);
+        gate_bwd_conv_kernel<<<cg, 256, 0, st>>>(dpre, pooled, p->sa1_w, p->sa2_w, dpooled, gr->sa1_w, gr->sa2_w, H, W);
     }
-    dim3 mg((g.HW + 255) / 256, B);
-    gate_bwd_map_kernel<<<mg, 256, 0, st>>>(dgmap, gmap, smap, p->lvl_w, dpre, gr->lvl_w, gr->lvl_b, g.HW);
-    dim3 cg(((H + 31) / 32) * ((W + 31) / 32), B, 2);
-    gate_bwd_conv_kernel<<<cg, 256, 0, st>>>(dpre, pooled, p->sa1_w, p->sa2_w, dpooled, gr->sa1_w, gr->sa2_w, H, W);
     int ag = (int)(((int64_t)g.HW * kC / 8 + 255) / 256);
     if (ag > 1024) ag = 1024;
     dim3 apg(ag, B, 2);
@@ -1511,6 +1518,30 @@ static int attn_bwd_impl(const void* dout, const void* x, const void* y, const r
 }  // namespace rss
 
 using namespace rss;
+
+// SpatialAttention.forward alone (multihead_isa_pool_attention.py:101-115): sigmoid(conv7x7([mean_c(x), max_c(x)])) of an
+// NCHW-CONTIGUOUS (B,32,H,W) tensor.  The pooling kernel of the fused path reads token memory through the reference's flat
+// (B,C,H,W) view (pool:150-151), which for NCHW-contiguous memory is the plain channel pooling this module defines.
+extern "C" int rss_spatial_attention_fwd(const void* x_nchw, const float* conv_w /*(1,2,7,7)*/, float* out /*(B,1,H,W)*/,
+                                         float* ws_pooled /*[B][4][HW]*/, uint8_t* ws_amax /*[B][2][HW]*/, float* ws_maps /*[2][B][2][HW]*/,
+                                         int B, int H, int W, int dtype, cudaStream_t st) {
+    if (B <= 0 || H <= 0 || W <= 0 || !x_nchw || !conv_w || !out) return RSS_ERR_SHAPE;
+    const int HW = H * W;
+    const LnRef none{nullptr, nullptr, nullptr, nullptr};
+    float* smap = ws_maps;
+    float* gmap = ws_maps + (size_t)B * 2 * HW;
+    dim3 pg((HW + 255) / 256, B, 2);
+    if (dtype == RSS_F32) gate_pool_kernel<float><<<pg, 256, 0, st>>>((const float*)x_nchw, (const float*)x_nchw, none, none, ws_pooled, ws_amax, HW);
+    else if (dtype == RSS_BF16) gate_pool_kernel<__nv_bfloat16><<<pg, 256, 0, st>>>((const __nv_bfloat16*)x_nchw, (const __nv_bfloat16*)x_nchw, none, none, ws_pooled, ws_amax, HW);
+    else return RSS_ERR_DTYPE;
+    dim3 mg(((W + kGmTW - 1) / kGmTW) * ((H + kGmTH - 1) / kGmTH), B);
+    // level weights are irrelevant for smap; the conv weight doubles as a valid (2,2)+(2) parameter block of finite numbers
+    gate_map_kernel<<<mg, kGmTW * kGmTH, 0, st>>>(ws_pooled, conv_w, conv_w, conv_w, conv_w, smap, gmap, H, W);
+    cudaError_t e = cudaMemcpy2DAsync(out, (size_t)HW * sizeof(float), smap, (size_t)2 * HW * sizeof(float), (size_t)HW * sizeof(float), B,
+                                      cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return RSS_ERR_CUDA; }
+    return check_launch();
+}
 
 extern "C" size_t rss_attn_bwd_workspace_bytes(int B, int H, int W, int dtype) {
     (void)dtype;

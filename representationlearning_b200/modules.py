@@ -76,6 +76,15 @@ class SpatialAttention(nn.Module):
             raise NotImplementedError("the RSSFormer path only builds SpatialAttention(7) (pool:143-144)")
         self.conv1 = nn.Conv2d(2, 1, kernel_size, padding=3, bias=False)
 
+    def forward(self, x):
+        """(B,32,H,W) -> (B,1,H,W) = sigmoid(conv1([mean_c(x), max_c(x)])), pool:110-115.  Inside the model this runs fused with
+        the level soft-max and the window attention (ops.WindowAttention); called on its own it is forward-only."""
+        if torch.is_grad_enabled() and (x.requires_grad or self.conv1.weight.requires_grad):
+            with torch.no_grad():
+                out = ops.spatial_attention(x, self.conv1.weight)
+            return out.to(x.dtype)        # no graph: the differentiable path is the fused block (ops.WindowAttention)
+        return ops.spatial_attention(x, self.conv1.weight).to(x.dtype)
+
 
 class Mhca(nn.Module):
     """modules/DAL.py:676-1030.  forward(query,key,value) takes sequence-first (L, Bw, C) windows."""
@@ -96,6 +105,23 @@ class Mhca(nn.Module):
     def proj_params(self):
         return (self.q_proj.weight, self.q_proj.bias, self.k_proj.weight, self.k_proj.bias,
                 self.v_proj.weight, self.v_proj.bias, self.out_proj.weight, self.out_proj.bias)
+
+    def forward(self, query, key, value, key_padding_mask=None, need_weights=False, attn_mask=None, residual_attn=None):
+        """DAL.py:726-735 / 873-1020 on sequence-first windows: query, key, value (L=49, Bw, C) -> (49, Bw, C).
+        softmax(q k^T / sqrt(d)) v per head, times sigmoid(avg+max pool of q^T k) per channel, then out_proj -- the same window
+        kernels as the fused block (differentiable), fed with the windows laid side by side as one 7 x 7*Bw image.  Only the call
+        pattern RSSFormer uses is supported: key is value, no masks, no attention weights returned."""
+        if key is not value or key_padding_mask is not None or attn_mask is not None or residual_attn is not None or need_weights:
+            raise NotImplementedError("RSSFormer calls Mhca(x_windows, y_windows, y_windows) without masks (pool:185)")
+        L, Bw, C = query.shape
+        if L != 49 or key.shape != query.shape:
+            raise NotImplementedError("7x7 windows only (L == 49), same shape for query and key")
+
+        def as_image(t):            # token r*7+c of window w -> pixel (r, 7*w + c)
+            return t.reshape(7, 7, Bw, C).permute(2, 0, 1, 3).reshape(1, Bw, 7, 7, C).permute(0, 4, 2, 1, 3).reshape(1, C, 7, Bw * 7)
+        xi, yi = as_image(query), as_image(key)
+        out = ops.WindowAttention.apply(xi, yi, 0.0, False, None, None, None, None, None, None, *self.proj_params())
+        return out.reshape(C, 7, Bw, 7).permute(1, 3, 2, 0).reshape(49, Bw, C)
 
 
 class InterlacedPoolAttention2(nn.Module):

@@ -16,7 +16,7 @@ from ._lib import check as _check
 CL = torch.channels_last
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; counted from the csrc/*.cu launch sites)
 KERNELS_PER_CALL = {
-    "rss_layernorm_fwd": 1, "rss_layernorm_bwd": 1, "rss_attn_fwd": 5, "rss_attn_bwd": 7, "rss_bn_stats": 1, "rss_bn_combine": 1,
+    "rss_layernorm_fwd": 1, "rss_layernorm_bwd": 1, "rss_attn_fwd": 5, "rss_spatial_attention_fwd": 2, "rss_attn_bwd": 7, "rss_bn_stats": 1, "rss_bn_combine": 1,
     "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1, "rss_bn_fwd_fused": 1, "rss_bn_bwd_fused": 1,
     "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 4, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
     "rss_headaux_fwd": 2, "rss_seg_loss_fwd": 2, "rss_seg_loss_bwd": 1, "rss_grad_sumsq": 1, "rss_sgd_step": 1,
@@ -157,7 +157,7 @@ _ATTN_NAMES = ("ln_w", "ln_b", "sa1_w", "sa2_w", "lvl_w", "lvl_b", "q_w", "q_b",
 
 class WindowAttention(torch.autograd.Function):
     """out = [x +] Attn([LN1](x), [LN1](y)); tensors are (B,C,H,W) channels_last.
-    params: 14 tensors in _ATTN_NAMES order; ln_w/ln_b may be None (no norm1)."""
+    params: 14 tensors in _ATTN_NAMES order; ln_w/ln_b may be None (no norm1); sa1_w..lvl_b may be None (no saliency gate)."""
 
     @staticmethod
     def forward(ctx, x, y, eps, residual, *params):
@@ -177,9 +177,10 @@ class WindowAttention(torch.autograd.Function):
         pooled = torch.empty(B, 4, HW, device=dev, dtype=torch.float32)
         amax = torch.empty(B, 2, HW, device=dev, dtype=torch.uint8)
         smap = torch.empty(B, 2, HW, device=dev, dtype=torch.float32)
-        gmap = torch.empty(B, 2, HW, device=dev, dtype=torch.float32)
+        no_gate = params[2] is None                      # Mhca.forward alone: constant gate of ones, no gradient into a gate branch
+        gmap = torch.ones(B, 2, HW, device=dev, dtype=torch.float32) if no_gate else torch.empty(B, 2, HW, device=dev, dtype=torch.float32)
         out = torch.empty_like(x, memory_format=CL)
-        flags = 0 if residual else 1
+        flags = (0 if residual else 1) | (4 if no_gate else 0)
         with timed("rss_attn_fwd"):
             check(lib.rss_attn_fwd(_p(x), _p(y), ctypes.byref(ap), B, H, W, _dt(x), flags, _p(ln_stats),
                                    _p(pooled), _p(amax), _p(smap), _p(gmap), _p(out), _st()), "rss_attn_fwd")
@@ -414,6 +415,25 @@ class FuseSum(torch.autograd.Function):
                 shared = d
             grads.append(d)
         return (None, None) + tuple(grads)
+
+
+def spatial_attention(x, conv_w):
+    """SpatialAttention.forward alone: sigmoid(conv7x7([mean_c(x), max_c(x)])) -> (B,1,H,W) fp32.  Forward only."""
+    _lib.require_device()
+    lib = _lib.load()
+    x = x.detach().contiguous()                          # NCHW-contiguous: the layout the reference module sees
+    B, C, H, W = x.shape
+    if C != 32:
+        raise _lib.RssError("the RSSFormer gate kernels are built for 32 channels (got %d)" % C)
+    HW = H * W
+    dev = x.device
+    out = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32)
+    pooled = torch.empty(B, 4, HW, device=dev, dtype=torch.float32)
+    amax = torch.empty(B, 2, HW, device=dev, dtype=torch.uint8)
+    maps = torch.empty(2, B, 2, HW, device=dev, dtype=torch.float32)
+    check(lib.rss_spatial_attention_fwd(_p(x), _p(_f32(conv_w)), _p(out), _p(pooled), _p(amax), _p(maps), B, H, W, _dt(x), _st()),
+          "rss_spatial_attention_fwd")
+    return out
 
 
 def fuse_sum(terms, ks, relu):

@@ -445,14 +445,18 @@ def test_cfg2_fp32_gradients_vs_reference_golden(P, report):
     torch.cuda.synchronize()
     errs["loss_rel"] = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
     named = dict(m.named_parameters())
+    env = _envelope(g)
+    worst_env = max(v for k, v in env.items() if k.startswith("fp32_grad_l2."))
     for k in g.files:
-        if k.startswith("grad."):
-            a, b = named[k[5:]].grad.double().cpu(), torch.as_tensor(g[k]).double()
-            errs["l2." + k[5:]] = float((a - b).norm() / b.norm())
-    report["cfg2_fp32"] = errs
+        if k.startswith("grad64."):
+            a, b = named[k[7:]].grad.double().cpu(), torch.as_tensor(g[k]).double()
+            errs["l2." + k[7:]] = float((a - b).norm() / b.norm())
+    report["cfg2_fp32"] = dict(errs, reference_fp32_vs_fp64_worst=worst_env)
     assert errs["probs_max_abs"] < 1e-5 and errs["argmax_mismatch_decided"] == 0.0 and errs["loss_rel"] < TOL_F32, errs
-    # two fp32 implementations with different summation orders: the same mask-flip mechanism as above at the 1e-7 level
-    assert max(v for k, v in errs.items() if k.startswith("l2.")) < 2e-2, errs
+    # Gradients are compared with the reference's fp64 run.  The reference's OWN fp32 run deviates from it by `fp32_grad_l2.*`
+    # (ReLU / window-arg-max flips at the 1e-7 level cascade through 140 layers; which tensor is worst is itself noise): the CUDA
+    # fp32 path, a different summation order, is held to 2x the worst of those.
+    assert max(v for k, v in errs.items() if k.startswith("l2.")) <= 2.0 * worst_env, (errs, worst_env)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -809,7 +813,7 @@ def test_conv_cf_bn_backward_epilogue(P, report, case):
         assert rel(y2.float(), ref) < 6e-3
 
 
-@pytest.mark.parametrize("shape", [(2, 32, 24, 40), (16, 32, 128, 128), (4, 64, 32, 32)])
+@pytest.mark.parametrize("shape", [(2, 32, 24, 40), (16, 32, 128, 128), (16, 64, 64, 64)])
 def test_fused_basic_block_vs_unfused(P, report, shape):
     """hrnet._BasicBlockFn (fused tcgen05 convs with statistics / BN-backward epilogues, residual gradient added in the last
     epilogue, weight shadows read in place) against the same block run layer by layer through the library conv + BN kernels:
@@ -920,6 +924,91 @@ def test_fuse_sum(P, report, dtype, relu, ks):
         errs["d%d" % j] = rel(tc[j].grad.float(), tr[j].grad)
     report["fuse_sum_%s_%d_%s" % (str(dtype)[6:], relu, "".join(map(str, ks)))] = errs
     assert max(errs.values()) < (TOL_F32 if dtype == torch.float32 else TOL_BF16), errs
+
+
+def test_train_py_unmodified_b200(P, report, tmp_path):
+    """the reference's train.py, unmodified, with RSS_IMPL=b200: `ever.registry` hands this repo's HRNetFusion to the 'th_amp_ddp'
+    work-alike trainer, which drives it with FlatSGD.  2 iterations of 2 synthetic 512x512 crops; the checkpoint it writes must
+    have the reference's state_dict layout (eval.py:36-41 loads it)."""
+    from test_cpu_train_py_unmodified import run_train_py
+    r, ckpt = run_train_py(tmp_path, "b200", iters=2, batch=2)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "step 2  loss" in r.stdout and os.path.exists(ckpt), r.stdout[-2000:]
+    sd = torch.load(ckpt, map_location="cpu")
+    keys = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+    assert [k[len("module."):] for k in sd] == list(keys)
+    losses = [float(l.split("loss")[1].split()[0]) for l in r.stdout.splitlines() if "  loss " in l]
+    report["train_py_b200_losses"] = losses
+    assert all(0.0 < v < 10.0 for v in losses), losses
+
+
+def test_module_surgery_into_reference_model(P, report):
+    """INTEGRATION.md seam 2: every GeneralTransformerBlock of the REAL reference model (imported unmodified from
+    /root/reference or the travelling archive) is replaced by this repo's block; eval forward on the GPU must match the
+    untouched reference model's own forward."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference sources not available")
+    torch.backends.cudnn.enabled = True
+    ref = ref_shim.build_reference_model()
+    ref.load_state_dict(R.synth_state_dict(2333))
+    ref = ref.to(DEV).eval()
+    img, _ = R.synth_batch(1, 128)
+    with torch.no_grad():
+        want = ref(img.to(DEV))
+    n = 0
+    for name, m in list(ref.named_modules()):
+        if type(m).__name__ == "GeneralTransformerBlock":
+            new = P.GeneralTransformerBlock(m.dim, m.out_dim, m.num_heads).to(DEV).eval()
+            new.load_state_dict(m.state_dict())
+            parent, attr = ref.get_submodule(name.rsplit(".", 1)[0]), name.rsplit(".", 1)[1]
+            setattr(parent, attr, new)
+            n += 1
+    with torch.no_grad():
+        got = ref(img.to(DEV))
+    err = rel(got, want)
+    report["surgery_blocks_replaced"] = n
+    report["surgery_probs"] = err
+    assert n == 8 and err < 1e-4, (n, err)
+
+
+def test_mhca_and_spatial_attention_forward_vs_torch(P, report):
+    """boundary modules called on their own: Mhca.forward(q, k, v) on sequence-first 7x7 windows (DAL.py:726-735,
+    873-1020) and SpatialAttention.forward (pool:110-115) against a torch fp32 restatement."""
+    torch.manual_seed(17)
+    C, Bw = 32, 6
+    mh = P.Mhca(C, 2).to(DEV)
+    q = torch.randn(49, Bw, C, device=DEV, requires_grad=True)
+    k = torch.randn(49, Bw, C, device=DEV, requires_grad=True)
+    out = mh(q, k, k)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+
+    def ref_mhca(q, k):
+        hd = C // 2
+        Q = torch.nn.functional.linear(q, mh.q_proj.weight, mh.q_proj.bias) * hd ** -0.5
+        K = torch.nn.functional.linear(k, mh.k_proj.weight, mh.k_proj.bias)
+        V = torch.nn.functional.linear(k, mh.v_proj.weight, mh.v_proj.bias)
+        Q, K, V = (t.contiguous().view(49, Bw * 2, hd).transpose(0, 1) for t in (Q, K, V))
+        A = torch.softmax(torch.bmm(Q, K.transpose(1, 2)), dim=-1)
+        G = torch.bmm(Q.transpose(1, 2), K)                                   # (Bw*heads, hd, hd)
+        # AdaptiveAvg/MaxPool2d(1) on the 3-D (Bw*heads, hd, hd) tensor pool over BOTH trailing dims: one scalar per window and head
+        alpha = torch.sigmoid(G.mean(dim=(1, 2), keepdim=True) + G.amax(dim=(1, 2), keepdim=True))
+        o = torch.bmm(A, V) * alpha
+        o = o.transpose(0, 1).contiguous().view(49, Bw, C)
+        return torch.nn.functional.linear(o, mh.out_proj.weight, mh.out_proj.bias)
+    q2, k2 = q.detach().clone().requires_grad_(True), k.detach().clone().requires_grad_(True)
+    want = ref_mhca(q2, k2)
+    want.backward(dout)
+    errs = dict(out=rel(out, want), dq=rel(q.grad, q2.grad), dk=rel(k.grad, k2.grad))
+    sa = P.SpatialAttention(7).to(DEV)
+    x = torch.randn(2, 32, 20, 24, device=DEV)
+    got = sa(x)
+    ref_sa = torch.sigmoid(torch.nn.functional.conv2d(torch.cat([x.mean(1, keepdim=True), x.max(1, keepdim=True).values], 1),
+                                                      sa.conv1.weight, padding=3))
+    errs["spatial_attention"] = rel(got, ref_sa)
+    report["boundary_modules"] = errs
+    assert max(errs.values()) < 1e-4, errs
 
 
 def test_flat_sgd_state_dict_resume(P, report):
