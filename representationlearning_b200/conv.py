@@ -165,6 +165,11 @@ def _lowp(w, dtype, channels_last=False):
     return w.detach().to(dtype)
 
 
+def lowp_cl(weight, dtype):
+    """channels-last low-precision copy of a conv weight for the library kernels (the per-step shadow when there is one)"""
+    return _lowp(weight, dtype, channels_last=True).contiguous(memory_format=CL)
+
+
 class _ConvLib(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, dilation, bias_grad):
@@ -334,6 +339,7 @@ def _cf_launch(x, packed, nt, tdy, tdx, Cin, Cout, in_aff, in_relu, stats, add=N
     isc = ish = None
     if in_aff is not None:
         isc, ish = in_aff[2].data_ptr(), in_aff[3].data_ptr()
+    ops.account("cf", x, y, add, None if bnred is None else bnred[0], None if bnred is None else bnred[1])
     with ops.timed("rss_conv_cf"):
         ops.check(lib.rss_conv_cf(x.data_ptr(), packed.data_ptr(), y.data_ptr(), B, H, W, Cin, Cout, nt, tdy, tdx,
                                   int(wstrides[0]), int(wstrides[1]), isc, ish,

@@ -79,11 +79,13 @@ class _BasicBlockFn(torch.autograd.Function):
         w1, n1, dy1, dx1, ws1, k1 = convmod.cf_weight(blk.conv1.weight, False)
         z1, aff1 = convmod._cf_launch(x, w1, n1, dy1, dx1, C, C, None, False, blk.bn1.stats_args(), wstrides=ws1)
         a1 = torch.empty_like(x, memory_format=ops.CL)
+        ops.account("bn", z1, a1)
         ops.check(lib.rss_bn_act_fwd(z1.data_ptr(), None, a1.data_ptr(), aff1[2].data_ptr(), aff1[3].data_ptr(), rows, C, _lib.ACT_RELU,
                                      dt, st), "rss_bn_act_fwd")
         w2, n2, dy2, dx2, ws2, k2 = convmod.cf_weight(blk.conv2.weight, False)
         z2, aff2 = convmod._cf_launch(a1, w2, n2, dy2, dx2, C, C, None, False, blk.bn2.stats_args(), wstrides=ws2)
         out = torch.empty_like(x, memory_format=ops.CL)
+        ops.account("bn", z2, x, out)
         ops.check(lib.rss_bn_act_fwd(z2.data_ptr(), x.data_ptr(), out.data_ptr(), aff2[2].data_ptr(), aff2[3].data_ptr(), rows, C,
                                      _lib.ACT_RELU, dt, st), "rss_bn_act_fwd")
         for bn in (blk.bn1, blk.bn2):
@@ -108,6 +110,7 @@ class _BasicBlockFn(torch.autograd.Function):
         # bn2 backward (residual layer: the ReLU mask comes from the stored block output)
         sc2 = blk.bn2._scratch
         sums2 = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+        ops.account("bn", z2, out, dout, z2, out, dout, x, x, z1, x, x)      # bn2 reduce + apply (2 outputs), bn1 apply (z1, g1 -> dz1)
         ops.check(lib.rss_bn_bwd_reduce_ws(p(z2), p(out), p(dout), p(aff2[2]), p(aff2[3]), p(aff2[0]), p(aff2[1]), p(sums2), p(sc2[2:]),
                                            p(sc2), None, rows, C, relu, dt, st), "rss_bn_bwd_reduce")
         dz2 = torch.empty_like(x, memory_format=ops.CL)
@@ -115,7 +118,7 @@ class _BasicBlockFn(torch.autograd.Function):
         ops.check(lib.rss_bn_bwd_apply(p(z2), p(out), p(dout), p(aff2[2]), p(aff2[3]), p(aff2[0]), p(aff2[1]), p(sums2), 1.0 / rows,
                                        p(dz2), p(dres), rows, C, relu, dt, p(sums2), p(blk.bn2.weight.grad), p(blk.bn2.bias.grad), st),
                   "rss_bn_bwd_apply")
-        convmod._wgrad(dz2, a1, a1, blk.conv2.weight, None, False, 1, 1, 1, blk.conv2.weight.dtype)
+        convmod._wgrad(dz2, a1, convmod.lowp_cl(blk.conv2.weight, x.dtype), blk.conv2.weight, None, False, 1, 1, 1, blk.conv2.weight.dtype)
         # conv2 data gradient; its epilogue applies bn1's ReLU mask and reduces bn1's backward sums
         w2, n2, dy2, dx2, ws2, k2 = convmod.cf_weight(blk.conv2.weight, True)
         g1, sums1 = convmod._cf_launch(dz2, w2, n2, dy2, dx2, C, C, None, False, None, bnred=(z1, None, aff1, True, blk.bn1._scratch),
@@ -124,7 +127,7 @@ class _BasicBlockFn(torch.autograd.Function):
         ops.check(lib.rss_bn_bwd_apply(p(z1), None, p(g1), p(aff1[2]), p(aff1[3]), p(aff1[0]), p(aff1[1]), p(sums1), 1.0 / rows,
                                        p(dz1), None, rows, C, relu, dt, p(sums1), p(blk.bn1.weight.grad), p(blk.bn1.bias.grad), st),
                   "rss_bn_bwd_apply")
-        convmod._wgrad(dz1, x, x, blk.conv1.weight, None, False, 1, 1, 1, blk.conv1.weight.dtype)
+        convmod._wgrad(dz1, x, convmod.lowp_cl(blk.conv1.weight, x.dtype), blk.conv1.weight, None, False, 1, 1, 1, blk.conv1.weight.dtype)
         # conv1 data gradient + the residual-path gradient in the epilogue
         w1, n1, dy1, dx1, ws1, k1 = convmod.cf_weight(blk.conv1.weight, True)
         dx, _ = convmod._cf_launch(dz1, w1, n1, dy1, dx1, C, C, None, False, None, add=dres, wstrides=ws1)

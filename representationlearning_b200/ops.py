@@ -23,6 +23,14 @@ KERNELS_PER_CALL = {
     "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_conv_wgrad": 1, "rss_conv_wgrad_tc": 1, "rss_conv_cf": 1, "rss_shadow_t_refresh": 1, "rss_shadow_cl_refresh": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
 }
 COUNTERS = {"launches": 0, "calls": 0}
+# algorithmic bytes (compulsory reads + writes of the tensors a call touches) per kernel family, filled only while bench.py asks
+ACCOUNT = {}
+ACCOUNT_ON = [False]
+
+
+def account(family, *tensors):
+    if ACCOUNT_ON[0]:
+        ACCOUNT[family] = ACCOUNT.get(family, 0.0) + sum(t.numel() * t.element_size() for t in tensors if t is not None)
 TIMED = {}            # op name -> list of (start_event, end_event), filled only while bench.py enables it
 TIMED_OPS = set()
 
@@ -181,6 +189,7 @@ class WindowAttention(torch.autograd.Function):
         gmap = torch.ones(B, 2, HW, device=dev, dtype=torch.float32) if no_gate else torch.empty(B, 2, HW, device=dev, dtype=torch.float32)
         out = torch.empty_like(x, memory_format=CL)
         flags = (0 if residual else 1) | (4 if no_gate else 0)
+        account("attn_fwd", x, y, out)
         with timed("rss_attn_fwd"):
             check(lib.rss_attn_fwd(_p(x), _p(y), ctypes.byref(ap), B, H, W, _dt(x), flags, _p(ln_stats),
                                    _p(pooled), _p(amax), _p(smap), _p(gmap), _p(out), _st()), "rss_attn_fwd")
@@ -209,6 +218,7 @@ class WindowAttention(torch.autograd.Function):
         ws = torch.empty(wsb, device=x.device, dtype=torch.uint8)
         dx = torch.empty_like(x, memory_format=CL)
         dy = torch.empty_like(x, memory_format=CL)
+        account("attn_bwd", dout, x, y, dx, dy)
         with timed("rss_attn_bwd"):
             check(lib.rss_attn_bwd(_p(dout), _p(x), _p(y), ctypes.byref(ap), B, H, W, _dt(x), ctx.flags,
                                    _p(ln_stats), _p(pooled), _p(amax), _p(smap), _p(gmap), _p(ws), wsb, _p(dx), _p(dy),
@@ -252,6 +262,7 @@ class BNAct(torch.autograd.Function):
         if fused and (scratch is None or scratch.numel() < 2 + 2 * C):
             scratch = torch.zeros(2 + 2 * C, device=dev, dtype=torch.float32)   # [0:2] barrier counters, [2:] accumulators; left zeroed
         y = torch.empty_like(x, memory_format=CL)
+        account("bn", None if (have_aff or not training) else x, x, residual, y)     # statistics pass + apply pass
         raw = False
         if fused and not have_aff:          # statistics + apply in ONE launch (device-wide barrier in between)
             check(lib.rss_bn_fwd_fused(_p(x), _p(residual), _p(y), _p(scratch[2:]), _p(scratch), rows, C, act, dt, _p(g), _p(b),
@@ -317,6 +328,7 @@ class BNAct(torch.autograd.Function):
         direct = sg is not None and sb is not None
         dx = torch.empty_like(x, memory_format=CL)
         dres = torch.empty_like(x, memory_format=CL) if ctx.has_res else None
+        account("bn", x, dy, y, x, dy, y, dx, dres)                                   # reduce pass + apply pass
         if ctx.fused:                       # reduce + apply in ONE launch (training mode, single rank, L2-resident tensor)
             local = None if direct else torch.empty(2 * C, device=x.device, dtype=torch.float32)
             sc = ctx.scratch
