@@ -157,6 +157,8 @@ __global__ void bn_stats_fused_kernel(const T* __restrict__ x, float* __restrict
                                       float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
                                       float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                       float* __restrict__ scale, float* __restrict__ shift, const float* __restrict__ pre_bias) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float sm[];               // [rpb][2][C]
     __shared__ bool is_last;
     const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -290,6 +292,8 @@ template <typename T, int ACT, bool RES>   // ACT: 0 none, 1 relu, 2 gelu
 __global__ void bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
                                   const float* __restrict__ scale, const float* __restrict__ shift,
                                   int64_t rows, int C, int cg, int rpb, const BnFin fin) {
+    pdl_wait();
+    pdl_trigger();
     const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
     float sc[8], sh[8];
     if (fin.accum) {
@@ -409,6 +413,8 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
                                      float* __restrict__ accum /*[2][C] persistent zeroed scratch, or NULL: sums was zeroed by the caller*/,
                                      unsigned int* __restrict__ ticket, T* __restrict__ dz_out /*NULL or [rows][C]: dz kept for the apply pass*/,
                                      int64_t rows, int C, int cg, int rpb) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float sm[];           // [rpb][2][C]
     __shared__ bool is_last;
     const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -488,6 +494,8 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
                                     const float* __restrict__ local_sums, float* __restrict__ dgamma_acc, float* __restrict__ dbeta_acc,
                                     float* __restrict__ raw_accum /*NULL, or the scratch bn_bwd_reduce_kernel added into ("raw" protocol)*/,
                                     unsigned int* __restrict__ raw_ticket, float* __restrict__ sums_out /*NULL or [2C]*/) {
+    pdl_wait();
+    pdl_trigger();
     const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
     if (!raw_accum && dgamma_acc && blockIdx.x == 0) {      // parameter gradients straight into the caller's (flat) grad buffer
         for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta_acc[c] += local_sums[c]; dgamma_acc[c] += local_sums[C + c]; }
@@ -558,6 +566,8 @@ __global__ void bn_bwd_apply_dz_kernel(const T* __restrict__ x, const T* __restr
                                        const float* __restrict__ sums, float inv_count, T* __restrict__ dx,
                                        int64_t rows, int C, int cg, int rpb,
                                        const float* __restrict__ local_sums, float* __restrict__ dgamma_acc, float* __restrict__ dbeta_acc) {
+    pdl_wait();
+    pdl_trigger();
     const int sub = threadIdx.x % cg, r = threadIdx.x / cg;
     if (dgamma_acc && blockIdx.x == 0) {
         for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta_acc[c] += local_sums[c]; dgamma_acc[c] += local_sums[C + c]; }
@@ -878,7 +888,7 @@ extern "C" int rss_bn_stats_fused(const void* x, float* accum_scratch, unsigned 
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 8, bn_ticket_bpsm());
     const size_t smem = (size_t)g.rpb * C * 2 * sizeof(float);
-    RSS_DISPATCH_DTYPE(dtype, bn_stats_fused_kernel<T><<<grid, g.threads, smem, st>>>((const T*)x, accum_scratch, ticket, rows, C, g.cg, g.rpb,
+    RSS_DISPATCH_DTYPE(dtype, launch_k(bn_stats_fused_kernel<T>, grid, g.threads, smem, st, (const T*)x, accum_scratch, ticket, rows, C, g.cg, g.rpb,
                        gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out, scale, shift, pre_bias));
     return check_launch();
 }
@@ -913,6 +923,14 @@ extern "C" int rss_bn_eval_affine(const float* gamma, const float* beta, const f
         case RSS_ACT_GELU: KERNEL<T, 2, false> __VA_ARGS__; break;                   \
         default: return RSS_ERR_SHAPE;                                               \
     }
+// same dispatch through launch_k (programmatic dependent launch, common.cuh)
+#define BN_ACT_LAUNCH(KERNEL, FLAG, GRID, BLOCK, SMEM, ST, ...)                      \
+    switch (act) {                                                                   \
+        case RSS_ACT_NONE: if (FLAG) launch_k(KERNEL<T, 0, true>, GRID, BLOCK, SMEM, ST, __VA_ARGS__); else launch_k(KERNEL<T, 0, false>, GRID, BLOCK, SMEM, ST, __VA_ARGS__); break; \
+        case RSS_ACT_RELU: if (FLAG) launch_k(KERNEL<T, 1, true>, GRID, BLOCK, SMEM, ST, __VA_ARGS__); else launch_k(KERNEL<T, 1, false>, GRID, BLOCK, SMEM, ST, __VA_ARGS__); break; \
+        case RSS_ACT_GELU: launch_k(KERNEL<T, 2, false>, GRID, BLOCK, SMEM, ST, __VA_ARGS__); break; \
+        default: return RSS_ERR_SHAPE;                                               \
+    }
 
 extern "C" int rss_bn_act_fwd(const void* x, const void* residual, void* y, const float* scale, const float* shift,
                               int64_t rows, int C, int act, int dtype, cudaStream_t st) {
@@ -920,7 +938,7 @@ extern "C" int rss_bn_act_fwd(const void* x, const void* residual, void* y, cons
     if (residual && act == RSS_ACT_GELU) return RSS_ERR_SHAPE;   // not a pattern of the reference (backward would need the residual)
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
-    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_act_fwd_kernel, residual != nullptr, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, rows, C, g.cg, g.rpb, BnFin{})));
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_LAUNCH(bn_act_fwd_kernel, residual != nullptr, grid, g.threads, 0, st, (const T*)x, (const T*)residual, (T*)y, scale, shift, rows, C, g.cg, g.rpb, BnFin{}));
     return check_launch();
 }
 
@@ -966,7 +984,7 @@ extern "C" int rss_bn_bwd_reduce_ws(const void* x, const void* y, const void* dy
         cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st);
         if (e != cudaSuccess) { g_last_cuda_error = (int)e; return RSS_ERR_CUDA; }
     }
-    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_reduce_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, smem, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, accum_scratch, ticket, (T*)dz_out, rows, C, g.cg, g.rpb)));
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_LAUNCH(bn_bwd_reduce_kernel, y != nullptr && act == RSS_ACT_RELU, grid, g.threads, smem, st, (const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, accum_scratch, ticket, (T*)dz_out, rows, C, g.cg, g.rpb));
     return check_launch();
 }
 
@@ -984,8 +1002,8 @@ extern "C" int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, co
     if (act == RSS_ACT_RELU && dres && !y) return RSS_ERR_SHAPE;     // residual layers must pass the saved output
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
-    RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
-                                                                                                           local_sums, dgamma_acc, dbeta_acc, nullptr, nullptr, nullptr)));
+    RSS_DISPATCH_DTYPE(dtype, BN_ACT_LAUNCH(bn_bwd_apply_kernel, y != nullptr && act == RSS_ACT_RELU, grid, g.threads, 0, st, (const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
+                                            local_sums, dgamma_acc, dbeta_acc, (float*)nullptr, (unsigned int*)nullptr, (float*)nullptr));
     return check_launch();
 }
 
@@ -1011,7 +1029,7 @@ extern "C" int rss_bn_bwd_apply_dz(const void* x, const void* dz, const float* s
     if (C <= 0 || C % 8 || rows <= 0 || !dz) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
     const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
-    RSS_DISPATCH_DTYPE(dtype, bn_bwd_apply_dz_kernel<T><<<grid, g.threads, 0, st>>>((const T*)x, (const T*)dz, scale, mean, invstd, sums,
+    RSS_DISPATCH_DTYPE(dtype, launch_k(bn_bwd_apply_dz_kernel<T>, grid, g.threads, 0, st, (const T*)x, (const T*)dz, scale, mean, invstd, sums,
                        inv_count, (T*)dx, rows, C, g.cg, g.rpb, local_sums, dgamma_acc, dbeta_acc));
     return check_launch();
 }

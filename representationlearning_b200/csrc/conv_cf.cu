@@ -199,6 +199,10 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
         const int plane = kc >> 3, c = kc & 7;
         *reinterpret_cast<uint4*>(smem + (size_t)(tap * KC + plane) * COUT * ROWB + cf_swz<ROWB>(co, c)) = v;
     }
+    // everything above touched only this CTA's shared memory / TMEM and the weight shadow (written by the PREVIOUS step's optimiser):
+    // it may overlap the tail of the preceding kernel.  From here on the kernel reads what its predecessors produced.
+    pdl_wait();
+    pdl_trigger();
     if (MODE == kCfStats) {
         for (int c = threadIdx.x; c < COUT; c += kCfThreads) cst[c] = ep.running_mean ? ep.running_mean[c] : 0.f;
     } else if (MODE == kCfBnRed) {
@@ -683,8 +687,8 @@ static cudaError_t cf_launch(const CUtensorMap& tm, const void* w_packed, void* 
         if (e != cudaSuccess) return e;
         attr[dev] = true;
     }
-    conv_cf_kernel<CIN, COUT, NTAPS, MODE><<<pl.grid, kCfThreads, pl.smem, stream>>>(
-        tm, (const __nv_bfloat16*)w_packed, (__nv_bfloat16*)y, in_scale, in_shift, pl.g, ep);
+    launch_k(conv_cf_kernel<CIN, COUT, NTAPS, MODE>, pl.grid, kCfThreads, pl.smem, stream,
+             tm, (const __nv_bfloat16*)w_packed, (__nv_bfloat16*)y, in_scale, in_shift, pl.g, ep);
     return cudaSuccess;
 }
 

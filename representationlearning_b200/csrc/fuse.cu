@@ -10,6 +10,8 @@ struct FuseTerms { const void* p[4]; int k[4]; int n; };
 
 template <typename T>
 __global__ void fuse_sum_fwd_kernel(FuseTerms t, T* __restrict__ out, int B, int H, int W, int C, int relu) {
+    pdl_wait();
+    pdl_trigger();
     const int groups = C / 8;
     const int64_t total = (int64_t)B * H * W * groups;
     const bool small = total < 0x7fffffffLL;
@@ -42,6 +44,8 @@ __global__ void fuse_sum_fwd_kernel(FuseTerms t, T* __restrict__ out, int B, int
 template <typename T>
 __global__ void fuse_sum_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ out, T* __restrict__ dterm,
                                     int B, int H, int W, int C, int k, int relu) {
+    pdl_wait();
+    pdl_trigger();
     const int groups = C / 8, h = H >> k, w = W >> k, s = 1 << k;
     const int64_t total = (int64_t)B * h * w * groups;
     const bool small = total < 0x7fffffffLL;
@@ -83,7 +87,7 @@ extern "C" int rss_fuse_sum_fwd(const void* const* terms, const int* log2_up, in
     const int64_t total = (int64_t)B * H * W * (C / 8);
     int grid = (int)((total + 255) / 256);
     if (grid > num_sms() * 16) grid = num_sms() * 16;
-    RSS_DISPATCH_DTYPE(dtype, fuse_sum_fwd_kernel<T><<<grid, 256, 0, st>>>(t, (T*)out, B, H, W, C, relu));
+    RSS_DISPATCH_DTYPE(dtype, launch_k(fuse_sum_fwd_kernel<T>, grid, 256, 0, st, t, (T*)out, B, H, W, C, relu));
     return check_launch();
 }
 
@@ -95,6 +99,6 @@ extern "C" int rss_fuse_sum_bwd(const void* dout, const void* out, void* dterm, 
     int grid = (int)((total + 255) / 256);
     if (grid > num_sms() * 16) grid = num_sms() * 16;
     if (grid < 1) grid = 1;
-    RSS_DISPATCH_DTYPE(dtype, fuse_sum_bwd_kernel<T><<<grid, 256, 0, st>>>((const T*)dout, (const T*)out, (T*)dterm, B, H, W, C, log2_up, relu));
+    RSS_DISPATCH_DTYPE(dtype, launch_k(fuse_sum_bwd_kernel<T>, grid, 256, 0, st, (const T*)dout, (const T*)out, (T*)dterm, B, H, W, C, log2_up, relu));
     return check_launch();
 }

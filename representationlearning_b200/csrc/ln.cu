@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, T*
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float eps, int64_t rows) {
+    pdl_wait();
+    pdl_trigger();
     constexpr int C = TPT * 8;
     const int sub = threadIdx.x % TPT;
     float g[8], b[8];
@@ -59,6 +61,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
                                                      const float* __restrict__ gamma, const T* __restrict__ dx_add,
                                                      T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      int64_t rows) {
+    pdl_wait();
+    pdl_trigger();
     constexpr int C = TPT * 8;
     __shared__ float red[2][256 / TPT][C + 1];
     const int sub = threadIdx.x % TPT;
@@ -126,7 +130,7 @@ static int ln_fwd_launch(const void* x, void* y, float* mean, float* rstd, const
     const int cap = num_sms() * 16;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-#define LN_CASE(TPT) case TPT: ln_fwd_kernel<T, TPT><<<grid, 256, 0, st>>>((const T*)x, (T*)y, mean, rstd, gamma, beta, eps, rows); break;
+#define LN_CASE(TPT) case TPT: launch_k(ln_fwd_kernel<T, TPT>, grid, 256, 0, st, (const T*)x, (T*)y, mean, rstd, gamma, beta, eps, rows); break;
     switch (tpt) { LN_CASE(1) LN_CASE(2) LN_CASE(4) LN_CASE(8) LN_CASE(16) LN_CASE(32) default: return RSS_ERR_SHAPE; }
 #undef LN_CASE
     return check_launch();
@@ -141,7 +145,7 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const
     const int cap = num_sms() * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-#define LN_CASE(TPT) case TPT: ln_bwd_kernel<T, TDY, TPT><<<grid, 256, 0, st>>>((const TDY*)dy, (const T*)x, mean, rstd, gamma, (const T*)dx_add, (T*)dx, dgamma, dbeta, rows); break;
+#define LN_CASE(TPT) case TPT: launch_k(ln_bwd_kernel<T, TDY, TPT>, grid, 256, 0, st, (const TDY*)dy, (const T*)x, mean, rstd, gamma, (const T*)dx_add, (T*)dx, dgamma, dbeta, rows); break;
     switch (tpt) { LN_CASE(1) LN_CASE(2) LN_CASE(4) LN_CASE(8) LN_CASE(16) LN_CASE(32) default: return RSS_ERR_SHAPE; }
 #undef LN_CASE
     return check_launch();
