@@ -281,6 +281,11 @@ int rss_sgd_step(float* params, float* grads, float* momentum_buf, int64_t n, co
  * Cout over the entries before e, row_start[n_entries] = total (int64, device memory); max_row_floats = max Cin*kh*kw. */
 int rss_shadow_cl_refresh(const float* params, void* shadow_cl, const int64_t* table, const int64_t* row_start,
                           int n_entries, int max_row_floats, cudaStream_t stream);
+/* dst_e[i] += (float)src_e[i] for a list of tensors in ONE launch (fp32 accumulation of the library's bf16 weight gradients into the
+ * flat gradient buffer).  table[e] = {src device pointer (bf16), dst device pointer (f32), numel, Cin, kk}: kk = 0 same element
+ * order, kk = kh*kw > 0: src in the library's channels-last (Cout,kh,kw,Cin) order, dst in parameter order (Cout,Cin,kh,kw).
+ * chunk_start[e] = index of the first 4096-element chunk of entry e, chunk_start[n_entries] = total_chunks.  Device memory. */
+int rss_accum_bf16_list(const int64_t* table, const int64_t* chunk_start, int n_entries, int64_t total_chunks, cudaStream_t stream);
 /* transposed bf16 copies for the data-gradient operand of rss_conv_cf: weight e = fp32 (Cout,Cin,kh,kw) at params + table[e][0]
  * -> bf16 [Cin][kh*kw][Cout] at shadow_t + table[e][1]; table[e] = {src offset, dst offset, Cout, Cin, kh*kw} (int64). */
 int rss_shadow_t_refresh(const float* params, void* shadow_t, const int64_t* table, int n_entries, cudaStream_t stream);

@@ -98,6 +98,7 @@ SIGNATURES = {
     "rss_sgd_step": (c_int, [P, P, P, c_int64, P, c_float, c_float, P, c_float, c_float, c_int, P, P]),
     "rss_shadow_cl_refresh": (c_int, [P, P, P, P, c_int, c_int, P]),
     "rss_shadow_t_refresh": (c_int, [P, P, P, c_int, P]),
+    "rss_accum_bf16_list": (c_int, [P, P, c_int, c_int64, P]),
 }
 
 _lib = None

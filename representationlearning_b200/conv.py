@@ -41,6 +41,38 @@ def wgrad_stream(dev):
     return lst[WGRAD["rr"]]
 
 
+# bf16 weight gradients of the library kernels waiting for their fp32 accumulation into the flat gradient buffer: one multi-tensor
+# launch at join time (rss_accum_bf16_list) instead of one torch elementwise kernel per convolution (RSS_WGRAD_BATCH=0: per conv)
+PENDING = {"on": os.environ.get("RSS_WGRAD_BATCH", "1") != "0", "items": [], "tables": {}}
+
+
+def _flush_pending():
+    items = PENDING["items"]
+    if not items:
+        return
+    PENDING["items"] = []
+    dev = items[0][0].device
+    cur = torch.cuda.current_stream(dev)
+    key = tuple((dw.data_ptr(), sink.data_ptr(), dw.numel(), cin, kk) for sink, dw, cin, kk in items)
+    ent = PENDING["tables"].get(key)
+    if ent is None:
+        if len(PENDING["tables"]) > 8:
+            PENDING["tables"].clear()
+        rows, starts, c = [], [0], 0
+        for src, dst, n, cin, kk in key:
+            rows.append([src, dst, n, cin, kk])
+            c += (n + 4095) // 4096
+            starts.append(c)
+        host = (torch.tensor(rows, dtype=torch.int64).pin_memory(), torch.tensor(starts, dtype=torch.int64).pin_memory())
+        ent = PENDING["tables"][key] = (host, torch.empty_like(host[0], device=dev), torch.empty_like(host[1], device=dev), c)
+    host, table, starts, total = ent
+    table.copy_(host[0], non_blocking=True)               # (captured as memcpy nodes: the pinned tables outlive the graph)
+    starts.copy_(host[1], non_blocking=True)
+    for it in items:
+        it[1].record_stream(cur)
+    ops.check(_lib.load().rss_accum_bf16_list(table.data_ptr(), starts.data_ptr(), len(items), total, ops._st()), "rss_accum_bf16_list")
+
+
 def join_wgrad(dev=None):
     """make the current stream wait for every outstanding weight-gradient kernel (call before reading gradients)"""
     for d, lst in WGRAD["streams"].items():
@@ -48,6 +80,7 @@ def join_wgrad(dev=None):
             for s in lst:
                 torch.cuda.current_stream(d).wait_stream(s)
     WGRAD["used"].clear()
+    _flush_pending()
 
 
 ENGINE["wgrad"] = os.environ.get("RSS_WGRAD_KERNEL", "1") != "0"     # hand-written split-K weight gradient (csrc/conv_wgrad.cu)
@@ -104,7 +137,12 @@ def _wgrad(dy, x, w_lp, weight, bias, want_b, stride, padding, dilation, wdtype)
                                                         [False, True, want_b])
         sw = ops.grad_sink(weight)
         if sw is not None:
-            sw.add_(dw)
+            kk = dw.shape[2] * dw.shape[3]
+            if PENDING["on"] and dw.dtype == torch.bfloat16 and sw.is_contiguous() and (dw.is_contiguous() or dw.is_contiguous(memory_format=CL)):
+                # the library returns k x k gradients in (Cout,kh,kw,Cin) memory order; the sink is in parameter order
+                PENDING["items"].append((sw, dw, dw.shape[1], 0 if (kk == 1 or dw.is_contiguous()) else kk))
+            else:
+                sw.add_(dw)
             dw = None
         else:
             dw = dw.to(wdtype)

@@ -256,6 +256,36 @@ __global__ void shadow_cl_kernel(const float* __restrict__ p, __nv_bfloat16* __r
     }
 }
 
+// dst_e[i] += float(src_e[i]) for a LIST of tensors in one launch: the fp32 accumulation of the library's bf16 weight gradients into
+// the flat gradient buffer (one torch elementwise launch per convolution before: 218 launches per step).
+// table[e] = {src pointer, dst pointer, numel, Cin, kk}: kk = 0: same element order; kk > 0: src is the (Cout,kh,kw,Cin) channels-last
+// layout the library returns for k x k weights, dst the (Cout,Cin,kh,kw) parameter order.
+// chunk_start[e] = first 4096-element chunk of entry e (chunk_start[n] = total chunks).
+__global__ void accum_list_kernel(const int64_t* __restrict__ table, const int64_t* __restrict__ chunk_start, int n_entries) {
+    const int64_t total = chunk_start[n_entries];
+    for (int64_t chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+        int lo = 0, hi = n_entries - 1;                     // last entry with chunk_start <= chunk
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (chunk_start[mid] <= chunk) lo = mid; else hi = mid - 1;
+        }
+        const int64_t* e = table + (int64_t)lo * 5;
+        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(e[0]);
+        float* dst = reinterpret_cast<float*>(e[1]);
+        const int64_t n = e[2], base = (chunk - chunk_start[lo]) * 4096;
+        const int cin = (int)e[3], kk = (int)e[4];
+        if (kk == 0) {
+            for (int64_t i = base + threadIdx.x; i < n && i < base + 4096; i += blockDim.x) dst[i] += __bfloat162float(src[i]);
+        } else {
+            const int row = cin * kk;
+            for (int64_t i = base + threadIdx.x; i < n && i < base + 4096; i += blockDim.x) {
+                const int co = (int)(i / row), rem = (int)(i - (int64_t)co * row), ci = rem / kk, t = rem - ci * kk;
+                dst[i] += __bfloat162float(src[((int64_t)co * kk + t) * cin + ci]);
+            }
+        }
+    }
+}
+
 // transposed copies for the data-gradient operand of the fused conv: out[(ci*kk + t)*Cout + co] = w[(co*Cin + ci)*kk + t]
 __global__ void shadow_t_kernel(const float* __restrict__ p, __nv_bfloat16* __restrict__ out, const int64_t* __restrict__ table) {
     const int64_t* e = table + (int64_t)blockIdx.y * 5;
@@ -271,6 +301,13 @@ __global__ void shadow_t_kernel(const float* __restrict__ p, __nv_bfloat16* __re
 }  // namespace rss
 
 using namespace rss;
+
+extern "C" int rss_accum_bf16_list(const int64_t* table, const int64_t* chunk_start, int n_entries, int64_t total_chunks, cudaStream_t st) {
+    if (n_entries <= 0 || total_chunks <= 0) return RSS_ERR_SHAPE;
+    int grid = (int)(total_chunks < (int64_t)num_sms() * 8 ? total_chunks : (int64_t)num_sms() * 8);
+    accum_list_kernel<<<grid, 256, 0, st>>>(table, chunk_start, n_entries);
+    return check_launch();
+}
 
 extern "C" int rss_shadow_t_refresh(const float* params, void* shadow_t, const int64_t* table, int n_entries, cudaStream_t st) {
     if (n_entries <= 0 || n_entries > 65535) return RSS_ERR_SHAPE;
