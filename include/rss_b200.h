@@ -281,6 +281,15 @@ int rss_sgd_step(float* params, float* grads, float* momentum_buf, int64_t n, co
  * Cout over the entries before e, row_start[n_entries] = total (int64, device memory); max_row_floats = max Cin*kh*kw. */
 int rss_shadow_cl_refresh(const float* params, void* shadow_cl, const int64_t* table, const int64_t* row_start,
                           int n_entries, int max_row_floats, cudaStream_t stream);
+/* ---- evaluation side (train.py:17,42-55, eval.py:48-80, module/tta.py:12-24,118-137) ----
+ * rss_bilinear_resize: dst = alpha * F.interpolate(src, (H,W), 'bilinear', align_corners=True) + beta * dst on `planes` NCHW fp32
+ * planes (beta == 0: dst is not read): the Scale transform of the test-time augmentation and its accumulating inverse.
+ * rss_confusion_matrix: cm_acc[truth*K + pred] += 1 over the pixels with truth != ignore_index (PixelMetric.forward), from the
+ * uint8 arg-max map of rss_head_probs; cm_acc (K*K uint64) is accumulated into. */
+int rss_bilinear_resize(const float* src, float* dst, int planes, int h, int w, int H, int W, float alpha, float beta, cudaStream_t stream);
+int rss_confusion_matrix(const uint8_t* pred, const int64_t* truth, unsigned long long* cm_acc, int64_t n, int num_classes,
+                         int ignore_index, cudaStream_t stream);
+
 /* dst_e[i] += (float)src_e[i] for a list of tensors in ONE launch (fp32 accumulation of the library's bf16 weight gradients into the
  * flat gradient buffer).  table[e] = {src device pointer (bf16), dst device pointer (f32), numel, Cin, kk}: kk = 0 same element
  * order, kk = kh*kw > 0: src in the library's channels-last (Cout,kh,kw,Cin) order, dst in parameter order (Cout,Cin,kh,kw).

@@ -21,7 +21,9 @@ from .model import HRNetFusion, MODEL, RSSFORMER_CONFIG, build_rssformer  # noqa
 from .modules import (FusedBNAct, GeneralTransformerBlock, InterlacedPoolAttention2, Mhca, MlpDWBN,  # noqa: F401
                       SimpleFusion8, SpatialAttention)
 from .trainer import FlatSGD, GraphedTrainStep, poly_lr, train_step  # noqa: F401
+from . import evalops  # noqa: F401
+from .evalops import PixelMetric, Scale, TestTimeAugmentation, tta  # noqa: F401
 
 __all__ = ["HRNetFusion", "MODEL", "RSSFORMER_CONFIG", "build_rssformer", "GeneralTransformerBlock",
            "InterlacedPoolAttention2", "Mhca", "MlpDWBN", "SimpleFusion8", "SpatialAttention", "FusedBNAct",
-           "FlatSGD", "GraphedTrainStep", "poly_lr", "train_step"]
+           "FlatSGD", "GraphedTrainStep", "poly_lr", "train_step", "PixelMetric", "Scale", "TestTimeAugmentation", "tta"]

@@ -54,6 +54,7 @@ struct CfGeom {
     int S;                               // ring stages (2 or 3)
     int tap_off[kCfMaxTaps];             // dy*Wp + dx (signed)
     int in_relu;
+    int xsplit, box_w;                   // Wp > 256 (TMA box limit): every staged row is fetched as xsplit boxes of box_w positions
     int w_row_stride, w_tap_stride;      // weight operand: element (tap, n, k) at n*w_row_stride + tap*w_tap_stride + k (k contiguous)
     unsigned int wp_magic;               // ceil(2^32 / Wp): q / Wp == __umulhi(q, wp_magic) for q < 2^32 / Wp (positions are < 2^17)
     int dbg;                             // profiling aid (RSS_CF_DBG bits): 1 epilogue does no math / staging stores, 4 no MMAs issued
@@ -229,9 +230,17 @@ conv_cf_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* 
                 const int r_lo = cf_row_lo(t * g.MT, g.halo, g.Wp);
                 const uint32_t full = smem_u32(bar_landed + si);
                 mbar_expect_tx(full, tx_bytes);
+                if (g.xsplit == 1) {
 #pragma unroll
-                for (int pl = 0; pl < KC; ++pl)
-                    tma_load_4d(a_s + si * stage_bytes + (uint32_t)(pl * g.P) * ROWB, &tmap_x, full, pl * 64, -g.halo, r_lo, b);
+                    for (int pl = 0; pl < KC; ++pl)
+                        tma_load_4d(a_s + si * stage_bytes + (uint32_t)(pl * g.P) * ROWB, &tmap_x, full, pl * 64, -g.halo, r_lo, b);
+                } else {                                                        // wide images: one box per row and column part
+                    for (int pl = 0; pl < KC; ++pl)
+                        for (int rr = 0; rr < g.NR; ++rr)
+                            for (int xs = 0; xs < g.xsplit; ++xs)
+                                tma_load_4d(a_s + si * stage_bytes + (uint32_t)(pl * g.P + rr * g.Wp + xs * g.box_w) * ROWB, &tmap_x, full,
+                                            pl * 64, -g.halo + xs * g.box_w, r_lo + rr, b);
+                }
                 if (++si == S) { si = 0; ++use; }
             }
         }
@@ -611,7 +620,12 @@ static int cf_plan(int B, int H, int W, int Cin, int Cout, int n_taps, const int
     g.halo = halo; g.Wp = W + 2 * halo; g.Q = H * g.Wp;
     g.wp_magic = (unsigned int)((0x100000000ull + (unsigned)g.Wp - 1) / (unsigned)g.Wp);
     g.dbg = 0;
-    if (g.Wp > 256 || g.Wp < 8) return RSS_ERR_SHAPE;                         // TMA box dimension limit; <= 32 row segments per block
+    if (g.Wp < 8) return RSS_ERR_SHAPE;                                       // <= 32 row segments per 128-position block
+    g.xsplit = 1; g.box_w = g.Wp;
+    if (g.Wp > 256) {                                                         // TMA box dimension limit: split every row in two boxes
+        if (g.Wp > 512 || (g.Wp & 1)) return RSS_ERR_SHAPE;
+        g.xsplit = 2; g.box_w = g.Wp / 2;
+    }
     for (int t = 0; t < kCfMaxTaps; ++t) g.tap_off[t] = t < n_taps ? dy[t] * g.Wp + dx[t] : 0;
     const int KC = (Cin + 63) / 64, rowb = Cin == 32 ? 64 : 128;
     const size_t w_bytes = (size_t)n_taps * KC * Cout * rowb;
@@ -758,7 +772,7 @@ extern "C" int rss_conv_cf(const void* x, const void* w_packed, void* y, int B, 
         const CfGeom& g = pl.g;
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-        cuuint32_t box[4] = {(cuuint32_t)(Cin == 32 ? 32 : 64), (cuuint32_t)g.Wp, (cuuint32_t)g.NR, 1};
+        cuuint32_t box[4] = {(cuuint32_t)(Cin == 32 ? 32 : 64), (cuuint32_t)g.box_w, (cuuint32_t)(g.xsplit == 1 ? g.NR : 1), 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, Cin == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,

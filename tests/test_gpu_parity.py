@@ -695,6 +695,7 @@ CF_CASES = [
     (2, 12, 20, 128, 64, 1, False, True),
     (16, 128, 128, 32, 32, 3, True, True),     # the benched branch-0 layer: 1040 tiles over 148 persistent CTAs, 2-stage ring wraps
     (16, 64, 64, 64, 64, 3, True, True),       # the benched branch-1 layer
+    (2, 40, 256, 32, 32, 3, True, True),       # cfg5 width (1024x1024 tiles: branch 0 is 256 wide): rows fetched as two TMA boxes
 ]
 
 
@@ -757,6 +758,7 @@ CF_EPI_CASES = [
     (2, 19, 23, 32, 3, False, False, True, False),     # plain BN+ReLU: mask recomputed from z and the affine
     (2, 16, 16, 64, 3, True, False, False, True),      # BN without activation (fuse/downsample layers)
     (16, 128, 128, 32, 3, True, True, True, False),    # benched geometry
+    (1, 24, 256, 32, 3, True, False, True, False),     # cfg5 width
     (4, 64, 64, 64, 3, False, False, True, False),
 ]
 
@@ -1027,6 +1029,52 @@ def test_two_rank_data_parallel_equivalence(P, report):
                        capture_output=True, text=True, timeout=900)
     report["dist_check_2gpu"] = r.stdout[-400:]
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_eval_side_tta_and_pixel_metric(P, report):
+    """the bilinear (align_corners=True) resize kernel vs F.interpolate, test-time augmentation
+    (module/tta.py:12-24 with the Scale transforms of eval.py:55-62) vs the same loop in torch, and the device confusion matrix vs
+    a host bincount (train.py:47-49 semantics: ignore_index pixels skipped)."""
+    torch.manual_seed(23)
+    errs = {}
+    x = torch.randn(2, 7, 37, 53, device=DEV)
+    for size in ((74, 106), (19, 26), (37, 53), (128, 31)):
+        got = P.evalops.bilinear_resize(x, size)
+        want = torch.nn.functional.interpolate(x, size=size, mode="bilinear", align_corners=True)
+        errs["resize_%dx%d" % size] = rel(got, want)
+    acc = torch.randn(2, 7, 74, 106, device=DEV)
+    want = 0.25 * torch.nn.functional.interpolate(x, size=(74, 106), mode="bilinear", align_corners=True) + acc
+    errs["resize_axpby"] = rel(P.evalops.bilinear_resize(x, (74, 106), acc.clone(), alpha=0.25, beta=1.0), want)
+    # TTA through the real model (fp32 activations), scales as in eval.py:55-62 reduced to three
+    m = _model(P, torch.float32).eval()
+    img, lbl = R.synth_batch(1, 128)
+    img = img.to(DEV)
+    scales = (0.5, 1.0, 1.5)
+    got = P.tta(m, img, [P.Scale(scale_factor=s) for s in scales])
+    with torch.no_grad():
+        outs = []
+        for s in scales:
+            im = torch.nn.functional.interpolate(img, scale_factor=s, mode="bilinear", align_corners=True)
+            outs.append(torch.nn.functional.interpolate(m(im), size=img.shape[2:], mode="bilinear", align_corners=True))
+        want = sum(outs) / len(outs)
+    errs["tta"] = rel(got, want)
+    # pixel metric
+    K = 7
+    pm = P.PixelMetric(K)
+    truth = torch.randint(-1, K, (3, 64, 80), device=DEV)
+    pred = torch.randint(0, K, (3, 64, 80), device=DEV)
+    pm.forward(truth, pred)
+    pm.forward(truth[:1], pred[:1])
+    valid = truth != -1
+    ref_cm = torch.bincount(truth[valid] * K + pred[valid], minlength=K * K) + \
+        torch.bincount(truth[:1][valid[:1]] * K + pred[:1][valid[:1]], minlength=K * K)
+    assert torch.equal(pm.cm, ref_cm), "confusion matrix must be exact"
+    s = pm.summary_all()
+    cm = ref_cm.view(K, K).double().cpu()
+    tp = cm.diag()
+    errs["miou"] = abs(s["miou"] - float((tp / (cm.sum(0) + cm.sum(1) - tp)).mean()))
+    report["eval_side"] = errs
+    assert max(errs.values()) < 1e-5, errs
 
 
 def test_flat_sgd_state_dict_resume(P, report):
