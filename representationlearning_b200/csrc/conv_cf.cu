@@ -617,14 +617,16 @@ static int cf_plan(int B, int H, int W, int Cin, int Cout, int n_taps, const int
         if (b > halo) halo = b;
     }
     if (halo > 1) return RSS_ERR_SHAPE;
-    g.halo = halo; g.Wp = W + 2 * halo; g.Q = H * g.Wp;
+    g.halo = halo; g.Wp = W + 2 * halo;
+    if (g.Wp > 256) g.Wp = (g.Wp + 15) & ~15;      // two TMA boxes per staged row (below): both must start on a swizzle-atom boundary
+    g.Q = H * g.Wp;
     g.wp_magic = (unsigned int)((0x100000000ull + (unsigned)g.Wp - 1) / (unsigned)g.Wp);
     g.dbg = 0;
     if (g.Wp < 8) return RSS_ERR_SHAPE;                                       // <= 32 row segments per 128-position block
     g.xsplit = 1; g.box_w = g.Wp;
     if (g.Wp > 256) {                                                         // TMA box dimension limit: split every row in two boxes
-        if (g.Wp > 512 || (g.Wp & 1)) return RSS_ERR_SHAPE;
-        g.xsplit = 2; g.box_w = g.Wp / 2;
+        if (g.Wp > 512) return RSS_ERR_SHAPE;                                 // (the pitch was rounded up to 16 positions: the extra
+        g.xsplit = 2; g.box_w = g.Wp / 2;                                     //  columns are dead positions like the padding ones)
     }
     for (int t = 0; t < kCfMaxTaps; ++t) g.tap_off[t] = t < n_taps ? dy[t] * g.Wp + dx[t] : 0;
     const int KC = (Cin + 63) / 64, rowb = Cin == 32 ? 64 : 128;
