@@ -151,20 +151,6 @@ int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, const float* 
                      const float* local_sums /*this rank's sums (== sums without SyncBN)*/,
                      float* dgamma_acc /*may be NULL*/, float* dbeta_acc, cudaStream_t stream);
 
-/* One-launch BatchNorm(+ReLU)(+residual) for the small L2-resident activations (C >= 64, C % 16 == 0, <= 12 MB, no GELU): a thread-
- * block cluster of 8 CTAs owns 16 channels over all rows, partial sums are exchanged through distributed shared memory around
- * hardware cluster barriers -- no atomics, tickets or scratch, deterministic.  Same results / outputs as rss_bn_stats_fused +
- * rss_bn_act_fwd (forward) and rss_bn_bwd_reduce_ws + rss_bn_bwd_apply (backward; sums_out [2C] optional, dgamma/dbeta accumulate). */
-int rss_bn_cluster_supported(int64_t rows, int C, int act, int dtype);
-int rss_bn_cluster_fwd(const void* x, const void* residual /*may be NULL*/, void* y, int64_t rows, int C, int act, int dtype,
-                       const float* gamma, const float* beta, float* running_mean /*may be NULL*/, float* running_var, float momentum,
-                       float eps, float* mean_out, float* invstd_out, float* scale, float* shift, const float* pre_bias /*may be NULL*/,
-                       cudaStream_t stream);
-int rss_bn_cluster_bwd(const void* x, const void* y /*saved output, residual ReLU layers only*/, const void* dy, const float* scale,
-                       const float* shift, const float* mean, const float* invstd, void* dx, void* dresidual /*may be NULL*/,
-                       int64_t rows, int C, int act, int dtype, float* sums_out /*may be NULL*/, float* dgamma_acc /*may be NULL*/,
-                       float* dbeta_acc, cudaStream_t stream);
-
 /* One-launch versions for activations that stay L2-resident between the two passes (<= 40 MB, ReLU / no activation):
  * statistics -> device-wide spin barrier -> apply, and reduce -> barrier -> apply.  Grid <= one block per SM, >= 4 resident blocks
  * per SM, so up to 4 concurrent streams can each hold a full grid.  accum_scratch: persistent zeroed float[2*C]; sync_scratch:

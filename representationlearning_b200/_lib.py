@@ -68,9 +68,6 @@ SIGNATURES = {
     "rss_bn_bwd_apply_raw": (c_int, [P, P, P, P, P, P, P, P, P, c_float, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
     "rss_bn_bwd_apply_dz": (c_int, [P, P, P, P, P, P, c_float, P, c_int64, c_int, c_int, P, P, P, P]),
     "rss_bn_bwd_apply": (c_int, [P, P, P, P, P, P, P, P, c_float, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
-    "rss_bn_cluster_supported": (c_int, [c_int64, c_int, c_int, c_int]),
-    "rss_bn_cluster_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P, c_float, c_float, P, P, P, P, P, P]),
-    "rss_bn_cluster_bwd": (c_int, [P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
     "rss_bn_fused_supported": (c_int, [c_int64, c_int, c_int, c_int]),
     "rss_bn_fwd_fused": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P, c_float, c_float, P, P, P, P, P, P]),
     "rss_bn_bwd_fused": (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),

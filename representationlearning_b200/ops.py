@@ -17,7 +17,7 @@ CL = torch.channels_last
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; counted from the csrc/*.cu launch sites)
 KERNELS_PER_CALL = {
     "rss_layernorm_fwd": 1, "rss_layernorm_bwd": 1, "rss_attn_fwd": 5, "rss_spatial_attention_fwd": 2, "rss_bilinear_resize": 1, "rss_confusion_matrix": 1, "rss_accum_bf16_list": 1, "rss_attn_bwd": 7, "rss_bn_stats": 1, "rss_bn_combine": 1,
-    "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1, "rss_bn_fwd_fused": 1, "rss_bn_bwd_fused": 1, "rss_bn_cluster_fwd": 1, "rss_bn_cluster_bwd": 1,
+    "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1, "rss_bn_fwd_fused": 1, "rss_bn_bwd_fused": 1,
     "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 4, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
     "rss_headaux_fwd": 2, "rss_seg_loss_fwd": 2, "rss_seg_loss_bwd": 1, "rss_grad_sumsq": 1, "rss_sgd_step": 1,
     "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_conv_wgrad": 1, "rss_conv_wgrad_tc": 1, "rss_conv_cf": 1, "rss_shadow_t_refresh": 1, "rss_shadow_cl_refresh": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
@@ -107,8 +107,10 @@ import os
 # split kernels, 382 vs 418 img/s -- so it is OFF by default; the kernels stay in the library (tests run them) for round 2.
 BN_FUSED = {"on": os.environ.get("RSS_BN_FUSED", "0") != "0"}
 BN_KEEP_DZ = {"on": os.environ.get("RSS_BN_KEEP_DZ", "1") != "0"}
-# one-launch cluster kernels (csrc/bn_cluster.cu) for the small L2-resident BatchNorm layers (C >= 64, <= 12 MB, ReLU / none)
-BN_CLUSTER = {"on": os.environ.get("RSS_BN_CLUSTER", "0") != "0"}
+# (round 2 also tried one-launch BatchNorm with 8-CTA thread-block clusters per 16-channel slice exchanging partial sums through
+#  distributed shared memory -- no atomics, no tickets: correct, but 37-52 us vs 14-15 us for the two split kernels on the 8.4 MB
+#  branch-1 tensors and no better on 2-4 MB ones (32-byte row slices at a 128-512 byte stride from 32-128 CTAs are L2-latency
+#  bound); removed again, numbers in profiles/bn_cluster_vs_split_r2.txt, code in the history at commit "Cluster/DSMEM ...")
 # "raw" BatchNorm protocol (csrc/bn.cu BnFin): the statistics / reduce kernels only add their sums into the layer's scratch and
 # the apply kernels finalise -- fewer dependent global round trips per layer
 # Measured on the B=16 step (gpurun 2026-10-17, timeline_s3f): statistics -3.3 us and reduce -2.1 us per layer, but the "last block
@@ -260,19 +262,6 @@ class BNAct(torch.autograd.Function):
             if not training:
                 raise _lib.RssError("pre_bias folding is only valid for training-mode BatchNorm")
             pre_bias = _f32(pre_bias)
-        cluster = (BN_CLUSTER["on"] and training and world == 1 and not have_aff and not BN_FUSED["on"] and not BN_RAW["on"]
-                   and bool(lib.rss_bn_cluster_supported(rows, C, act, dt)))
-        if cluster:
-            y = torch.empty_like(x, memory_format=CL)
-            account("bn", x, x, residual, y)
-            check(lib.rss_bn_cluster_fwd(_p(x), _p(residual), _p(y), rows, C, act, dt, _p(g), _p(b), _p(running_mean), _p(running_var),
-                                         momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), _p(pre_bias), st), "rss_bn_cluster_fwd")
-            ctx.fused, ctx.scratch, ctx.cluster = False, scratch, True
-            ctx.save_for_backward(x, y if (act == _lib.ACT_RELU and residual is not None) else None, aff)
-            ctx.act, ctx.training, ctx.group, ctx.world, ctx.has_res = act, training, group, world, residual is not None
-            ctx.refs = (gamma, beta)
-            return y
-        ctx.cluster = False
         fused = BN_FUSED["on"] and training and world == 1 and bool(lib.rss_bn_fused_supported(rows, C, act, dt))
         if fused and (scratch is None or scratch.numel() < 2 + 2 * C):
             scratch = torch.zeros(2 + 2 * C, device=dev, dtype=torch.float32)   # [0:2] barrier counters, [2:] accumulators; left zeroed
@@ -344,14 +333,6 @@ class BNAct(torch.autograd.Function):
         dx = torch.empty_like(x, memory_format=CL)
         dres = torch.empty_like(x, memory_format=CL) if ctx.has_res else None
         account("bn", x, dy, y, x, dy, y, dx, dres)                                   # reduce pass + apply pass
-        if ctx.cluster:                     # reduce + apply in ONE launch (thread-block clusters, csrc/bn_cluster.cu)
-            local = None if direct else torch.empty(2 * C, device=x.device, dtype=torch.float32)
-            check(lib.rss_bn_cluster_bwd(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(dx), _p(dres), rows, C,
-                                         ctx.act, dt, _p(local), _p(sg) if direct else None, _p(sb) if direct else None, st),
-                  "rss_bn_cluster_bwd")
-            if direct:
-                return (dx, dres) + (None,) * 12
-            return (dx, dres, local[C:], local[:C]) + (None,) * 10
         if ctx.fused:                       # reduce + apply in ONE launch (training mode, single rank, L2-resident tensor)
             local = None if direct else torch.empty(2 * C, device=x.device, dtype=torch.float32)
             sc = ctx.scratch
