@@ -29,7 +29,8 @@ WGRAD = {"async": os.environ.get("RSS_WGRAD_STREAM", "1") != "0", "streams": {},
 WGRAD["n"] = max(1, int(os.environ.get("RSS_WGRAD_STREAMS", "2")))
 # RSS_WGRAD_AFTER_DGRAD=1: issue the data gradient (on the critical chain) before forking the weight gradient, so the side stream
 # waits for it instead of competing with it for SMs
-WGRAD["after_dgrad"] = os.environ.get("RSS_WGRAD_AFTER_DGRAD", "0") != "0"
+# (round 2, with the fused branch-0 blocks: 513.4 img/s with it vs 507-510 without -> on by default)
+WGRAD["after_dgrad"] = os.environ.get("RSS_WGRAD_AFTER_DGRAD", "1") != "0"
 
 
 def wgrad_stream(dev):

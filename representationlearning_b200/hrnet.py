@@ -118,19 +118,20 @@ class _BasicBlockFn(torch.autograd.Function):
         ops.check(lib.rss_bn_bwd_apply(p(z2), p(out), p(dout), p(aff2[2]), p(aff2[3]), p(aff2[0]), p(aff2[1]), p(sums2), 1.0 / rows,
                                        p(dz2), p(dres), rows, C, relu, dt, p(sums2), p(blk.bn2.weight.grad), p(blk.bn2.bias.grad), st),
                   "rss_bn_bwd_apply")
-        convmod._wgrad(dz2, a1, convmod.lowp_cl(blk.conv2.weight, x.dtype), blk.conv2.weight, None, False, 1, 1, 1, blk.conv2.weight.dtype)
+        # (weight gradients are issued AFTER the data-gradient kernel they could compete with: the side stream then waits for it)
         # conv2 data gradient; its epilogue applies bn1's ReLU mask and reduces bn1's backward sums
         w2, n2, dy2, dx2, ws2, k2 = convmod.cf_weight(blk.conv2.weight, True)
         g1, sums1 = convmod._cf_launch(dz2, w2, n2, dy2, dx2, C, C, None, False, None, bnred=(z1, None, aff1, True, blk.bn1._scratch),
                                        wstrides=ws2)
+        convmod._wgrad(dz2, a1, convmod.lowp_cl(blk.conv2.weight, x.dtype), blk.conv2.weight, None, False, 1, 1, 1, blk.conv2.weight.dtype)
         dz1 = torch.empty_like(x, memory_format=ops.CL)
         ops.check(lib.rss_bn_bwd_apply(p(z1), None, p(g1), p(aff1[2]), p(aff1[3]), p(aff1[0]), p(aff1[1]), p(sums1), 1.0 / rows,
                                        p(dz1), None, rows, C, relu, dt, p(sums1), p(blk.bn1.weight.grad), p(blk.bn1.bias.grad), st),
                   "rss_bn_bwd_apply")
-        convmod._wgrad(dz1, x, convmod.lowp_cl(blk.conv1.weight, x.dtype), blk.conv1.weight, None, False, 1, 1, 1, blk.conv1.weight.dtype)
         # conv1 data gradient + the residual-path gradient in the epilogue
         w1, n1, dy1, dx1, ws1, k1 = convmod.cf_weight(blk.conv1.weight, True)
         dx, _ = convmod._cf_launch(dz1, w1, n1, dy1, dx1, C, C, None, False, None, add=dres, wstrides=ws1)
+        convmod._wgrad(dz1, x, convmod.lowp_cl(blk.conv1.weight, x.dtype), blk.conv1.weight, None, False, 1, 1, 1, blk.conv1.weight.dtype)
         return dx, None
 
 
