@@ -193,17 +193,22 @@ FAMILIES = (
 )
 
 
-def cupti_step_summary(run_step, n=2):
+def cupti_step_summary(run_step, n=2, profile_here=True):
     """per-kernel durations of the REPLAYED step (CUPTI through torch.profiler): {name: (total_us, count)} averaged over n replays.
-    Durations under the profiler are used for shares and per-launch kernel times only, never for the bench value."""
+    Durations under the profiler are used for shares and per-launch kernel times only, never for the bench value.
+    EVERY rank must call this (the step contains collectives); only the rank with profile_here=True records."""
+    import contextlib
     import torch
     from torch.profiler import ProfilerActivity, profile
     run_step()
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    ctx = profile(activities=[ProfilerActivity.CUDA]) if profile_here else contextlib.nullcontext()
+    with ctx as prof:
         for _ in range(n):
             run_step()
         torch.cuda.synchronize()
+    if not profile_here:
+        return None
     per = {}
     for e in prof.key_averages():
         t = getattr(e, "device_time_total", None)
@@ -232,7 +237,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = "cfg2: RSSFormer(hrnetv2_w32) train step, %d tiles/GPU of %dx%d, synthetic LoveDA-shape" % (args.batch, args.size, args.size)
+    global METRIC, FLOP_PER_IMG_TRAIN
+    cfg = "cfg2" if args.size == 512 else ("cfg5" if args.size == 1024 else "custom")
+    workload = "%s: RSSFormer(hrnetv2_w32) train step, %d tiles/GPU of %dx%d, synthetic LoveDA-shape" % (cfg, args.batch, args.size, args.size)
+    if args.size != 512:        # BASELINE cfg5 (1024x1024 large tiles, 4 per GPU): same step, its own metric name and FLOP count
+        METRIC = "RSSFormer %dx%d bf16 training images/sec" % (args.size, args.size)
+        FLOP_PER_IMG_TRAIN = 2111.09e9 if args.size == 1024 else FLOP_PER_IMG_TRAIN * (args.size / 512.0) ** 2
 
     if args.impl == "reference":
         # the reference's own CPU implementation on the host cores: each step = a bounded SAMPLE of the workload (4 of the 16 tiles,
@@ -361,9 +371,9 @@ def main():
         return 0
 
     fam = None
-    if not args.no_cupti and rank == 0:
+    if not args.no_cupti:
         try:
-            fam = cupti_step_summary(run_step)
+            fam = cupti_step_summary(run_step, profile_here=(rank == 0))      # all ranks replay: the step contains collectives
         except Exception as e:  # noqa: BLE001
             fam = None
             sys.stderr.write("CUPTI summary failed: %r\n" % (e,))

@@ -116,8 +116,10 @@ def _own_wgrad_ok(dy, x, weight, want_b, stride, padding, dilation):
     return bool(_lib.load().rss_conv_wgrad_supported(Cin, Cout, k, stride, padding, dilation))
 
 
-def _wgrad(dy, x, w_lp, weight, bias, want_b, stride, padding, dilation, wdtype):
-    """weight (+bias) gradient, accumulated into the flat fp32 grad buffer when there is one; returns (dw, db) to hand back
+def _wgrad(dy, x, w_lp, weight, bias, want_b, stride, padding, dilation, wdtype, make_x=None):
+    """make_x: optional callable run on the weight-gradient stream right before the kernel, returning the activation `x` (used by
+    the fused BasicBlock, which never materialises relu(bn1(.)) in the forward pass and re-creates it here, off the critical chain)
+    weight (+bias) gradient, accumulated into the flat fp32 grad buffer when there is one; returns (dw, db) to hand back
     through autograd (None when already accumulated).  Engine: csrc/conv_wgrad.cu (split-K mma kernel, float atomics straight
     into the fp32 gradient) for the HRNet-family shapes, the library's wgrad otherwise."""
     own = _own_wgrad_ok(dy, x, weight, want_b, stride, padding, dilation)
@@ -157,6 +159,9 @@ def _wgrad(dy, x, w_lp, weight, bias, want_b, stride, padding, dilation, wdtype)
         return dw, db
 
     def run():
+        nonlocal x
+        if make_x is not None:
+            x = make_x()
         if not own:
             return run_lib()
         sink = ops.grad_sink(weight)

@@ -32,6 +32,13 @@ static inline int bn_apply_bpsm() {
     if (v == 0) { const char* e = getenv("RSS_BN_APPLY_BPSM"); v = e ? atoi(e) : 8; if (v < 1 || v > 16) v = 8; }
     return v;
 }
+// the ticket kernels on BIG tensors (the 67 MB hidden activations of the FFN): 2 blocks per SM keep only ~32 KB of loads in flight per
+// SM (statistics pass: 37 us for a 67 MB read = 1.8 TB/s, ncu: 27 % of DRAM throughput); there the ticket tail is noise next to the
+// streaming time, so they get the apply kernels' grid
+static inline int bn_ticket_bpsm_for(int64_t rows, int C, int dtype) {
+    const int64_t bytes = rows * C * (dtype == RSS_F32 ? 4 : 2);
+    return bytes >= ((int64_t)24 << 20) ? bn_apply_bpsm() : bn_ticket_bpsm();
+}
 static inline int bn_grid(int64_t rows, int rpb, int per_sm) {
     int64_t g = (rows + rpb - 1) / rpb;
     const int64_t cap = (int64_t)num_sms() * per_sm;
@@ -886,7 +893,7 @@ extern "C" int rss_bn_stats_fused(const void* x, float* accum_scratch, unsigned 
                                   const float* pre_bias, cudaStream_t st) {
     if (C <= 0 || C % 8 || C > 2048 || rows <= 0 || !ticket || !accum_scratch) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 8, bn_ticket_bpsm());
+    const int grid = bn_grid(rows, g.rpb * 8, bn_ticket_bpsm_for(rows, C, dtype));
     const size_t smem = (size_t)g.rpb * C * 2 * sizeof(float);
     RSS_DISPATCH_DTYPE(dtype, launch_k(bn_stats_fused_kernel<T>, grid, g.threads, smem, st, (const T*)x, accum_scratch, ticket, rows, C, g.cg, g.rpb,
                        gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out, scale, shift, pre_bias));
@@ -978,7 +985,7 @@ extern "C" int rss_bn_bwd_reduce_ws(const void* x, const void* y, const void* dy
                                     void* dz_out, int64_t rows, int C, int act, int dtype, cudaStream_t st) {
     if (C <= 0 || C % 8 || rows <= 0 || (ticket && !accum_scratch)) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 8, bn_ticket_bpsm());
+    const int grid = bn_grid(rows, g.rpb * 8, bn_ticket_bpsm_for(rows, C, dtype));
     const size_t smem = (size_t)g.rpb * 2 * C * sizeof(float);
     if (!accum_scratch) {
         cudaError_t e = cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st);

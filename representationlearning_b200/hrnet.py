@@ -63,7 +63,15 @@ def _run(conv, bn, x, residual=None):
 #             -> bn1 backward apply -> conv1 data gradient whose epilogue adds the residual-path gradient; weight gradients on the
 #             side streams.  7 chain kernels -> 5, no library conv, no autograd accumulation kernel.
 BLOCK_FUSED = {"on": os.environ.get("RSS_BLOCK_FUSED", "1") != "0",
-               "channels": tuple(int(c) for c in os.environ.get("RSS_BLOCK_FUSED_C", "32").split(",") if c)}
+               "channels": tuple(int(c) for c in os.environ.get("RSS_BLOCK_FUSED_C", "32").split(",") if c),
+               # xform: conv2 applies bn1+ReLU to its staged input tile instead of reading a materialised activation
+               "xform": os.environ.get("RSS_BLOCK_XFORM", "0") != "0",
+               # chain: the last kernel of block k+1's backward (conv1 data gradient + residual gradient) also masks with block k's
+               # output ReLU and reduces block k's bn2 backward sums, so block k starts with its apply pass
+               "chain": os.environ.get("RSS_BLOCK_CHAIN", "0") != "0"}
+# Both variants are bit-checked (test_fused_block_chain_vs_unfused) and OFF by default: measured on the B=16 step (gpurun 2026-10-17,
+# profiles/ab_block_variants_r2.txt) 506.3 img/s with both, 506.5 xform only, 507.6 chain only, 510.0 with neither -- the in-place
+# transform pass and the extra epilogue operands cost what the removed bn_act / bn_bwd_reduce launches saved.
 
 
 class _BasicBlockFn(torch.autograd.Function):
@@ -78,12 +86,16 @@ class _BasicBlockFn(torch.autograd.Function):
         rows, dt, st = B * H * W, _lib.RSS_BF16, ops._st()
         w1, n1, dy1, dx1, ws1, k1 = convmod.cf_weight(blk.conv1.weight, False)
         z1, aff1 = convmod._cf_launch(x, w1, n1, dy1, dx1, C, C, None, False, blk.bn1.stats_args(), wstrides=ws1)
-        a1 = torch.empty_like(x, memory_format=ops.CL)
-        ops.account("bn", z1, a1)
-        ops.check(lib.rss_bn_act_fwd(z1.data_ptr(), None, a1.data_ptr(), aff1[2].data_ptr(), aff1[3].data_ptr(), rows, C, _lib.ACT_RELU,
-                                     dt, st), "rss_bn_act_fwd")
         w2, n2, dy2, dx2, ws2, k2 = convmod.cf_weight(blk.conv2.weight, False)
-        z2, aff2 = convmod._cf_launch(a1, w2, n2, dy2, dx2, C, C, None, False, blk.bn2.stats_args(), wstrides=ws2)
+        if BLOCK_FUSED["xform"]:
+            a1 = None                                  # relu(bn1(z1)) exists only inside conv2's staged tiles
+            z2, aff2 = convmod._cf_launch(z1, w2, n2, dy2, dx2, C, C, aff1, True, blk.bn2.stats_args(), wstrides=ws2)
+        else:
+            a1 = torch.empty_like(x, memory_format=ops.CL)
+            ops.account("bn", z1, a1)
+            ops.check(lib.rss_bn_act_fwd(z1.data_ptr(), None, a1.data_ptr(), aff1[2].data_ptr(), aff1[3].data_ptr(), rows, C, _lib.ACT_RELU,
+                                         dt, st), "rss_bn_act_fwd")
+            z2, aff2 = convmod._cf_launch(a1, w2, n2, dy2, dx2, C, C, None, False, blk.bn2.stats_args(), wstrides=ws2)
         out = torch.empty_like(x, memory_format=ops.CL)
         ops.account("bn", z2, x, out)
         ops.check(lib.rss_bn_act_fwd(z2.data_ptr(), x.data_ptr(), out.data_ptr(), aff2[2].data_ptr(), aff2[3].data_ptr(), rows, C,
@@ -93,6 +105,12 @@ class _BasicBlockFn(torch.autograd.Function):
                 bn.num_batches_tracked += 1
         ctx.save_for_backward(x, z1, a1, z2, out, aff1, aff2)
         ctx.blk = blk
+        # hand-off for the chained backward: the producer of x (the previous fused block of this branch) left its bn2 context on the
+        # tensor; this block's last backward kernel will do that block's bn2 masking + reduction and leave the sums in `box`
+        ctx.prev = getattr(x, "_rss_bn2_ctx", None) if BLOCK_FUSED["chain"] else None
+        ctx.box = {}
+        if BLOCK_FUSED["chain"]:
+            out._rss_bn2_ctx = (z2, aff2, blk.bn2._scratch, ctx.box)
         return out
 
     @staticmethod
@@ -111,8 +129,11 @@ class _BasicBlockFn(torch.autograd.Function):
         sc2 = blk.bn2._scratch
         sums2 = torch.empty(2 * C, device=x.device, dtype=torch.float32)
         ops.account("bn", z2, out, dout, z2, out, dout, x, x, z1, x, x)      # bn2 reduce + apply (2 outputs), bn1 apply (z1, g1 -> dz1)
-        ops.check(lib.rss_bn_bwd_reduce_ws(p(z2), p(out), p(dout), p(aff2[2]), p(aff2[3]), p(aff2[0]), p(aff2[1]), p(sums2), p(sc2[2:]),
-                                           p(sc2), None, rows, C, relu, dt, st), "rss_bn_bwd_reduce")
+        if "sums" in ctx.box:          # the next block's last backward kernel already masked dout and reduced (sum g, sum g*xhat)
+            sums2 = ctx.box.pop("sums")
+        else:
+            ops.check(lib.rss_bn_bwd_reduce_ws(p(z2), p(out), p(dout), p(aff2[2]), p(aff2[3]), p(aff2[0]), p(aff2[1]), p(sums2), p(sc2[2:]),
+                                               p(sc2), None, rows, C, relu, dt, st), "rss_bn_bwd_reduce")
         dz2 = torch.empty_like(x, memory_format=ops.CL)
         dres = torch.empty_like(x, memory_format=ops.CL)
         ops.check(lib.rss_bn_bwd_apply(p(z2), p(out), p(dout), p(aff2[2]), p(aff2[3]), p(aff2[0]), p(aff2[1]), p(sums2), 1.0 / rows,
@@ -123,14 +144,27 @@ class _BasicBlockFn(torch.autograd.Function):
         w2, n2, dy2, dx2, ws2, k2 = convmod.cf_weight(blk.conv2.weight, True)
         g1, sums1 = convmod._cf_launch(dz2, w2, n2, dy2, dx2, C, C, None, False, None, bnred=(z1, None, aff1, True, blk.bn1._scratch),
                                        wstrides=ws2)
-        convmod._wgrad(dz2, a1, convmod.lowp_cl(blk.conv2.weight, x.dtype), blk.conv2.weight, None, False, 1, 1, 1, blk.conv2.weight.dtype)
+        make_a1 = None
+        if a1 is None:                 # re-create relu(bn1(z1)) on the weight-gradient stream, off the critical chain
+            def make_a1():
+                t = torch.empty_like(z1, memory_format=ops.CL)
+                ops.check(lib.rss_bn_act_fwd(p(z1), None, p(t), p(aff1[2]), p(aff1[3]), rows, C, relu, dt, ops._st()), "rss_bn_act_fwd")
+                return t
+        convmod._wgrad(dz2, z1 if a1 is None else a1, convmod.lowp_cl(blk.conv2.weight, x.dtype), blk.conv2.weight, None, False, 1, 1, 1,
+                       blk.conv2.weight.dtype, make_x=make_a1)
         dz1 = torch.empty_like(x, memory_format=ops.CL)
         ops.check(lib.rss_bn_bwd_apply(p(z1), None, p(g1), p(aff1[2]), p(aff1[3]), p(aff1[0]), p(aff1[1]), p(sums1), 1.0 / rows,
                                        p(dz1), None, rows, C, relu, dt, p(sums1), p(blk.bn1.weight.grad), p(blk.bn1.bias.grad), st),
                   "rss_bn_bwd_apply")
         # conv1 data gradient + the residual-path gradient in the epilogue
         w1, n1, dy1, dx1, ws1, k1 = convmod.cf_weight(blk.conv1.weight, True)
-        dx, _ = convmod._cf_launch(dz1, w1, n1, dy1, dx1, C, C, None, False, None, add=dres, wstrides=ws1)
+        if ctx.prev is not None:       # x is the previous fused block's output: its bn2 backward reduction rides in this epilogue
+            pz2, paff2, pscratch, pbox = ctx.prev
+            dx, psums = convmod._cf_launch(dz1, w1, n1, dy1, dx1, C, C, None, False, None, add=dres,
+                                           bnred=(pz2, x, paff2, True, pscratch), wstrides=ws1)
+            pbox["sums"] = psums
+        else:
+            dx, _ = convmod._cf_launch(dz1, w1, n1, dy1, dx1, C, C, None, False, None, add=dres, wstrides=ws1)
         convmod._wgrad(dz1, x, convmod.lowp_cl(blk.conv1.weight, x.dtype), blk.conv1.weight, None, False, 1, 1, 1, blk.conv1.weight.dtype)
         return dx, None
 

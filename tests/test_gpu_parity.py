@@ -870,6 +870,47 @@ def test_fused_basic_block_vs_unfused(P, report, shape):
     assert max(v for k, v in errs.items() if k not in ("out", "dx", "dx_frac_off", "out_max")) < 5e-2, errs
 
 
+@pytest.mark.parametrize("xform,chain", [(True, True), (False, True), (True, False)])
+def test_fused_block_chain_vs_unfused(P, report, xform, chain):
+    """a branch of 3 fused BasicBlocks (hrnet._BasicBlockFn): conv2 applying bn1+ReLU to its staged input tile (xform) and the last
+    backward kernel of block k+1 doing block k's bn2 masking + reduction (chain), against the layer-by-layer library path."""
+    from representationlearning_b200 import conv, hrnet, trainer
+    B, C, H, W = 4, 32, 40, 56
+    torch.manual_seed(31)
+    x = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    dout = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    res = {}
+    saved = dict(hrnet.BLOCK_FUSED)
+    try:
+        for mode in ("fused", "unfused"):
+            torch.manual_seed(6)
+            net = torch.nn.Sequential(*[hrnet.BasicBlock(C, C) for _ in range(3)]).to(DEV).train()
+            with torch.no_grad():
+                for m in net.modules():
+                    if isinstance(m, P.FusedBNAct):
+                        m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.3)
+            opt = trainer.FlatSGD(net)
+            hrnet.BLOCK_FUSED.update(on=(mode == "fused"), channels=(32,), xform=xform, chain=chain)
+            xi = nchw_from(x).requires_grad_(True)
+            out = net(xi)
+            out.backward(nchw_from(dout))
+            conv.join_wgrad()
+            torch.cuda.synchronize()
+            res[mode] = dict(out=out.float(), dx=xi.grad.float(), **{n: p.grad.clone() for n, p in net.named_parameters()})
+            for m in net.modules():
+                if isinstance(m, P.FusedBNAct):
+                    assert float(m._scratch.abs().max()) == 0.0
+    finally:
+        hrnet.BLOCK_FUSED.update(saved)
+
+    def l2(a, b):
+        a, b = a.double(), b.double()
+        return float((a - b).norm() / (b.norm() + 1e-30))
+    errs = {k: l2(res["fused"][k], res["unfused"][k]) for k in res["fused"]}
+    report["fused_chain_x%d_c%d" % (xform, chain)] = errs
+    assert errs["out"] < 1e-2 and max(errs.values()) < 8e-2, errs          # (ReLU-mask flips accumulate over 6 BatchNorm layers)
+
+
 def test_conv_cf_block_through_autograd(P, report):
     """conv_bn_stats -> FusedBNAct(aff=...) forward and backward: data gradient through the transposed pack of the same kernel,
     weight gradient through conv_wgrad.cu.  bf16 rounding of the conv output flips ReLU masks relative to an fp32 chain (a CPU
