@@ -518,6 +518,21 @@ class HighResolutionNet(nn.Module):
         x_list = self._next_inputs(self.transition2, y_list, self.stage3_cfg["num_branches"])
         y_list = self._stage(self.stage3, x_list)
         x_list = self._next_inputs(self.transition3, y_list, self.stage4_cfg["num_branches"])
+        # trainer.FlatSGD (world > 1) sets _stage4_hook: called once per backward pass when the gradients of ALL stage-4 inputs exist,
+        # i.e. when every backward node of stage 4, the neck and the head has been issued -- their gradients (a contiguous tail of
+        # the flat buffer) can be all-reduced while stages 3..1 are still differentiating
+        fn = getattr(self, "_stage4_hook", None)
+        if fn is not None and torch.is_grad_enabled():
+            ts = [t for t in x_list if t.requires_grad]
+            left = {"n": len(ts)}
+
+            def _cb(g):
+                left["n"] -= 1
+                if left["n"] == 0:
+                    fn()
+                return g
+            for t in ts:
+                t.register_hook(_cb)
         y_list = self._stage(self.stage4, x_list)
         return flow_join(y_list) if _dataflow(y_list[0]) else y_list
 

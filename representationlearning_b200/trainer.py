@@ -69,9 +69,22 @@ class FlatSGD:
             if isinstance(m, FusedBNAct):
                 m.defer_counter = True                      # instance attribute: other models in the process keep counting themselves
                 self._bn_counters.append(m.num_batches_tracked)
+        self._tail_off, self._early_done, self._comm, self._group = None, False, None, None
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and dev.type == "cuda":
             dist.broadcast(self.flat_p, src=0)              # replicas must start identical (DDP does this in its constructor)
             self.sync_shadows()
+            # overlapped gradient all-reduce: parameters are laid out in module order, the backward pass produces gradients in reverse
+            # order, so [first stage-4 parameter : end] (stage 4 + neck + head, ~2/3 of the bytes) is final when stage 4 has been
+            # differentiated; HighResolutionNet._stage4_hook fires there and that tail is all-reduced on a side stream under stages 3..1
+            import os
+            from . import hrnet
+            first = next((o for n, o in zip(self.names, self.offsets) if ".stage4." in n), None)
+            if first is not None and os.environ.get("RSS_EARLY_ALLREDUCE", "1") != "0":
+                nets = [m for m in model.modules() if isinstance(m, hrnet.HighResolutionNet)]
+                if len(nets) == 1:
+                    self._tail_off = first
+                    self._comm = torch.cuda.Stream(dev)
+                    nets[0]._stage4_hook = self.early_all_reduce
 
     def state_dict(self):
         """momentum buffer, schedule position and hyper-parameters (the parameters themselves are the model's state_dict)"""
@@ -166,10 +179,39 @@ class FlatSGD:
                     v.copy_(p.grad)
                 p.grad = v
 
+    def early_all_reduce(self):
+        """backward-pass hook (HighResolutionNet._stage4_hook): all-reduce the stage-4 / neck / head gradients on the communication stream.
+        Every kernel that contributes to them has been ISSUED by now (autograd is past stage 4) on the chain streams or the
+        weight-gradient streams: the communication stream waits for all of those, then runs the batched fp32 accumulation of the
+        library gradients collected so far, then the collective."""
+        if self._tail_off is None or self._early_done:
+            return
+        from . import hrnet
+        dev = self.flat_g.device
+        comm = self._comm
+        comm.wait_stream(torch.cuda.current_stream(dev))
+        if self._main_stream is not None:
+            comm.wait_stream(self._main_stream)
+        for s in hrnet._SIDE.get(dev, []):
+            comm.wait_stream(s)
+        for s in conv.WGRAD["streams"].get(dev, []):
+            comm.wait_stream(s)
+        with torch.cuda.stream(comm):
+            conv._flush_pending()
+            dist.all_reduce(self.flat_g[self._tail_off:], group=self._group)
+        self._early_done = True
+
+    _main_stream = None
+
     def all_reduce_grads(self, group=None):
         conv.join_wgrad()                      # weight-gradient kernels run on a side stream: join before touching flat_g
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat_g, group=group)          # sum; the 1/world mean is folded into the step kernels
+            if self._early_done:               # the tail went out during the backward pass (early_all_reduce)
+                dist.all_reduce(self.flat_g[:self._tail_off], group=group)
+                torch.cuda.current_stream(self.flat_g.device).wait_stream(self._comm)
+                self._early_done = False
+            else:
+                dist.all_reduce(self.flat_g, group=group)      # sum; the 1/world mean is folded into the step kernels
             return 1.0 / dist.get_world_size(group)
         return 1.0
 
@@ -200,6 +242,8 @@ class FlatSGD:
 
 
 def _device_train_step(model, opt, img, labels, group=None):
+    opt._group = group
+    opt._main_stream = torch.cuda.current_stream(img.device) if img.is_cuda else None
     losses = model(img, {"cls": labels})
     loss = sum(losses.values())
     loss.backward()
