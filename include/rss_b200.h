@@ -151,6 +151,23 @@ int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, const float* 
                      const float* local_sums /*this rank's sums (== sums without SyncBN)*/,
                      float* dgamma_acc /*may be NULL*/, float* dbeta_acc, cudaStream_t stream);
 
+/* ---- SyncBatchNorm exchange over NVLink peer memory (ffn_block.py:222,231,234), replacing one NCCL collective per layer and pass.
+ * `bases[r]` = address of rank r's symmetric buffer (channels of rss_sync_exchange_bytes(world) bytes each, zero-initialised, every
+ * peer mapped, e.g. torch.distributed._symmetric_memory); one CHANNEL (chan_off_bytes) and one zero-initialised device uint32
+ * `counter` per BatchNorm layer: only the exchanges of one layer are ordered identically on all ranks.  One-CTA kernels: write the
+ * local vector into every rank's slot, system fence, publish a sequence number, spin (bounded) for all ranks, sum in rank order.
+ * All ranks must issue the same sequence of exchange calls.
+ *   rss_sync_allreduce_small: out[0:n] = sum over ranks of vec, local_out = vec (may be NULL); vec is cleared (backward sums).
+ *   rss_sync_bn_finalize:     accum[2C] = this rank's raw statistics (rss_bn_stats_raw) -> global mean / invstd / scale / shift and
+ *                             running statistics (as rss_bn_finalize); accum is cleared. */
+size_t rss_sync_exchange_bytes(int world);
+int rss_sync_allreduce_small(const int64_t* bases, int64_t chan_off_bytes, int rank, int world, unsigned int* counter, float* vec, int n,
+                             float* out, float* local_out, cudaStream_t stream);
+int rss_sync_bn_finalize(const int64_t* bases, int64_t chan_off_bytes, int rank, int world, unsigned int* counter, float* accum, int C,
+                         int64_t local_rows,
+                         const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                         float* mean_out, float* invstd_out, float* scale, float* shift, const float* pre_bias, cudaStream_t stream);
+
 /* One-launch versions for activations that stay L2-resident between the two passes (<= 40 MB, ReLU / no activation):
  * statistics -> device-wide spin barrier -> apply, and reduce -> barrier -> apply.  Grid <= one block per SM, >= 4 resident blocks
  * per SM, so up to 4 concurrent streams can each hold a full grid.  accum_scratch: persistent zeroed float[2*C]; sync_scratch:

@@ -68,6 +68,9 @@ SIGNATURES = {
     "rss_bn_bwd_apply_raw": (c_int, [P, P, P, P, P, P, P, P, P, c_float, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
     "rss_bn_bwd_apply_dz": (c_int, [P, P, P, P, P, P, c_float, P, c_int64, c_int, c_int, P, P, P, P]),
     "rss_bn_bwd_apply": (c_int, [P, P, P, P, P, P, P, P, c_float, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
+    "rss_sync_exchange_bytes": (c_size_t, [c_int]),
+    "rss_sync_allreduce_small": (c_int, [P, c_int64, c_int, c_int, P, P, c_int, P, P, P]),
+    "rss_sync_bn_finalize": (c_int, [P, c_int64, c_int, c_int, P, P, c_int, c_int64, P, P, P, P, c_float, c_float, P, P, P, P, P, P]),
     "rss_bn_fused_supported": (c_int, [c_int64, c_int, c_int, c_int]),
     "rss_bn_fwd_fused": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P, c_float, c_float, P, P, P, P, P, P]),
     "rss_bn_bwd_fused": (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),

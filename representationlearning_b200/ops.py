@@ -17,7 +17,7 @@ CL = torch.channels_last
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; counted from the csrc/*.cu launch sites)
 KERNELS_PER_CALL = {
     "rss_layernorm_fwd": 1, "rss_layernorm_bwd": 1, "rss_attn_fwd": 5, "rss_spatial_attention_fwd": 2, "rss_bilinear_resize": 1, "rss_confusion_matrix": 1, "rss_accum_bf16_list": 1, "rss_attn_bwd": 7, "rss_bn_stats": 1, "rss_bn_combine": 1,
-    "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1, "rss_bn_fwd_fused": 1, "rss_bn_bwd_fused": 1,
+    "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1, "rss_bn_fwd_fused": 1, "rss_bn_bwd_fused": 1, "rss_sync_bn_finalize": 1, "rss_sync_allreduce_small": 1, "rss_bn_stats_raw": 1,
     "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 4, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
     "rss_headaux_fwd": 2, "rss_seg_loss_fwd": 2, "rss_seg_loss_bwd": 1, "rss_grad_sumsq": 1, "rss_sgd_step": 1,
     "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_conv_wgrad": 1, "rss_conv_wgrad_tc": 1, "rss_conv_cf": 1, "rss_shadow_t_refresh": 1, "rss_shadow_cl_refresh": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
@@ -116,6 +116,60 @@ BN_KEEP_DZ = {"on": os.environ.get("RSS_BN_KEEP_DZ", "1") != "0"}
 # Measured on the B=16 step (gpurun 2026-10-17, timeline_s3f): statistics -3.3 us and reduce -2.1 us per layer, but the "last block
 # finished" ticket costs more on the 1184-block apply grids (+6.9 / +3.2 us), 453 vs 458 img/s -> OFF by default.
 BN_RAW = {"on": os.environ.get("RSS_BN_RAW", "0") != "0"}
+
+
+# SyncBatchNorm statistics exchange over NVLink peer memory (csrc/sync_exchange.cu) instead of one NCCL collective per layer and pass.
+# Needs torch.distributed._symmetric_memory on the default process group; anything else (sub-groups, rendezvous failure,
+# RSS_SYNC_SYMM=0) keeps the NCCL path.
+SYNC_SYMM = {"on": os.environ.get("RSS_SYNC_SYMM", "1") != "0", "obj": None, "failed": False}
+
+
+class _SyncExchange:
+    CHANNELS = 512                          # one per SyncBN layer (assigned in first-use order = program order, identical on all ranks)
+
+    def __init__(self, dev):
+        import torch.distributed._symmetric_memory as symm_mem
+        lib = _lib.load()
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.chan_bytes = (lib.rss_sync_exchange_bytes(self.world) + 255) // 256 * 256
+        if self.chan_bytes == 0:
+            raise RuntimeError("world size not supported by the exchange kernel")
+        self.buf = symm_mem.empty(self.CHANNELS * self.chan_bytes // 4, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.bases = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.counters = torch.zeros(self.CHANNELS, dtype=torch.int32, device=dev)
+        self.channels = {}
+        torch.cuda.synchronize(dev)
+        dist.barrier()                      # every rank's buffer is zeroed and mapped before the first exchange
+
+    def channel(self, scratch):
+        """(byte offset, counter pointer) of the channel of the layer owning `scratch`; None when the channels are used up"""
+        k = scratch.data_ptr()
+        c = self.channels.get(k)
+        if c is None:
+            if len(self.channels) >= self.CHANNELS:
+                return None
+            c = self.channels[k] = len(self.channels)
+        return c * self.chan_bytes, self.counters[c:c + 1].data_ptr()
+
+
+def sync_exchange(group, dev, C):
+    """the symmetric-memory exchange for SyncBN on the DEFAULT group, or None (then the NCCL collectives are used).  The first call
+    is collective (rendezvous + barrier): it happens in the eager warm-up step, at the same layer on every rank."""
+    if not SYNC_SYMM["on"] or SYNC_SYMM["failed"] or group is not True or dev.type != "cuda" or 2 * C + 1 > 2 * 512 + 7:
+        return None
+    if SYNC_SYMM["obj"] is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        try:
+            SYNC_SYMM["obj"] = _SyncExchange(dev)
+        except Exception as e:  # noqa: BLE001  (no peer mapping on this box / torch build: fall back to NCCL, on every rank alike)
+            SYNC_SYMM["failed"] = True
+            import sys
+            sys.stderr.write("representationlearning_b200: symmetric-memory SyncBN exchange unavailable (%r), using NCCL\n" % (e,))
+            return None
+    return SYNC_SYMM["obj"]
 
 
 def _world(group):
@@ -292,6 +346,15 @@ class BNAct(torch.autograd.Function):
                 check(lib.rss_bn_stats_fused(_p(x), _p(scratch[2:]), _p(scratch), rows, C, dt, _p(g), _p(b),
                                              _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
                                              _p(aff[3]), _p(pre_bias), st), "rss_bn_stats_fused")
+            elif (training and world > 1 and scratch is not None and scratch.numel() >= 2 + 2 * C and sync_exchange(group, dev, C) is not None
+                  and sync_exchange(group, dev, C).channel(scratch) is not None):
+                # SyncBN: raw local sums -> one-shot exchange over NVLink peer memory, finalised by the same one-CTA kernel
+                ex = sync_exchange(group, dev, C)
+                off, cnt = ex.channel(scratch)
+                check(lib.rss_bn_stats_raw(_p(x), _p(scratch[2:]), rows, C, dt, _p(running_mean), _p(pre_bias), st), "rss_bn_stats_raw")
+                check(lib.rss_sync_bn_finalize(_p(ex.bases), off, ex.rank, ex.world, cnt, _p(scratch[2:]), C, rows, _p(g), _p(b),
+                                               _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
+                                               _p(aff[3]), _p(pre_bias), st), "rss_sync_bn_finalize")
             elif training:
                 nparts = lib.rss_bn_stats_nparts(rows, C)
                 part = torch.empty(nparts * C * 2 + nparts, device=dev, dtype=torch.float32)
@@ -357,13 +420,24 @@ class BNAct(torch.autograd.Function):
             if direct:
                 return (dx, dres) + (None,) * 12
             return (dx, dres, sums[C:], sums[:C]) + (None,) * 10
-        check(lib.rss_bn_bwd_reduce_ws(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(sums),
-                                       _p(sc[2:]) if have_sc else None, _p(sc) if have_sc else None, _p(dz),
-                                       rows, C, ctx.act, dt, st), "rss_bn_bwd_reduce")
-        local = sums
+        ex = sync_exchange(ctx.group, x.device, C) if (ctx.training and ctx.world > 1 and have_sc) else None
+        if ex is not None and ex.channel(sc) is None:
+            ex = None
+        if ex is not None:          # SyncBN: local sums stay in the scratch (no ticket), exchanged over NVLink peer memory
+            check(lib.rss_bn_bwd_reduce_ws(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), None,
+                                           _p(sc[2:]), None, _p(dz), rows, C, ctx.act, dt, st), "rss_bn_bwd_reduce")
+            local = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+            off, cnt = ex.channel(sc)
+            check(lib.rss_sync_allreduce_small(_p(ex.bases), off, ex.rank, ex.world, cnt, _p(sc[2:]), 2 * C, _p(sums), _p(local), st),
+                  "rss_sync_allreduce_small")
+        else:
+            check(lib.rss_bn_bwd_reduce_ws(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(sums),
+                                           _p(sc[2:]) if have_sc else None, _p(sc) if have_sc else None, _p(dz),
+                                           rows, C, ctx.act, dt, st), "rss_bn_bwd_reduce")
+            local = sums
         if ctx.training:
             red = sums
-            if ctx.world > 1:       # SyncBN: dx needs the global sums, the parameter gradients the local ones (DDP averages them)
+            if ctx.world > 1 and ex is None:       # SyncBN: dx needs the global sums, the parameter gradients the local ones (DDP averages them)
                 local = sums.clone()
                 dist.all_reduce(red, group=None if ctx.group is True else ctx.group)
             inv_count = 1.0 / (rows * ctx.world)
