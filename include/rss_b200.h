@@ -316,6 +316,28 @@ int rss_accum_bf16_list(const int64_t* table, const int64_t* chunk_start, int n_
  * -> bf16 [Cin][kh*kw][Cout] at shadow_t + table[e][1]; table[e] = {src offset, dst offset, Cout, Cin, kh*kw} (int64). */
 int rss_shadow_t_refresh(const float* params, void* shadow_t, const int64_t* table, int n_entries, cudaStream_t stream);
 
+/* ---- SCD-AAAI2023 DenseEnergyLoss: permutohedral-lattice bilateral filter ----
+ * Replaces `void bilateralfilter_batch(float* images, int len_images, float* ins, int len_ins, float* outs, int len_outs, int N,
+ * int K, int H, int W, float sigmargb, float sigmaxy)` (SCD-AAAI2023/wrapper/bilateralfilter/bilateralfilter.hpp:12, .cpp:43-55;
+ * SWIG typemaps bilateralfilter.i:21-25; caller utils/losses.py:66-70): images (N,3,H,W) de-normalised RGB, ins/outs (N,K,H,W),
+ * flat contiguous fp32; outs[n,k] = lattice filter of ins[n,k] guided by (x/sigmaxy, y/sigmaxy, rgb/sigmargb) of image n.
+ * Results are bit-identical to the reference built with its own setup.py flags (x86-64 SSE path of permutohedral.cpp).
+ *
+ * rss_bilateralfilter_batch: DEVICE pointers, stream-ordered, no host synchronisation; `workspace` (>= rss_bilateral_workspace_bytes,
+ * 16-byte aligned) is caller-owned scratch; lattice_points (device int[1] or NULL) receives the number of lattice points of the batch.
+ * rss_bilateralfilter_batch_host: the reference's argument list verbatim (HOST arrays, outs written in place, lengths checked),
+ * synchronous; the only entry point that owns device memory (a process-wide arena grown on demand).
+ * rss_dense_energy_gate: the element-wise part of DenseEnergyLossFunction.forward (utils/losses.py:54-64,71-74) fused into one
+ * pass over device data: AS[i] *= gate(n,pixel) with gate = 1 where unlabeled, else max(ROI - max_k seg, 0); loss_acc[0] -=
+ * sum(seg_roi * AS) / N (double, atomic, caller zeroes it); seg_roi is the ROI-masked segmentation that went into the filter. */
+size_t rss_bilateral_workspace_bytes(int N, int K, int H, int W);
+int rss_bilateralfilter_batch(const float* images, const float* ins, float* outs, int N, int K, int H, int W, float sigmargb,
+                              float sigmaxy, void* workspace, size_t workspace_bytes, int* lattice_points, cudaStream_t stream);
+int rss_bilateralfilter_batch_host(const float* images, int len_images, const float* ins, int len_ins, float* outs, int len_outs,
+                                   int N, int K, int H, int W, float sigmargb, float sigmaxy);
+int rss_dense_energy_gate(const float* seg, const float* rois, const uint8_t* unlabeled, const float* seg_roi, float* AS,
+                          double* loss_acc, int N, int K, int H, int W, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

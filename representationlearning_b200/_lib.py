@@ -104,6 +104,10 @@ SIGNATURES = {
     "rss_accum_bf16_list": (c_int, [P, P, c_int, c_int64, P]),
     "rss_bilinear_resize": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, P]),
     "rss_confusion_matrix": (c_int, [P, P, P, c_int64, c_int, c_int, P]),
+    "rss_bilateral_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "rss_bilateralfilter_batch": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, P, c_size_t, P, P]),
+    "rss_bilateralfilter_batch_host": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float]),
+    "rss_dense_energy_gate": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
 }
 
 _lib = None
