@@ -60,8 +60,12 @@ __global__ void pl_embed_kernel(const float* __restrict__ images, int N, int P, 
                                 EmbedConsts ec, LKey* table, unsigned mask, int* __restrict__ id_of_slot, LKey* __restrict__ key_of_id,
                                 int* counters, int* __restrict__ vertex, float* __restrict__ weight) {
     const long long total = (long long)N * P4;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(idx / P4), p = (int)(idx - (long long)b * P4);
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count: the lanes of a warp de-duplicate their keys with __match_any_sync before anyone probes the table
+    for (long long base0 = (long long)blockIdx.x * blockDim.x; base0 < total; base0 += (long long)gridDim.x * blockDim.x) {
+        const long long idx = base0 + threadIdx.x;
+        const bool active = idx < total;
+        const int b = active ? (int)(idx / P4) : 0, p = active ? (int)(idx - (long long)b * P4) : P4;
         float f[PD] = {0.f, 0.f, 0.f, 0.f, 0.f};
         if (p < P) {
             const int y = p / W, x = p - y * W;
@@ -139,21 +143,30 @@ __global__ void pl_embed_kernel(const float* __restrict__ images, int N, int P, 
             unsigned short c[PD];
 #pragma unroll
             for (int i = 0; i < PD; ++i) c[i] = (unsigned short)(short)(ibase[i] + (rank[i] <= PD - r ? r : r - PV));
-            const LKey key{(unsigned)c[0] | (unsigned)c[1] << 16, (unsigned)c[2] | (unsigned)c[3] << 16, (unsigned)c[4], (unsigned)b};
+            // inactive lanes carry a per-lane key no pixel can have (image index 0xfffffffe) and never touch the table
+            const LKey key = active ? LKey{(unsigned)c[0] | (unsigned)c[1] << 16, (unsigned)c[2] | (unsigned)c[3] << 16, (unsigned)c[4], (unsigned)b}
+                                    : LKey{(unsigned)lane, 0u, 0u, 0xfffffffeu};
             const LKey empty{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+            // neighbouring pixels share most of their lattice points: only the first lane of every group of equal keys probes
+            const unsigned grp = __match_any_sync(0xffffffffu, (unsigned long long)key.w1 << 32 | key.w0) &
+                                 __match_any_sync(0xffffffffu, (unsigned long long)key.w3 << 32 | key.w2);
+            const int leader = __ffs(grp) - 1;
             unsigned h = key_hash(key) & mask;
-            for (;;) {
-                LKey cur = load_key(table + h);
-                if (key_empty(cur)) cur = atomicCAS(table + h, empty, key);
-                if (key_empty(cur)) {                      // this thread created the lattice point
-                    const int id = atomicAdd(counters, 1);
-                    id_of_slot[h] = id;
-                    key_of_id[id] = key;
-                    break;
+            if (active && lane == leader) {
+                for (;;) {
+                    LKey cur = load_key(table + h);
+                    if (key_empty(cur)) cur = atomicCAS(table + h, empty, key);
+                    if (key_empty(cur)) {                  // this thread created the lattice point
+                        const int id = atomicAdd(counters, 1);
+                        id_of_slot[h] = id;
+                        key_of_id[id] = key;
+                        break;
+                    }
+                    if (key_eq(cur, key)) break;
+                    h = (h + 1) & mask;
                 }
-                if (key_eq(cur, key)) break;
-                h = (h + 1) & mask;
             }
+            h = __shfl_sync(0xffffffffu, h, leader);
             if (p < P) {
                 const size_t e = ((size_t)b * P + p) * PV + r;
                 vertex[e] = (int)h;                        // hash slot for now; pl_entries_kernel turns it into the point id
@@ -186,7 +199,46 @@ __global__ void pl_sort_hist_kernel(const unsigned* __restrict__ keys, unsigned 
     hist[(size_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan in place, one block of 1024 threads (the array is 256 x #tiles: 38 k entries at the reference's working size)
+// exclusive scan of the digit histograms (256 x #tiles entries), two levels: every block scans a chunk of 4096 in place and leaves its
+// total in sums[chunk]; pl_scan_kernel scans the totals; the scatter kernel adds sums[i / 4096] when it reads entry i.
+// (First version: ONE block over the whole array = 120 us of the 335 us call at N=2, 160x160 and 11 ms of 18 ms at N=16, 512x512.)
+constexpr int SCAN_CHUNK = 4096;
+__global__ void pl_scan_chunks_kernel(unsigned* __restrict__ a, unsigned len, unsigned* __restrict__ sums) {
+    __shared__ unsigned wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned i0 = blockIdx.x * SCAN_CHUNK + threadIdx.x * 4;
+    unsigned v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = i0 + q < len ? a[i0 + q] : 0u;
+    const unsigned tsum = v[0] + v[1] + v[2] + v[3];
+    unsigned inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned sv = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, sv, o);
+            if (lane >= o) sv += t;
+        }
+        wsum[lane] = sv;
+    }
+    __syncthreads();
+    unsigned run = inc - tsum + (warp > 0 ? wsum[warp - 1] : 0u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (i0 + q < len) a[i0 + q] = run;
+        run += v[q];
+    }
+    if (threadIdx.x == 0) sums[blockIdx.x] = wsum[31];
+}
+
+// exclusive scan in place, one block of 1024 threads (used on the chunk totals: a few hundred entries)
 __global__ void pl_scan_kernel(unsigned* __restrict__ a, unsigned len) {
     __shared__ unsigned wsum[32];
     __shared__ unsigned carry;
@@ -225,7 +277,8 @@ __global__ void pl_scan_kernel(unsigned* __restrict__ a, unsigned len) {
 // A block scatters its tile in index order: warp w owns 256 consecutive entries and takes them 32 at a time; inside a round the
 // rank among equal digits comes from __match_any_sync, across rounds and warps from per-warp digit counters -> the pass is stable.
 __global__ void pl_sort_scatter_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ vals, unsigned* __restrict__ okeys,
-                                       unsigned* __restrict__ ovals, unsigned n, int shift, const unsigned* __restrict__ hist, int nblk) {
+                                       unsigned* __restrict__ ovals, unsigned n, int shift, const unsigned* __restrict__ hist,
+                                       const unsigned* __restrict__ sums, int nblk) {
     __shared__ unsigned wcnt[8][256];
     __shared__ unsigned gbase[256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -261,7 +314,8 @@ __global__ void pl_sort_scatter_kernel(const unsigned* __restrict__ keys, const 
             wcnt[ww][d] = run;
             run += c;
         }
-        gbase[d] = hist[(size_t)d * nblk + blockIdx.x];
+        const unsigned hi = (unsigned)d * (unsigned)nblk + blockIdx.x;
+        gbase[d] = hist[hi] + sums[hi / SCAN_CHUNK];
     }
     __syncthreads();
 #pragma unroll
@@ -277,9 +331,14 @@ __global__ void pl_sort_scatter_kernel(const unsigned* __restrict__ keys, const 
 }
 
 // ---- 4. list bounds of every lattice point in the sorted pairs (points made only by padding lanes keep the empty list 0..0) ----
-__global__ void pl_segments_kernel(const unsigned* __restrict__ skeys, unsigned E, int* __restrict__ seg_start, int* __restrict__ seg_end) {
+__global__ void pl_segments_kernel(const unsigned* __restrict__ skeys, const unsigned* __restrict__ svals, const float* __restrict__ weight,
+                                   unsigned E, int* __restrict__ seg_start, int* __restrict__ seg_end, unsigned* __restrict__ spix,
+                                   float* __restrict__ sweight) {
     for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < E; t += gridDim.x * blockDim.x) {
         const unsigned id = skeys[t];
+        const unsigned e = svals[t];
+        spix[t] = e / PV;                                   // batch-wide pixel index (the splat reads pixel-major values)
+        sweight[t] = weight[e];
         if (t == 0 || skeys[t - 1] != id) seg_start[id] = (int)t;
         if (t == E - 1 || skeys[t + 1] != id) seg_end[id] = (int)(t + 1);
     }
@@ -317,40 +376,53 @@ __global__ void pl_neighbors_kernel(const LKey* __restrict__ table, unsigned mas
     }
 }
 
-// ---- 6. splat: one warp per lattice point, lanes = class planes, pixels in raster order (:505-513) ------------------------------
-// values[(id + 1) * K + k]; row 0 stands for "no such lattice point" and stays zero in both buffers
-__global__ void pl_splat_kernel(const float* __restrict__ ins, const unsigned* __restrict__ svals, const float* __restrict__ weight,
-                                const int* __restrict__ seg_start, const int* __restrict__ seg_end, const LKey* __restrict__ key_of_id,
-                                const int* __restrict__ counters, float* __restrict__ va, float* __restrict__ vb, int K, int P) {
+// ---- 6. splat (:505-513) -------------------------------------------------------------------------------------------------------
+// (N,K,P) -> (N,P,K): a lattice point's list names pixels, and with plane-major values every (entry, plane) load was its own 32-byte
+// sector (E*K sectors: 1.6 GB of L2->SM traffic at N=8, 224x224, 11.6 GB from DRAM at N=16, 512x512); pixel-major it is K
+// contiguous floats per entry.
+constexpr int TP = 128, TK = 32;
+__global__ void pl_pixel_major_kernel(const float* __restrict__ ins, float* __restrict__ insT, int K, int P) {
+    __shared__ float tile[TK][TP + 1];
+    const int b = blockIdx.y, p0 = blockIdx.x * TP, k0 = blockIdx.z * TK;
+    const int np = min(TP, P - p0), nk = min(TK, K - k0);
+    for (int i = threadIdx.x; i < nk * TP; i += blockDim.x) {
+        const int k = i / TP, px = i - k * TP;
+        if (px < np) tile[k][px] = __ldg(ins + ((size_t)b * K + k0 + k) * P + p0 + px);
+    }
+    __syncthreads();
+    float* dst = insT + ((size_t)b * P + p0) * K + k0;
+    for (int i = threadIdx.x; i < np * nk; i += blockDim.x) {
+        const int px = i / nk, k = i - px * nk;
+        dst[(size_t)px * K + k] = tile[k][px];
+    }
+}
+
+// one thread per (lattice point, class plane), planes fastest: the threads of a point read the same list entry (broadcast) and K
+// contiguous values; the chain of adds per (point, plane) runs in raster order.  values[(id + 1) * K + k]; row 0 stands for "no
+// such lattice point" and stays zero in both buffers.
+__global__ void pl_splat_kernel(const float* __restrict__ insT, const unsigned* __restrict__ spix, const float* __restrict__ sweight,
+                                const int* __restrict__ seg_start, const int* __restrict__ seg_end, const int* __restrict__ counters,
+                                float* __restrict__ va, float* __restrict__ vb, int K) {
     const int M = counters[0];
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; id < M; id += warps) {
+    const long long total = (long long)M * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int id = (int)(i / K), k = (int)(i - (long long)id * K);
         const int s = seg_start[id], t_end = seg_end[id];
-        const unsigned b = key_of_id[id].w3;
-        const unsigned e_base = b * (unsigned)P * PV;        // entries of image b start here
-        for (int k0 = 0; k0 < K; k0 += 32) {
-            const int k = k0 + lane;
-            const float* plane = ins + ((size_t)b * K + (k < K ? k : 0)) * P;
-            float acc = 0.f;
-            for (int t = s; t < t_end; t += 32) {
-                const int cnt = min(32, t_end - t);
-                unsigned my_e = 0;
-                float my_w = 0.f;
-                if (lane < cnt) { my_e = svals[t + lane]; my_w = weight[my_e]; }
-                const unsigned my_p = (my_e - e_base) / PV;
-#pragma unroll 8
-                for (int j = 0; j < cnt; ++j) {
-                    const unsigned p = __shfl_sync(0xffffffffu, my_p, j);
-                    const float wgt = __shfl_sync(0xffffffffu, my_w, j);
-                    acc = __fadd_rn(acc, __fmul_rn(wgt, __ldg(plane + p)));
-                }
+        float acc = 0.f;
+        int t = s;
+        for (; t + 4 <= t_end; t += 4) {                     // four independent loads in flight, adds in order
+            float x[4], w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                w[q] = __ldg(sweight + t + q);
+                x[q] = __ldg(insT + (size_t)__ldg(spix + t + q) * K + k);
             }
-            if (k < K) {
-                va[(size_t)(id + 1) * K + k] = acc;
-                if (id == 0) { va[k] = 0.f; vb[k] = 0.f; }
-            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc = __fadd_rn(acc, __fmul_rn(w[q], x[q]));
         }
+        for (; t < t_end; ++t) acc = __fadd_rn(acc, __fmul_rn(__ldg(sweight + t), __ldg(insT + (size_t)__ldg(spix + t) * K + k)));
+        va[(size_t)(id + 1) * K + k] = acc;
+        if (id == 0) { va[k] = 0.f; vb[k] = 0.f; }
     }
 }
 
@@ -428,15 +500,15 @@ __global__ void dense_energy_gate_kernel(const float* __restrict__ seg, const fl
 struct Plan {
     long long P, P4, E, Eins, Mmax;
     unsigned cap;
-    int nblk, passes;
-    size_t off_table, off_idslot, off_keyid, off_counters, off_vertex, off_weight, off_k[2], off_v[2], off_hist, off_seg0, off_seg1, off_nb,
+    int nblk, passes, nchunks;
+    size_t off_table, off_idslot, off_keyid, off_counters, off_vertex, off_weight, off_k[2], off_v[2], off_hist, off_sums, off_seg0, off_seg1, off_nb, off_insT,
         off_va, off_vb, total;
 };
 
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static bool make_plan(int N, int K, int H, int W, Plan& pl) {
-    if (N <= 0 || K <= 0 || H <= 0 || W <= 0) return false;
+    if (N <= 0 || K <= 0 || K > 65535 * TK || H <= 0 || W <= 0 || N > 65535) return false;   // grid.y / grid.z of the staging kernel
     pl.P = (long long)H * W;
     pl.P4 = (pl.P + 3) & ~3ll;
     pl.E = (long long)N * pl.P * PV;
@@ -460,6 +532,9 @@ static bool make_plan(int N, int K, int H, int W, Plan& pl) {
     pl.off_weight = take((size_t)pl.E * 4);
     for (int i = 0; i < 2; ++i) { pl.off_k[i] = take((size_t)pl.E * 4); pl.off_v[i] = take((size_t)pl.E * 4); }
     pl.off_hist = take((size_t)256 * pl.nblk * 4);
+    pl.nchunks = (256 * pl.nblk + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    pl.off_sums = take((size_t)pl.nchunks * 4);
+    pl.off_insT = take((size_t)N * pl.P * K * 4);
     pl.off_seg0 = take((size_t)(pl.Mmax + 1) * 4);
     pl.off_seg1 = take((size_t)(pl.Mmax + 1) * 4);
     pl.off_nb = take((size_t)PV * pl.Mmax * sizeof(int2));
@@ -513,6 +588,8 @@ extern "C" int rss_bilateralfilter_batch(const float* images, const float* ins, 
     unsigned* sk[2] = {(unsigned*)(ws + pl.off_k[0]), (unsigned*)(ws + pl.off_k[1])};
     unsigned* sv[2] = {(unsigned*)(ws + pl.off_v[0]), (unsigned*)(ws + pl.off_v[1])};
     unsigned* hist = (unsigned*)(ws + pl.off_hist);
+    unsigned* sums = (unsigned*)(ws + pl.off_sums);
+    float* insT = (float*)(ws + pl.off_insT);
     int* seg_start = (int*)(ws + pl.off_seg0);
     int* seg_end = (int*)(ws + pl.off_seg1);
     int2* nb = (int2*)(ws + pl.off_nb);
@@ -532,13 +609,18 @@ extern "C" int rss_bilateralfilter_batch(const float* images, const float* ins, 
     int cur = 0;
     for (int pass = 0; pass < pl.passes; ++pass) {
         pl_sort_hist_kernel<<<pl.nblk, 256, 0, st>>>(sk[cur], E, 8 * pass, hist, pl.nblk);
-        pl_scan_kernel<<<1, 1024, 0, st>>>(hist, 256u * (unsigned)pl.nblk);
-        pl_sort_scatter_kernel<<<pl.nblk, 256, 0, st>>>(sk[cur], sv[cur], sk[cur ^ 1], sv[cur ^ 1], E, 8 * pass, hist, pl.nblk);
+        pl_scan_chunks_kernel<<<pl.nchunks, 1024, 0, st>>>(hist, 256u * (unsigned)pl.nblk, sums);
+        pl_scan_kernel<<<1, 1024, 0, st>>>(sums, (unsigned)pl.nchunks);
+        pl_sort_scatter_kernel<<<pl.nblk, 256, 0, st>>>(sk[cur], sv[cur], sk[cur ^ 1], sv[cur ^ 1], E, 8 * pass, hist, sums, pl.nblk);
         cur ^= 1;
     }
-    pl_segments_kernel<<<grid_for(E, 256, 8), 256, 0, st>>>(sk[cur], E, seg_start, seg_end);
+    // the sort's spare buffers take the sorted pixel indices / weights
+    unsigned* spix = sk[cur ^ 1];
+    float* sweight = (float*)sv[cur ^ 1];
+    pl_segments_kernel<<<grid_for(E, 256, 8), 256, 0, st>>>(sk[cur], sv[cur], weight, E, seg_start, seg_end, spix, sweight);
+    pl_pixel_major_kernel<<<dim3((unsigned)((pl.P + TP - 1) / TP), (unsigned)N, (unsigned)((K + TK - 1) / TK)), 256, 0, st>>>(ins, insT, K, (int)pl.P);
     pl_neighbors_kernel<<<num_sms() * 8, 256, 0, st>>>(table, pl.cap - 1, id_of_slot, key_of_id, counters, nb, (int)pl.Mmax);
-    pl_splat_kernel<<<num_sms() * 8, 256, 0, st>>>(ins, sv[cur], weight, seg_start, seg_end, key_of_id, counters, va, vb, K, (int)pl.P);
+    pl_splat_kernel<<<num_sms() * 8, 256, 0, st>>>(insT, spix, sweight, seg_start, seg_end, counters, va, vb, K);
     float *a = va, *b = vb;
     for (int dir = 0; dir < PV; ++dir) {
         pl_blur_kernel<<<num_sms() * 8, 256, 0, st>>>(a, b, nb + (size_t)dir * pl.Mmax, counters, K);
