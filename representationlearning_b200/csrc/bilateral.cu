@@ -50,7 +50,10 @@ __device__ __forceinline__ unsigned key_hash(const LKey& k) {
 }
 
 __device__ __forceinline__ LKey load_key(const LKey* p) {
-    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p));        // one 16-byte L2 access; EMPTY -> key is the only transition
+    // one 16-byte access, cached in L1: a slot only ever goes EMPTY -> key, so a stale EMPTY just sends the thread to the CAS (which is
+    // authoritative) and a cached key is final.  L2-only loads (first version) hot-spotted the few L2 lines that every warp working
+    // on the same image region probes.
+    const uint4 v = __ldca(reinterpret_cast<const uint4*>(p));
     return LKey{v.x, v.y, v.z, v.w};
 }
 
@@ -65,6 +68,12 @@ __global__ void pl_embed_kernel(const float* __restrict__ images, int N, int P, 
     for (long long base0 = (long long)blockIdx.x * blockDim.x; base0 < total; base0 += (long long)gridDim.x * blockDim.x) {
         const long long idx = base0 + threadIdx.x;
         const bool active = idx < total;
+        // ids are handed out per block: one global atomic per 256 pixels (one per created point serialised the kernel on a single L2
+        // address: 65 us of its 81 us at N=8, 224x224)
+        __shared__ int blk_created, blk_base;
+        if (threadIdx.x == 0) blk_created = 0;
+        __syncthreads();
+        int my_slot[PV], my_rank[PV];
         const int b = active ? (int)(idx / P4) : 0, p = active ? (int)(idx - (long long)b * P4) : P4;
         float f[PD] = {0.f, 0.f, 0.f, 0.f, 0.f};
         if (p < P) {
@@ -152,14 +161,14 @@ __global__ void pl_embed_kernel(const float* __restrict__ images, int N, int P, 
                                  __match_any_sync(0xffffffffu, (unsigned long long)key.w3 << 32 | key.w2);
             const int leader = __ffs(grp) - 1;
             unsigned h = key_hash(key) & mask;
+            my_rank[r] = -1;
             if (active && lane == leader) {
                 for (;;) {
                     LKey cur = load_key(table + h);
                     if (key_empty(cur)) cur = atomicCAS(table + h, empty, key);
                     if (key_empty(cur)) {                  // this thread created the lattice point
-                        const int id = atomicAdd(counters, 1);
-                        id_of_slot[h] = id;
-                        key_of_id[id] = key;
+                        my_rank[r] = atomicAdd(&blk_created, 1);
+                        my_slot[r] = (int)h;
                         break;
                     }
                     if (key_eq(cur, key)) break;
@@ -173,18 +182,42 @@ __global__ void pl_embed_kernel(const float* __restrict__ images, int N, int P, 
                 weight[e] = bary[r];
             }
         }
+        __syncthreads();
+        if (threadIdx.x == 0) blk_base = blk_created ? atomicAdd(counters, blk_created) : 0;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < PV; ++r)
+            if (my_rank[r] >= 0) {
+                unsigned short c[PD];
+#pragma unroll
+                for (int i = 0; i < PD; ++i) c[i] = (unsigned short)(short)(ibase[i] + (rank[i] <= PD - r ? r : r - PV));
+                const int id = blk_base + my_rank[r];
+                id_of_slot[my_slot[r]] = id;
+                key_of_id[id] = LKey{(unsigned)c[0] | (unsigned)c[1] << 16, (unsigned)c[2] | (unsigned)c[3] << 16, (unsigned)c[4], (unsigned)b};
+            }
     }
 }
 
 // ---- 2. (point id, entry) pairs for the sort ---------------------------------------------------------------------------------
+// one block per sort tile; also leaves the tile's histogram of the first digit (saves the first pl_sort_hist_kernel launch)
 __global__ void pl_entries_kernel(int* __restrict__ vertex, const int* __restrict__ id_of_slot, unsigned* __restrict__ keys,
-                                  unsigned* __restrict__ vals, unsigned E) {
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
-        const int id = id_of_slot[vertex[e]];
-        vertex[e] = id;
-        keys[e] = (unsigned)id;
-        vals[e] = e;
+                                  unsigned* __restrict__ vals, unsigned E, unsigned* __restrict__ hist, int nblk) {
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned t0 = blockIdx.x * 2048u;
+    for (int i = threadIdx.x; i < 2048; i += 256) {
+        const unsigned e = t0 + i;
+        if (e < E) {
+            const int id = id_of_slot[vertex[e]];
+            vertex[e] = id;
+            keys[e] = (unsigned)id;
+            vals[e] = e;
+            atomicAdd(&h[(unsigned)id & 255u], 1u);
+        }
     }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
 // ---- 3. stable LSD radix sort of the pairs by point id, 8 bits per pass --------------------------------------------------------
@@ -200,11 +233,47 @@ __global__ void pl_sort_hist_kernel(const unsigned* __restrict__ keys, unsigned 
 }
 
 // exclusive scan of the digit histograms (256 x #tiles entries), two levels: every block scans a chunk of 4096 in place and leaves its
-// total in sums[chunk]; pl_scan_kernel scans the totals; the scatter kernel adds sums[i / 4096] when it reads entry i.
+// total in sums[chunk]; the last block to finish scans the totals; the scatter kernel adds sums[i / 4096] when it reads entry i.
 // (First version: ONE block over the whole array = 120 us of the 335 us call at N=2, 160x160 and 11 ms of 18 ms at N=16, 512x512.)
 constexpr int SCAN_CHUNK = 4096;
-__global__ void pl_scan_chunks_kernel(unsigned* __restrict__ a, unsigned len, unsigned* __restrict__ sums) {
+// exclusive scan in place by ONE block of 1024 threads (the chunk totals: a few hundred entries)
+__device__ __forceinline__ void block_scan_inplace(unsigned* a, unsigned len, unsigned* wsum, unsigned* carry) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) *carry = 0;
+    __syncthreads();
+    for (unsigned base = 0; base < len; base += 1024) {
+        const unsigned i = base + threadIdx.x;
+        const unsigned v = i < len ? __ldcg(a + i) : 0u;
+        unsigned inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned s = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += t;
+            }
+            wsum[lane] = s;                                 // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned before = *carry + (warp > 0 ? wsum[warp - 1] : 0u);
+        if (i < len) a[i] = before + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) *carry += wsum[31];
+        __syncthreads();
+    }
+}
+
+__global__ void pl_scan_chunks_kernel(unsigned* __restrict__ a, unsigned len, unsigned* sums, int* ticket) {
     __shared__ unsigned wsum[32];
+    __shared__ unsigned carry;
+    __shared__ int last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned i0 = blockIdx.x * SCAN_CHUNK + threadIdx.x * 4;
     unsigned v[4];
@@ -235,42 +304,16 @@ __global__ void pl_scan_chunks_kernel(unsigned* __restrict__ a, unsigned len, un
         if (i0 + q < len) a[i0 + q] = run;
         run += v[q];
     }
-    if (threadIdx.x == 0) sums[blockIdx.x] = wsum[31];
-}
-
-// exclusive scan in place, one block of 1024 threads (used on the chunk totals: a few hundred entries)
-__global__ void pl_scan_kernel(unsigned* __restrict__ a, unsigned len) {
-    __shared__ unsigned wsum[32];
-    __shared__ unsigned carry;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
+    // the block that finishes last scans the chunk totals (one launch per pass instead of two)
+    if (threadIdx.x == 0) {
+        sums[blockIdx.x] = wsum[31];
+        __threadfence();
+        last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    }
     __syncthreads();
-    for (unsigned base = 0; base < len; base += 1024) {
-        const unsigned i = base + threadIdx.x;
-        const unsigned v = i < len ? a[i] : 0u;
-        unsigned inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned s = wsum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane >= o) s += t;
-            }
-            wsum[lane] = s;                                 // inclusive over warps
-        }
-        __syncthreads();
-        const unsigned before = carry + (warp > 0 ? wsum[warp - 1] : 0u);
-        if (i < len) a[i] = before + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += wsum[31];
-        __syncthreads();
+    if (last) {
+        __threadfence();
+        block_scan_inplace(sums, gridDim.x, wsum, &carry);
     }
 }
 
@@ -400,10 +443,9 @@ __global__ void pl_pixel_major_kernel(const float* __restrict__ ins, float* __re
 // one thread per (lattice point, class plane), planes fastest: the threads of a point read the same list entry (broadcast) and K
 // contiguous values; the chain of adds per (point, plane) runs in raster order.  values[(id + 1) * K + k]; row 0 stands for "no
 // such lattice point" and stays zero in both buffers.
-__global__ void pl_splat_kernel(const float* __restrict__ insT, const unsigned* __restrict__ spix, const float* __restrict__ sweight,
-                                const int* __restrict__ seg_start, const int* __restrict__ seg_end, const int* __restrict__ counters,
-                                float* __restrict__ va, float* __restrict__ vb, int K) {
-    const int M = counters[0];
+__device__ __forceinline__ void splat_phase(const float* __restrict__ insT, const unsigned* __restrict__ spix, const float* __restrict__ sweight,
+                                            const int* __restrict__ seg_start, const int* __restrict__ seg_end, int M,
+                                            float* __restrict__ va, float* __restrict__ vb, int K) {
     const long long total = (long long)M * K;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int id = (int)(i / K), k = (int)(i - (long long)id * K);
@@ -427,9 +469,7 @@ __global__ void pl_splat_kernel(const float* __restrict__ insT, const unsigned* 
 }
 
 // ---- 7. blur along one lattice direction, Jacobi style (:515-531) -------------------------------------------------------------
-__global__ void pl_blur_kernel(const float* __restrict__ cur, float* __restrict__ nxt, const int2* __restrict__ nb,
-                               const int* __restrict__ counters, int K) {
-    const int M = counters[0];
+__device__ __forceinline__ void blur_phase(const float* __restrict__ cur, float* __restrict__ nxt, const int2* __restrict__ nb, int M, int K) {
     const long long total = (long long)M * K;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int id = (int)(i / K), k = (int)(i - (long long)id * K);
@@ -440,8 +480,8 @@ __global__ void pl_blur_kernel(const float* __restrict__ cur, float* __restrict_
 }
 
 // ---- 8. slice: one thread per pixel, all class planes (:536-546) ---------------------------------------------------------------
-__global__ void pl_slice_kernel(const float* __restrict__ values, const int* __restrict__ vertex, const float* __restrict__ weight,
-                                float* __restrict__ outs, int N, int K, int P, float alpha) {
+__device__ __forceinline__ void slice_phase(const float* __restrict__ values, const int* __restrict__ vertex, const float* __restrict__ weight,
+                                            float* __restrict__ outs, int N, int K, int P, float alpha) {
     const long long total = (long long)N * P;
     for (long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x; gp < total; gp += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(gp / P), p = (int)(gp - (long long)b * P);
@@ -462,6 +502,25 @@ __global__ void pl_slice_kernel(const float* __restrict__ values, const int* __r
     }
 }
 
+__global__ void pl_splat_kernel(const float* __restrict__ insT, const unsigned* __restrict__ spix, const float* __restrict__ sweight,
+                                const int* __restrict__ seg_start, const int* __restrict__ seg_end, const int* __restrict__ counters,
+                                float* __restrict__ va, float* __restrict__ vb, int K) {
+    splat_phase(insT, spix, sweight, seg_start, seg_end, counters[0], va, vb, K);
+}
+__global__ void pl_blur_kernel(const float* __restrict__ cur, float* __restrict__ nxt, const int2* __restrict__ nb,
+                               const int* __restrict__ counters, int K) {
+    blur_phase(cur, nxt, nb, counters[0], K);
+}
+__global__ void pl_slice_kernel(const float* __restrict__ values, const int* __restrict__ vertex, const float* __restrict__ weight,
+                                float* __restrict__ outs, int N, int K, int P, float alpha) {
+    slice_phase(values, vertex, weight, outs, N, K, P, alpha);
+}
+
+// MEASURED AND REJECTED (gpurun 2026-10-17): splat -> 6 blur passes -> slice as ONE cooperative launch with grid-wide barriers instead
+// of 8 launches: 142 us vs 84 us for the separate kernels at N=2, 160x160 and 494 vs 262 us at N=8, 224x224 (64 registers x 256 threads
+// hold the grid to 4 blocks/SM for every phase, and a grid barrier costs more than the kernel boundary it replaces once the call is
+// replayed from a CUDA graph).  Four elements per thread and trip in the blur with L2-only loads was slower too (the rows of
+// neighbouring lattice points are re-read by neighbouring threads: they want L1).
 
 // ---- 9. element-wise part of DenseEnergyLossFunction.forward (utils/losses.py:54-64,71-74), one pass ---------------------------
 // gate = 1 where unlabeled, else max(ROI - max_k seg, 0); AS *= gate; loss -= sum(seg_roi * AS) / N (double accumulation)
@@ -527,7 +586,6 @@ static bool make_plan(int N, int K, int H, int W, Plan& pl) {
     pl.off_table = take((size_t)cap * sizeof(LKey));
     pl.off_idslot = take((size_t)cap * 4);
     pl.off_keyid = take((size_t)pl.Mmax * sizeof(LKey));
-    pl.off_counters = take(256);
     pl.off_vertex = take((size_t)pl.E * 4);
     pl.off_weight = take((size_t)pl.E * 4);
     for (int i = 0; i < 2; ++i) { pl.off_k[i] = take((size_t)pl.E * 4); pl.off_v[i] = take((size_t)pl.E * 4); }
@@ -535,6 +593,7 @@ static bool make_plan(int N, int K, int H, int W, Plan& pl) {
     pl.nchunks = (256 * pl.nblk + SCAN_CHUNK - 1) / SCAN_CHUNK;
     pl.off_sums = take((size_t)pl.nchunks * 4);
     pl.off_insT = take((size_t)N * pl.P * K * 4);
+    pl.off_counters = take(256);                            // [0] lattice points, [1 + pass] scan tickets; zeroed together with the list bounds
     pl.off_seg0 = take((size_t)(pl.Mmax + 1) * 4);
     pl.off_seg1 = take((size_t)(pl.Mmax + 1) * 4);
     pl.off_nb = take((size_t)PV * pl.Mmax * sizeof(int2));
@@ -599,18 +658,16 @@ extern "C" int rss_bilateralfilter_batch(const float* images, const float* ins, 
     const unsigned E = (unsigned)pl.E;
 
     cudaMemsetAsync(table, 0xFF, (size_t)pl.cap * sizeof(LKey), st);
-    cudaMemsetAsync(counters, 0, 256, st);
-    // both list bounds in one call: the two arrays are adjacent up to alignment padding
-    cudaMemsetAsync(seg_start, 0, (pl.off_seg1 - pl.off_seg0) + (size_t)(pl.Mmax + 1) * 4, st);
+    // counters, scan tickets and both list bounds in one call: the arrays are adjacent up to alignment padding
+    cudaMemsetAsync(counters, 0, (pl.off_seg1 - pl.off_counters) + (size_t)(pl.Mmax + 1) * 4, st);
 
     pl_embed_kernel<<<grid_for((long long)N * pl.P4, 256, 8), 256, 0, st>>>(images, N, (int)pl.P, (int)pl.P4, W, sigmargb, sigmaxy, ec, table,
                                                                            pl.cap - 1, id_of_slot, key_of_id, counters, vertex, weight);
-    pl_entries_kernel<<<grid_for(E, 256, 8), 256, 0, st>>>(vertex, id_of_slot, sk[0], sv[0], E);
+    pl_entries_kernel<<<pl.nblk, 256, 0, st>>>(vertex, id_of_slot, sk[0], sv[0], E, hist, pl.nblk);
     int cur = 0;
     for (int pass = 0; pass < pl.passes; ++pass) {
-        pl_sort_hist_kernel<<<pl.nblk, 256, 0, st>>>(sk[cur], E, 8 * pass, hist, pl.nblk);
-        pl_scan_chunks_kernel<<<pl.nchunks, 1024, 0, st>>>(hist, 256u * (unsigned)pl.nblk, sums);
-        pl_scan_kernel<<<1, 1024, 0, st>>>(sums, (unsigned)pl.nchunks);
+        if (pass > 0) pl_sort_hist_kernel<<<pl.nblk, 256, 0, st>>>(sk[cur], E, 8 * pass, hist, pl.nblk);
+        pl_scan_chunks_kernel<<<pl.nchunks, 1024, 0, st>>>(hist, 256u * (unsigned)pl.nblk, sums, counters + 1 + pass);
         pl_sort_scatter_kernel<<<pl.nblk, 256, 0, st>>>(sk[cur], sv[cur], sk[cur ^ 1], sv[cur ^ 1], E, 8 * pass, hist, sums, pl.nblk);
         cur ^= 1;
     }
