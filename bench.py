@@ -230,6 +230,7 @@ def main():
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch run of the unmodified reference on this GPU")
+    ap.add_argument("--no-bilateral", action="store_true", help="skip the bilateral-filter side measurement")
     ap.add_argument("--no-cupti", action="store_true", help="skip the CUPTI kernel summary of the replayed step (family rooflines)")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile", action="store_true", help="profiling run (under ncu): skip the e2e and cpu legs; numbers are not bench values")
@@ -492,6 +493,15 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args.cpu_baseline_steps, 1, 4, S, budget_s=60.0)
         out["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    if rank == 0 and world == 1 and not args.no_bilateral:
+        # second C-ABI path of the repo: the SCD DenseEnergyLoss bilateral filter, device vs the compiled reference on
+        # the host threads it can use; reported beside the headline, not part of it
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bilateral_bench as BB
+            out["bilateral_filter"] = [BB.run_workload(*w, iters=20, hbm=pk["hbm"]) for w in BB.WORKLOADS[:2]]
+        except Exception as e:  # noqa: BLE001
+            out["bilateral_filter"] = {"error": repr(e)}
     if rank == 0:
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
