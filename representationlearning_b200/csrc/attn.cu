@@ -854,7 +854,8 @@ win_attn_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef lx, 
 //   Q^T K gate terms added on the fp32 accumulators;  d(tokens) = G.W;  dW += G^T X  (persistent register accumulators).
 // ------------------------------------------------------------------------------------------
 constexpr int kPB = 72;                                  // bf16 row stride of the P / dS tiles (64 keys + pad, 144 B rows)
-constexpr int kBwdTcSmem = (11 * kRows * kTS + 4 * kRows * kPB + 4 * kC * kTS) * 2 + (4 * kC + 32) * 4;
+// 9 token tiles + P, dS of ONE head + 4 weight matrices: 75.4 KB -> 3 CTAs/SM (was 104 KB / 2 CTAs with both heads' P, dS resident)
+constexpr int kBwdTcSmem = (9 * kRows * kTS + 2 * kRows * kPB + 4 * kC * kTS) * 2 + (4 * kC + 32) * 4;
 
 // acc[nt] = A[16 rows][32] . W[k][n]  (W stored [k][n] row-major: the transposed use of a (out,in) weight)
 __device__ __forceinline__ void projT_mma(const __nv_bfloat16* A, const __nv_bfloat16* Wm, int row0, int lane, float acc[4][4], bool zero) {
@@ -878,7 +879,7 @@ __device__ __forceinline__ void projT_mma(const __nv_bfloat16* A, const __nv_bfl
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 win_attn_bwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef lx, LnRef ly, const float* __restrict__ gmap,
                        const T* __restrict__ dout, float* __restrict__ dxg, float* __restrict__ dyg,
                        rss_attn_params p, rss_attn_grads gr, WinGeom g) {
@@ -892,11 +893,13 @@ win_attn_bwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef l
     __nv_bfloat16* Om = vs + kRows * kTS;
     __nv_bfloat16* dAb = Om + kRows * kTS;
     __nv_bfloat16* Gq = dAb + kRows * kTS;
-    __nv_bfloat16* Gk = Gq + kRows * kTS;
-    __nv_bfloat16* Gv = Gk + kRows * kTS;
-    __nv_bfloat16* Pb = Gv + kRows * kTS;                 // [2 heads][64][72]
-    __nv_bfloat16* dSb = Pb + 2 * kRows * kPB;            // [2 heads][64][72]
-    __nv_bfloat16* Wsm = dSb + 2 * kRows * kPB;           // [4][32][40]
+    // dk, dv overwrite k, v: head h's columns of k / v are dead once the query side of head h is done (block barrier below), the
+    // key side reads only its own rows of k (gate terms) before it writes them, and nothing reads them again before the next window
+    __nv_bfloat16* Gk = ks;
+    __nv_bfloat16* Gv = vs;
+    __nv_bfloat16* Pb = Gq + kRows * kTS;                 // [64][72], one head at a time
+    __nv_bfloat16* dSb = Pb + kRows * kPB;                // [64][72]
+    __nv_bfloat16* Wsm = dSb + kRows * kPB;               // [4][32][40]
     float* bsm = reinterpret_cast<float*>(Wsm + 4 * kC * kTS);
     float* misc = bsm + 4 * kC;                           // [0..1] gate, [2..3] argmax (int), [4..11] dgate partials [h][warp]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
@@ -1020,7 +1023,7 @@ win_attn_bwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef l
 #pragma unroll
             for (int j = 0; j < 7; ++j) { S[j][0] *= i0; S[j][1] *= i0; S[j][2] *= i1; S[j][3] *= i1; }   // P
             // P -> smem (bf16) for dv = P^T dA
-            __nv_bfloat16* Prow = Pb + (h * kRows + row0) * kPB;
+            __nv_bfloat16* Prow = Pb + row0 * kPB;
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
                 *reinterpret_cast<uint32_t*>(Prow + gq * kPB + j * 8 + tq * 2) = pack_bf16(S[j][0], S[j][1]);
@@ -1069,7 +1072,7 @@ win_attn_bwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef l
             // dP = dA v^T (K = 16 head dims): A operand straight from the dA accumulators
             uint32_t ada[4] = {pack_bf16(dA[0][0], dA[0][1]), pack_bf16(dA[0][2], dA[0][3]),
                                pack_bf16(dA[1][0], dA[1][1]), pack_bf16(dA[1][2], dA[1][3])};
-            __nv_bfloat16* dSrow = dSb + (h * kRows + row0) * kPB;
+            __nv_bfloat16* dSrow = dSb + row0 * kPB;
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
                 float dP[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1102,19 +1105,16 @@ win_attn_bwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef l
                     mma_bf16(dq[h][nd], as, bkk);
                 }
             }
-        }
-        __syncthreads();
-        // ---- key side: this warp owns keys row0..row0+15: dk = dS^T q, dv = P^T dA ; then the Q^T K gate terms
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+            __syncthreads();
+            // ---- key side of head h: this warp owns keys row0..row0+15: dk = dS^T q, dv = P^T dA ; then the Q^T K gate terms
             float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
             for (int kq = 0; kq < 4; ++kq) {                 // queries 16kq..16kq+15 are the contraction index
                 uint32_t a1[4], a2[4];
                 const int i = lane >> 3;
                 // A[m=key][k=query] = dS[query][key]: transposed load of the [query][key] tile
-                ldsm_x4_t(a1, dSb + (h * kRows + kq * 16 + (lane & 7) + 8 * (i >> 1)) * kPB + row0 + 8 * (i & 1));
-                ldsm_x4_t(a2, Pb + (h * kRows + kq * 16 + (lane & 7) + 8 * (i >> 1)) * kPB + row0 + 8 * (i & 1));
+                ldsm_x4_t(a1, dSb + (kq * 16 + (lane & 7) + 8 * (i >> 1)) * kPB + row0 + 8 * (i & 1));
+                ldsm_x4_t(a2, Pb + (kq * 16 + (lane & 7) + 8 * (i >> 1)) * kPB + row0 + 8 * (i & 1));
 #pragma unroll
                 for (int nd = 0; nd < 2; ++nd) {
                     uint32_t bq[2], bd[2];
@@ -1124,7 +1124,6 @@ win_attn_bwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef l
                     mma_bf16(dv[nd], a2, bd);
                 }
             }
-            const float gate = misc[h];
             const float dz = (misc[4 + h * 4 + 0] + misc[4 + h * 4 + 1] + misc[4 + h * 4 + 2] + misc[4 + h * 4 + 3]) * gate * (1.0f - gate);
             const float u = dz * (1.0f / 256.0f);
             const int am = reinterpret_cast<int*>(misc)[2 + h], as_ = am >> 4, bs_ = am & 15;
@@ -1148,6 +1147,7 @@ win_attn_bwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef l
                         dk[nd][half * 2 + e] += u * qsum + (d == bs_ ? dz * q_as : 0.f);
                     }
             }
+            __syncwarp();                                    // every lane has read its rows of k (now overwritten by dk)
 #pragma unroll
             for (int nd = 0; nd < 2; ++nd) {
                 const int col = h * kHD + nd * 8 + tq * 2;
@@ -1159,8 +1159,8 @@ win_attn_bwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef l
                 *reinterpret_cast<uint32_t*>(Gv + r0 * kTS + col) = pack_bf16(dv[nd][0], dv[nd][1]);
                 *reinterpret_cast<uint32_t*>(Gv + r1 * kTS + col) = pack_bf16(dv[nd][2], dv[nd][3]);
             }
+            __syncthreads();                                 // P / dS of this head are free for the next one; Gq, Gk, Gv complete after h = 1
         }
-        __syncthreads();
         // ---- gradients w.r.t. the gated tokens (rows of this warp): dxs = Gq.Wq ; dys = Gk.Wk + Gv.Wv
         {
             float ax[4][4], ay[4][4];
@@ -1475,6 +1475,7 @@ static int attn_bwd_impl(const void* dout, const void* x, const void* y, const r
     int grid = num_sms() * 2;
     if (grid > g.nWin) grid = g.nWin;
     if (sizeof(T) == 2 && !(flags & RSS_ATTN_SIMT)) {
+        grid = num_sms() * 3 < g.nWin ? num_sms() * 3 : g.nWin;      // 75.4 KB of shared memory, <= 168 registers: 3 CTAs/SM
         static bool tc_attr = false;
         if (!tc_attr) {
             cudaFuncSetAttribute(win_attn_bwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
