@@ -26,6 +26,9 @@ struct WinGeom { int B, H, W, HW, ph, pw, qh, qw, nWin; };
 int layernorm_bwd_f32dy(const float* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                         const void* dx_add, void* dx, float* dgamma_acc, float* dbeta_acc, int64_t rows, int C, int dtype,
                         cudaStream_t stream);
+int layernorm_bwd_gated(const float* dxg, const float* dyg, const void* x, const void* y, const float* stats, const float* gamma,
+                        const void* dx_add, void* dx, void* dy, float* dgamma_acc, float* dbeta_acc, int64_t rows, int HW,
+                        const float* gmap, const float* dpooled, const uint8_t* amax, int dtype, cudaStream_t stream);
 
 static inline WinGeom make_geom(int B, int H, int W) {
     WinGeom g; g.B = B; g.H = H; g.W = W; g.HW = H * W;
@@ -441,8 +444,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 template <typename T>
 __device__ __forceinline__ void load_window_bf16(const T* __restrict__ src, const LnRef& ln, const float* __restrict__ gate_b,
                                                  __nv_bfloat16* dst, const WinGeom& g, int b, int wi, int wj) {
+    // idx = threadIdx.x + k * kThreads and kThreads % 4 == 0: a thread always handles the same 8-channel part, so its LayerNorm
+    // weights are loaded once per window instead of once per token
+    const int part = threadIdx.x & 3;
+    float gm[8], bt[8];
+    if (ln.mean) {
+        load8(ln.gamma + part * 8, gm);
+        load8(ln.beta + part * 8, bt);
+    }
+    const bool gate_vec = (g.HW & 7) == 0;                   // then the 8 gate values of a part never wrap around HW
     for (int idx = threadIdx.x; idx < kRows * 4; idx += kThreads) {
-        const int t = idx >> 2, part = idx & 3;
+        const int t = idx >> 2;
         const int n = t < kL ? token_pixel(g, wi, wj, t) : -1;
         float v[8];
 #pragma unroll
@@ -452,12 +464,19 @@ __device__ __forceinline__ void load_window_bf16(const T* __restrict__ src, cons
             if (ln.mean) {
                 const float mu = ln.mean[(size_t)b * g.HW + n], rs = ln.rstd[(size_t)b * g.HW + n];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = (v[i] - mu) * rs * ln.gamma[part * 8 + i] + ln.beta[part * 8 + i];
+                for (int i = 0; i < 8; ++i) v[i] = (v[i] - mu) * rs * gm[i] + bt[i];
             }
             if (gate_b) {
                 int gi = (int)(((uint32_t)n * kC + part * 8) % (uint32_t)g.HW);      // n < HW <= 2^26: 32-bit modulo
+                if (gate_vec) {
+                    float gv[8];
+                    load8(gate_b + gi, gv);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { v[i] *= gate_b[gi]; if (++gi == g.HW) gi = 0; }
+                    for (int i = 0; i < 8; ++i) v[i] *= gv[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { v[i] *= gate_b[gi]; if (++gi == g.HW) gi = 0; }
+                }
             }
         }
         *reinterpret_cast<uint4*>(dst + t * kTS + part * 8) =
@@ -485,7 +504,7 @@ __device__ __forceinline__ void proj_mma(const __nv_bfloat16* A, const __nv_bflo
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 6)
 win_attn_fwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef lx, LnRef ly, const float* __restrict__ gmap,
                        const T* __restrict__ xres, T* __restrict__ out, rss_attn_params p, WinGeom g) {
     __shared__ __align__(16) __nv_bfloat16 xs[kRows * kTS], ys[kRows * kTS], qkv[3 * kRows * kTS], Wsm[4 * kC * kTS];
@@ -1506,6 +1525,15 @@ static int attn_bwd_impl(const void* dout, const void* x, const void* y, const r
     if (ag > 1024) ag = 1024;
     dim3 apg(ag, B, 2);
     // the apply kernel is elementwise: in place (fp32) when LayerNorm backward follows, else straight into dx/dy
+    // with LayerNorm-1 behind it (the block path) and HW % 8 == 0 the apply step rides on the LayerNorm backward's load of the gradient:
+    // one launch for gate apply + both LayerNorm backwards (RSS_GATE_LN_FUSED=0: the three separate launches)
+    static const bool fuse_ln = !(getenv("RSS_GATE_LN_FUSED") && getenv("RSS_GATE_LN_FUSED")[0] == '0');
+    if (has_ln && fuse_ln && (g.HW & 7) == 0 && kC == 32) {
+        int rc0 = check_launch();
+        if (rc0 != RSS_OK) return rc0;
+        return layernorm_bwd_gated(dxg, dyg, x, y, ln_stats, p->ln_w, has_res ? dout : nullptr, dx, dy, gr->ln_w, gr->ln_b, rows, g.HW,
+                                   gmap, dpooled, amax, dt, st);
+    }
     if (has_ln) gate_bwd_apply_kernel<T, float><<<apg, 256, 0, st>>>(dxg, dyg, gmap, dpooled, amax, (const T*)nullptr, dxg, dyg, g.HW);
     else gate_bwd_apply_kernel<T, T><<<apg, 256, 0, st>>>(dxg, dyg, gmap, dpooled, amax, has_res ? (const T*)dout : (const T*)nullptr,
                                                           (T*)dx, (T*)dy, g.HW);

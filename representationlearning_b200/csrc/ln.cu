@@ -121,6 +121,99 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
     }
 }
 
+// LayerNorm-1 backward of BOTH token streams of the attention region (x: queries + residual, y: keys/values) in one launch, with the
+// element-wise tail of the saliency-gate backward applied to the incoming gradient on load:
+//   d normed[f] = d gated[f] * gate[f mod HW] + d avgpool[f mod HW] / C + (argmax[f mod HW] == f div HW ? d maxpool[f mod HW] : 0)
+// (f = flat index n*C + c of the token tensor of one image: the reference pools over the flat (C, H, W) VIEW of token memory,
+// multihead_isa_pool_attention.py:150-151).  Replaces gate_bwd_apply_kernel (an in-place fp32 read-modify-write of both 33.5 MB
+// gradient tensors) + two ln_bwd_kernel launches; same expressions in the same order, so the results are bit-identical.
+// Needs HW % 8 == 0 (the 8 flat positions of a lane stay inside one row of the view); C = 32.
+template <typename T>
+__global__ void __launch_bounds__(256) ln_bwd_gated_kernel(const float* __restrict__ dxg, const float* __restrict__ dyg, const T* __restrict__ x,
+                                                           const T* __restrict__ y, const float* __restrict__ stats /*[4][rows]*/,
+                                                           const float* __restrict__ gamma, const T* __restrict__ dx_add,
+                                                           T* __restrict__ dx, T* __restrict__ dy, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int64_t rows, int HW,
+                                                           const float* __restrict__ gmap, const float* __restrict__ dpooled,
+                                                           const uint8_t* __restrict__ amax) {
+    constexpr int TPT = 4, C = 32;
+    __shared__ float red[2][256 / TPT][C + 1];
+    const int z = blockIdx.y;
+    const float* dyv = z == 0 ? dxg : dyg;
+    const T* xv = z == 0 ? x : y;
+    T* dxo = z == 0 ? dx : dy;
+    const T* add = z == 0 ? dx_add : nullptr;
+    const float* mean = stats + (size_t)(2 * z) * rows;
+    const float* rstd = stats + (size_t)(2 * z + 1) * rows;
+    const int sub = threadIdx.x % TPT;
+    const int grp = threadIdx.x / TPT;
+    float g[8], ag[8], ab[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g[i] = gamma[sub * 8 + i]; ag[i] = 0.f; ab[i] = 0.f; }
+    const int64_t rows_per_block = blockDim.x / TPT;
+    const int64_t iters = (rows + rows_per_block * gridDim.x - 1) / (rows_per_block * gridDim.x);
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t row = (it * gridDim.x + blockIdx.x) * rows_per_block + grp;
+        const bool live = row < rows;
+        float d[8], v[8];
+        float mu = 0.f, rs = 0.f;
+        if (live) {
+            load8(dyv + row * C + sub * 8, d);
+            load8(xv + row * C + sub * 8, v);
+            mu = mean[row]; rs = rstd[row];
+            const int b = (int)(row / HW), n = (int)(row - (int64_t)b * HW);
+            const uint32_t f0 = (uint32_t)n * C + sub * 8;
+            const int kk = (int)(f0 / (uint32_t)HW), j = (int)(f0 - (uint32_t)kk * (uint32_t)HW);
+            float g8[8], a8[8], m8[8];
+            load8(gmap + ((size_t)b * 2 + z) * HW + j, g8);
+            load8(dpooled + ((size_t)b * 4 + z * 2 + 0) * HW + j, a8);
+            load8(dpooled + ((size_t)b * 4 + z * 2 + 1) * HW + j, m8);
+            const uint2 am8 = __ldg(reinterpret_cast<const uint2*>(amax + ((size_t)b * 2 + z) * HW + j));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int a = (int)(((i < 4 ? am8.x : am8.y) >> (8 * (i & 3))) & 0xffu);
+                d[i] = d[i] * g8[i] + a8[i] * (1.0f / C) + (a == kk ? m8[i] : 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { d[i] = 0.f; v[i] = 0.f; }
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[i] = (v[i] - mu) * rs;                  // xhat
+            ag[i] += d[i] * v[i];
+            ab[i] += d[i];
+            d[i] *= g[i];                             // dy*gamma
+            s1 += d[i];
+            s2 += d[i] * v[i];
+        }
+        s1 = group_sum<TPT>(s1) * (1.0f / C);
+        s2 = group_sum<TPT>(s2) * (1.0f / C);
+        if (live) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = rs * (d[i] - s1 - v[i] * s2);
+            if (add) {
+                float a[8];
+                load8(add + row * C + sub * 8, a);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] += a[i];
+            }
+            store8(dxo + row * C + sub * 8, o);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red[0][grp][sub * 8 + i] = ag[i]; red[1][grp][sub * 8 + i] = ab[i]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+        const int which = c / C, ch = c % C;
+        float s = 0.f;
+        for (int r = 0; r < (int)rows_per_block; ++r) s += red[which][r][ch];
+        atomicAdd((which == 0 ? dgamma : dbeta) + ch, s);
+    }
+}
+
 template <typename T>
 static int ln_fwd_launch(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta, float eps,
                          int64_t rows, int C, cudaStream_t st) {
@@ -170,6 +263,19 @@ extern "C" int rss_layernorm_bwd(const void* dy, const void* x, const float* mea
 
 // internal variant used by the attention region: the incoming gradient is fp32 whatever the activation dtype
 namespace rss {
+int layernorm_bwd_gated(const float* dxg, const float* dyg, const void* x, const void* y, const float* stats, const float* gamma,
+                        const void* dx_add, void* dx, void* dy, float* dgamma_acc, float* dbeta_acc, int64_t rows, int HW,
+                        const float* gmap, const float* dpooled, const uint8_t* amax, int dtype, cudaStream_t stream) {
+    if (rows <= 0) return RSS_OK;
+    if (HW <= 0 || (HW & 7) || rows % HW) return RSS_ERR_SHAPE;
+    int grid = (int)((rows + 63) / 64);
+    const int cap = num_sms() * 4;                       // x 2 token streams in grid.y
+    if (grid > cap) grid = cap;
+    RSS_DISPATCH_DTYPE(dtype, (ln_bwd_gated_kernel<T><<<dim3(grid, 2), 256, 0, stream>>>(dxg, dyg, (const T*)x, (const T*)y, stats, gamma,
+                                                                                         (const T*)dx_add, (T*)dx, (T*)dy, dgamma_acc, dbeta_acc,
+                                                                                         rows, HW, gmap, dpooled, amax)));
+    return check_launch();
+}
 int layernorm_bwd_f32dy(const float* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                         const void* dx_add, void* dx, float* dgamma_acc, float* dbeta_acc, int64_t rows, int C, int dtype,
                         cudaStream_t stream) {
