@@ -10,7 +10,9 @@
  * here, plus an int status:
  *
  *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator); the library
- *     allocates nothing, keeps no state between calls, and launches only on the `stream` it is given;
+ *     allocates nothing and launches only on the `stream` it is given (one exception, stated at its declaration:
+ *     rss_bilateralfilter_batch_host takes HOST arrays and owns a device arena); the only state kept between calls is per-process
+ *     launch configuration read once (opt-in shared-memory attributes, SM count, RSS_* environment switches): one GPU per process;
  *   - no host synchronisation, no host reads of device data;
  *   - activations are NHWC (== token-major (B, H*W, C)), element type selected by `dtype`
  *     (RSS_F32 or RSS_BF16); parameters, statistics and all accumulation are fp32;
@@ -168,21 +170,6 @@ int rss_sync_bn_finalize(const int64_t* bases, int64_t chan_off_bytes, int rank,
                          const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                          float* mean_out, float* invstd_out, float* scale, float* shift, const float* pre_bias, cudaStream_t stream);
 
-/* One-launch versions for activations that stay L2-resident between the two passes (<= 40 MB, ReLU / no activation):
- * statistics -> device-wide spin barrier -> apply, and reduce -> barrier -> apply.  Grid <= one block per SM, >= 4 resident blocks
- * per SM, so up to 4 concurrent streams can each hold a full grid.  accum_scratch: persistent zeroed float[2*C]; sync_scratch:
- * persistent zeroed unsigned[2]; both are left zeroed.  Single rank only (SyncBN under a process group keeps the split kernels). */
-int rss_bn_fused_supported(int64_t rows, int C, int act, int dtype);
-int rss_bn_fwd_fused(const void* x, const void* residual /*may be NULL*/, void* y, float* accum_scratch, unsigned int* sync_scratch,
-                     int64_t rows, int C, int act, int dtype, const float* gamma, const float* beta,
-                     float* running_mean /*may be NULL*/, float* running_var, float momentum, float eps,
-                     float* mean_out, float* invstd_out, float* scale, float* shift, const float* pre_bias /*may be NULL*/,
-                     cudaStream_t stream);
-int rss_bn_bwd_fused(const void* x, const void* y /*saved output, residual ReLU layers only*/, const void* dy,
-                     const float* scale, const float* shift, const float* mean, const float* invstd,
-                     float* accum_scratch, unsigned int* sync_scratch, void* dx, void* dresidual /*may be NULL*/,
-                     int64_t rows, int C, int act, int dtype, float* sums_out /*[2C] or NULL*/,
-                     float* dgamma_acc /*may be NULL*/, float* dbeta_acc, cudaStream_t stream);
 
 /* ---- multi-resolution fuse sum of HighResolutionModule.forward (_hrnet_rssformer.py:418-435) and the residual+ReLU closing a
  *      transformer block (MTFM.py:109, _hrnet_rssformer.py:435): out = [relu](sum_j nearest_up_{2^k_j}(term_j)), NHWC ---- */

@@ -71,9 +71,6 @@ SIGNATURES = {
     "rss_sync_exchange_bytes": (c_size_t, [c_int]),
     "rss_sync_allreduce_small": (c_int, [P, c_int64, c_int, c_int, P, P, c_int, P, P, P]),
     "rss_sync_bn_finalize": (c_int, [P, c_int64, c_int, c_int, P, P, c_int, c_int64, P, P, P, P, c_float, c_float, P, P, P, P, P, P]),
-    "rss_bn_fused_supported": (c_int, [c_int64, c_int, c_int, c_int]),
-    "rss_bn_fwd_fused": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P, c_float, c_float, P, P, P, P, P, P]),
-    "rss_bn_bwd_fused": (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P]),
     "rss_fuse_sum_fwd": (c_int, [POINTER(c_void_p), POINTER(c_int), c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "rss_fuse_sum_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "rss_conv_igemm_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),

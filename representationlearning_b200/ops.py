@@ -17,7 +17,7 @@ CL = torch.channels_last
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; counted from the csrc/*.cu launch sites)
 KERNELS_PER_CALL = {
     "rss_layernorm_fwd": 1, "rss_layernorm_bwd": 1, "rss_attn_fwd": 5, "rss_spatial_attention_fwd": 2, "rss_bilinear_resize": 1, "rss_confusion_matrix": 1, "rss_accum_bf16_list": 1, "rss_attn_bwd": 7, "rss_bn_stats": 1, "rss_bn_combine": 1,
-    "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1, "rss_bn_fwd_fused": 1, "rss_bn_bwd_fused": 1, "rss_sync_bn_finalize": 1, "rss_sync_allreduce_small": 1, "rss_bn_stats_raw": 1,
+    "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1, "rss_sync_bn_finalize": 1, "rss_sync_allreduce_small": 1, "rss_bn_stats_raw": 1,
     "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 4, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
     "rss_headaux_fwd": 2, "rss_seg_loss_fwd": 2, "rss_seg_loss_bwd": 1, "rss_grad_sumsq": 1, "rss_sgd_step": 1,
     "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_conv_wgrad": 1, "rss_conv_wgrad_tc": 1, "rss_conv_cf": 1, "rss_shadow_t_refresh": 1, "rss_shadow_cl_refresh": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
@@ -102,10 +102,8 @@ def grad_sink(p):
 
 
 import os
-# one-launch BatchNorm (statistics/reduce + device-wide spin barrier + apply) for L2-resident activations.  Measured on the B=16 step
-# (gpurun 2026-10-17): the barrier costs more than the launch it saves -- 13-32 us per fused kernel vs ~10 + ~5 us for the two
-# split kernels, 382 vs 418 img/s -- so it is OFF by default; the kernels stay in the library (tests run them) for round 2.
-BN_FUSED = {"on": os.environ.get("RSS_BN_FUSED", "0") != "0"}
+# (a one-launch BatchNorm with a device-wide spin barrier between the statistics and the apply phase was measured at 382 vs 418 img/s
+#  -- the barrier costs more than the launch it saves -- and removed from the library after round 2)
 BN_KEEP_DZ = {"on": os.environ.get("RSS_BN_KEEP_DZ", "1") != "0"}
 # (round 2 also tried one-launch BatchNorm with 8-CTA thread-block clusters per 16-channel slice exchanging partial sums through
 #  distributed shared memory -- no atomics, no tickets: correct, but 37-52 us vs 14-15 us for the two split kernels on the 8.4 MB
@@ -316,66 +314,58 @@ class BNAct(torch.autograd.Function):
             if not training:
                 raise _lib.RssError("pre_bias folding is only valid for training-mode BatchNorm")
             pre_bias = _f32(pre_bias)
-        fused = BN_FUSED["on"] and training and world == 1 and bool(lib.rss_bn_fused_supported(rows, C, act, dt))
-        if fused and (scratch is None or scratch.numel() < 2 + 2 * C):
-            scratch = torch.zeros(2 + 2 * C, device=dev, dtype=torch.float32)   # [0:2] barrier counters, [2:] accumulators; left zeroed
         y = torch.empty_like(x, memory_format=CL)
         account("bn", None if (have_aff or not training) else x, x, residual, y)     # statistics pass + apply pass
         raw = False
-        if fused and not have_aff:          # statistics + apply in ONE launch (device-wide barrier in between)
-            check(lib.rss_bn_fwd_fused(_p(x), _p(residual), _p(y), _p(scratch[2:]), _p(scratch), rows, C, act, dt, _p(g), _p(b),
-                                       _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
-                                       _p(aff[3]), _p(pre_bias), st), "rss_bn_fwd_fused")
-        else:
-            if have_aff:
-                pass
-            elif training and world == 1:
-                if scratch is None or scratch.numel() < 2 + 2 * C:      # [0] last-block ticket, [2:] accumulators; kernel leaves zeros
-                    scratch = torch.zeros(2 + 2 * C, device=dev, dtype=torch.float32)
-                raw = BN_RAW["on"]
-                if raw:
-                    check(lib.rss_bn_stats_raw(_p(x), _p(scratch[2:]), rows, C, dt, _p(running_mean), _p(pre_bias), st), "rss_bn_stats_raw")
-                    check(lib.rss_bn_act_fwd_raw(_p(x), _p(residual), _p(y), _p(scratch[2:]), _p(scratch), rows, C, act, dt, _p(g), _p(b),
-                                                 _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
-                                                 _p(aff[3]), _p(pre_bias), st), "rss_bn_act_fwd_raw")
+        if have_aff:
+            pass
+        elif training and world == 1:
+            if scratch is None or scratch.numel() < 2 + 2 * C:      # [0] last-block ticket, [2:] accumulators; kernel leaves zeros
+                scratch = torch.zeros(2 + 2 * C, device=dev, dtype=torch.float32)
+            raw = BN_RAW["on"]
             if raw:
-                pass
-            elif have_aff:
-                pass
-            elif training and world == 1:
-                check(lib.rss_bn_stats_fused(_p(x), _p(scratch[2:]), _p(scratch), rows, C, dt, _p(g), _p(b),
-                                             _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
-                                             _p(aff[3]), _p(pre_bias), st), "rss_bn_stats_fused")
-            elif (training and world > 1 and scratch is not None and scratch.numel() >= 2 + 2 * C and sync_exchange(group, dev, C) is not None
-                  and sync_exchange(group, dev, C).channel(scratch) is not None):
-                # SyncBN: raw local sums -> one-shot exchange over NVLink peer memory, finalised by the same one-CTA kernel
-                ex = sync_exchange(group, dev, C)
-                off, cnt = ex.channel(scratch)
                 check(lib.rss_bn_stats_raw(_p(x), _p(scratch[2:]), rows, C, dt, _p(running_mean), _p(pre_bias), st), "rss_bn_stats_raw")
-                check(lib.rss_sync_bn_finalize(_p(ex.bases), off, ex.rank, ex.world, cnt, _p(scratch[2:]), C, rows, _p(g), _p(b),
-                                               _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
-                                               _p(aff[3]), _p(pre_bias), st), "rss_sync_bn_finalize")
-            elif training:
-                nparts = lib.rss_bn_stats_nparts(rows, C)
-                part = torch.empty(nparts * C * 2 + nparts, device=dev, dtype=torch.float32)
-                cnt = part[nparts * C * 2:]
-                check(lib.rss_bn_stats(_p(x), _p(part), _p(cnt), rows, C, dt, st), "rss_bn_stats")
-                stat = torch.empty(C * 2 + 1, device=dev, dtype=torch.float32)
-                check(lib.rss_bn_combine(_p(part), _p(cnt), nparts, C, _p(stat), _p(stat[C * 2:]), st), "rss_bn_combine")
-                if world > 1:     # SyncBN: exchange (mean, M2, count) per rank, Chan-combine again
-                    gathered = torch.empty(world, C * 2 + 1, device=dev, dtype=torch.float32)
-                    dist.all_gather_into_tensor(gathered, stat, group=None if group is True else group)
-                    parts = gathered[:, :C * 2].contiguous()
-                    cnts = gathered[:, C * 2].contiguous()
-                    check(lib.rss_bn_combine(_p(parts), _p(cnts), world, C, _p(stat), _p(stat[C * 2:]), st), "rss_bn_combine")
-                check(lib.rss_bn_finalize(_p(stat), _p(stat[C * 2:]), _p(g), _p(b), _p(running_mean), _p(running_var),
-                                          momentum, eps, C, _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), _p(pre_bias), st), "rss_bn_finalize")
-            else:
-                check(lib.rss_bn_eval_affine(_p(g), _p(b), _p(running_mean), _p(running_var), eps, C,
-                                             _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), st), "rss_bn_eval_affine")
-            if not raw:
-                check(lib.rss_bn_act_fwd(_p(x), _p(residual), _p(y), _p(aff[2]), _p(aff[3]), rows, C, act, dt, st), "rss_bn_act_fwd")
-        ctx.fused, ctx.scratch = fused, scratch
+                check(lib.rss_bn_act_fwd_raw(_p(x), _p(residual), _p(y), _p(scratch[2:]), _p(scratch), rows, C, act, dt, _p(g), _p(b),
+                                             _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
+                                             _p(aff[3]), _p(pre_bias), st), "rss_bn_act_fwd_raw")
+        if raw:
+            pass
+        elif have_aff:
+            pass
+        elif training and world == 1:
+            check(lib.rss_bn_stats_fused(_p(x), _p(scratch[2:]), _p(scratch), rows, C, dt, _p(g), _p(b),
+                                         _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
+                                         _p(aff[3]), _p(pre_bias), st), "rss_bn_stats_fused")
+        elif (training and world > 1 and scratch is not None and scratch.numel() >= 2 + 2 * C and sync_exchange(group, dev, C) is not None
+              and sync_exchange(group, dev, C).channel(scratch) is not None):
+            # SyncBN: raw local sums -> one-shot exchange over NVLink peer memory, finalised by the same one-CTA kernel
+            ex = sync_exchange(group, dev, C)
+            off, cnt = ex.channel(scratch)
+            check(lib.rss_bn_stats_raw(_p(x), _p(scratch[2:]), rows, C, dt, _p(running_mean), _p(pre_bias), st), "rss_bn_stats_raw")
+            check(lib.rss_sync_bn_finalize(_p(ex.bases), off, ex.rank, ex.world, cnt, _p(scratch[2:]), C, rows, _p(g), _p(b),
+                                           _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
+                                           _p(aff[3]), _p(pre_bias), st), "rss_sync_bn_finalize")
+        elif training:
+            nparts = lib.rss_bn_stats_nparts(rows, C)
+            part = torch.empty(nparts * C * 2 + nparts, device=dev, dtype=torch.float32)
+            cnt = part[nparts * C * 2:]
+            check(lib.rss_bn_stats(_p(x), _p(part), _p(cnt), rows, C, dt, st), "rss_bn_stats")
+            stat = torch.empty(C * 2 + 1, device=dev, dtype=torch.float32)
+            check(lib.rss_bn_combine(_p(part), _p(cnt), nparts, C, _p(stat), _p(stat[C * 2:]), st), "rss_bn_combine")
+            if world > 1:     # SyncBN: exchange (mean, M2, count) per rank, Chan-combine again
+                gathered = torch.empty(world, C * 2 + 1, device=dev, dtype=torch.float32)
+                dist.all_gather_into_tensor(gathered, stat, group=None if group is True else group)
+                parts = gathered[:, :C * 2].contiguous()
+                cnts = gathered[:, C * 2].contiguous()
+                check(lib.rss_bn_combine(_p(parts), _p(cnts), world, C, _p(stat), _p(stat[C * 2:]), st), "rss_bn_combine")
+            check(lib.rss_bn_finalize(_p(stat), _p(stat[C * 2:]), _p(g), _p(b), _p(running_mean), _p(running_var),
+                                      momentum, eps, C, _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), _p(pre_bias), st), "rss_bn_finalize")
+        else:
+            check(lib.rss_bn_eval_affine(_p(g), _p(b), _p(running_mean), _p(running_var), eps, C,
+                                         _p(aff[0]), _p(aff[1]), _p(aff[2]), _p(aff[3]), st), "rss_bn_eval_affine")
+        if not raw:
+            check(lib.rss_bn_act_fwd(_p(x), _p(residual), _p(y), _p(aff[2]), _p(aff[3]), rows, C, act, dt, st), "rss_bn_act_fwd")
+        ctx.scratch = scratch
         ctx.save_for_backward(x, y if (act == _lib.ACT_RELU and residual is not None) else None, aff)
         ctx.act, ctx.training, ctx.group, ctx.world, ctx.has_res = act, training, group, world, residual is not None
         ctx.refs = (gamma, beta)
@@ -396,15 +386,6 @@ class BNAct(torch.autograd.Function):
         dx = torch.empty_like(x, memory_format=CL)
         dres = torch.empty_like(x, memory_format=CL) if ctx.has_res else None
         account("bn", x, dy, y, x, dy, y, dx, dres)                                   # reduce pass + apply pass
-        if ctx.fused:                       # reduce + apply in ONE launch (training mode, single rank, L2-resident tensor)
-            local = None if direct else torch.empty(2 * C, device=x.device, dtype=torch.float32)
-            sc = ctx.scratch
-            check(lib.rss_bn_bwd_fused(_p(x), _p(y), _p(dy), _p(aff[2]), _p(aff[3]), _p(aff[0]), _p(aff[1]), _p(sc[2:]), _p(sc),
-                                       _p(dx), _p(dres), rows, C, ctx.act, dt, _p(local), _p(sg) if direct else None,
-                                       _p(sb) if direct else None, st), "rss_bn_bwd_fused")
-            if direct:
-                return (dx, dres) + (None,) * 12
-            return (dx, dres, local[C:], local[:C]) + (None,) * 10
         sums = torch.empty(2 * C, device=x.device, dtype=torch.float32)
         sc = ctx.scratch        # the layer's persistent zeroed scratch (forward statistics kernel): no memset node per launch
         have_sc = sc is not None and sc.numel() >= 2 + 2 * C

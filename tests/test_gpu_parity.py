@@ -65,12 +65,12 @@ def test_layernorm(P, report, dtype, shape):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("act", [0, 1, 2])
 @pytest.mark.parametrize("shape,res", [((2, 32, 16, 16), False), ((2, 64, 9, 11), True), ((1, 480, 8, 8), False), ((4, 128, 32, 32), True)])
-@pytest.mark.parametrize("proto", ["split", "fused"])
+@pytest.mark.parametrize("proto", ["split", "raw"])
 def test_bn_act(P, report, dtype, act, shape, res, proto, monkeypatch):
     from representationlearning_b200 import ops
-    fused = proto == "fused"
-    # split: statistics + apply kernels (atomics + ticket); fused: one launch with a device-wide barrier (round 1, off by default)
-    monkeypatch.setitem(ops.BN_FUSED, "on", fused)
+    # split: statistics kernel finalises (atomics + ticket), apply kernel streams; raw: the statistics / reduce kernels only add sums
+    # and the apply kernels finalise (the protocol the peer-memory SyncBN exchange builds on; off by default on one rank)
+    monkeypatch.setitem(ops.BN_RAW, "on", proto == "raw")
     torch.manual_seed(2)
     B, C, H, W = shape
     if act == 2 and res:      # not a pattern of the reference: the ABI must refuse it, loudly
