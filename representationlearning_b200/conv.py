@@ -280,7 +280,8 @@ class _ConvIgemm(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cfg, *wb):
-        ksizes, dils, bias_grad = cfg
+        ksizes, dils, bias_grad = cfg[:3]
+        stats = cfg[3] if len(cfg) > 3 else None         # (scratch, running_mean): BatchNorm raw sums from the GEMM's epilogue
         n = len(ksizes)
         weights, biases = wb[:n], wb[n:]
         lib = _lib.load()
@@ -290,10 +291,16 @@ class _ConvIgemm(torch.autograd.Function):
         packed, bias_sum, nt, dy, dx, keep = _pack(weights, biases, ksizes, dils, Cout, Cin, False, x.device)
         y = torch.empty((B, Cout, H, W), device=x.device, dtype=x.dtype, memory_format=CL)
         with ops.timed("rss_conv_igemm"):
-            ops.check(lib.rss_conv_igemm(x.data_ptr(), packed.data_ptr(), None if bias_sum is None else bias_sum.data_ptr(),
-                                         y.data_ptr(), B, H, W, Cin, Cout, nt, dy, dx, ops._st()), "rss_conv_igemm")
+            if stats is not None:
+                scratch, shift = stats
+                ops.check(lib.rss_conv_igemm_stats(x.data_ptr(), packed.data_ptr(), None if bias_sum is None else bias_sum.data_ptr(),
+                                                   y.data_ptr(), B, H, W, Cin, Cout, nt, dy, dx, scratch[2:].data_ptr(), ops._p(shift),
+                                                   ops._st()), "rss_conv_igemm_stats")
+            else:
+                ops.check(lib.rss_conv_igemm(x.data_ptr(), packed.data_ptr(), None if bias_sum is None else bias_sum.data_ptr(),
+                                             y.data_ptr(), B, H, W, Cin, Cout, nt, dy, dx, ops._st()), "rss_conv_igemm")
         ctx.save_for_backward(x)
-        ctx.cfg, ctx.refs, ctx.n = cfg, wb, n
+        ctx.cfg, ctx.refs, ctx.n = cfg[:3], wb, n
         return y
 
     @staticmethod
@@ -481,12 +488,26 @@ def conv_bn_stats(x, weight, stride, padding, dilation, bn_stats):
     return _ConvLib.apply(x, weight, None, stride, padding, dilation, False), None
 
 
-def conv_sum(x, convs, bias_grad=True):
+# BatchNorm statistics of the FFN's norm2 from the epilogue of the dw + dw6 + dw12 GEMM (rss_conv_igemm_stats); RSS_IGEMM_STATS=0: the
+# separate statistics pass over the 67 MB tensor
+ENGINE["igemm_stats"] = os.environ.get("RSS_IGEMM_STATS", "1") != "0"
+
+
+def conv_sum_stats_ok(x, Cout):
+    """True when conv_sum(x, ..., stats=...) would run the igemm kernel with the statistics epilogue"""
+    return ENGINE["igemm_stats"] and Cout <= 128 and _igemm_ok(x, Cout)
+
+
+def conv_sum(x, convs, bias_grad=True, stats=None):
     """sum of parallel stride-1 'same' convolutions of the same input (the FFN's dw + dw6 + dw12): one igemm launch when the
-    geometry is supported, else the library convs added up.  convs: list of (weight, bias, ksize, dilation)."""
+    geometry is supported, else the library convs added up.  convs: list of (weight, bias, ksize, dilation).
+    stats = (scratch, running_mean) of the BatchNorm that consumes the sum: its raw sums are produced by the GEMM's epilogue
+    (only valid when conv_sum_stats_ok(x, Cout); the BatchNorm is then called with aff=ops.RAW_SUMS)."""
     Cout = convs[0][0].shape[0]
+    if stats is not None and not conv_sum_stats_ok(x, Cout):
+        raise _lib.RssError("conv_sum: statistics epilogue requested for a geometry the igemm kernel does not cover")
     if _igemm_ok(x, Cout):
-        cfg = (tuple(c[2] for c in convs), tuple(c[3] for c in convs), bias_grad)
+        cfg = (tuple(c[2] for c in convs), tuple(c[3] for c in convs), bias_grad) + ((stats,) if stats is not None else ())
         return _ConvIgemm.apply(x, cfg, *[c[0] for c in convs], *[c[1] for c in convs])
     out = None
     for w, b, k, d in convs:

@@ -14,14 +14,15 @@
 // im2col buffer and no boundary code exist.  Operands land in 128B-swizzled shared memory, tcgen05.mma
 // (cta_group::1, M=128, kind::f16, bf16 x bf16 -> fp32) accumulates in TMEM, and a 4-warp epilogue drains
 // TMEM with tcgen05.ld (+bias, ->bf16) while the MMA warp already works on the next tile (2 TMEM stages).
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.  Persistent: one CTA per SM.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue (two warps per TMEM lane quarter, each taking every
+// other 16-column chunk: with the statistics epilogue four warps needed ~1.3x the MMA time of a tile).  Persistent: one CTA per SM.
 #include <stdlib.h>
 #include "tc05.cuh"
 
 namespace rss {
 
 constexpr int kBlockM = 128, kBlockK = 64, kUmmaK = 16;
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
 constexpr int kATileBytes = kBlockM * kBlockK * 2;          // 16 KB
 constexpr int kMaxTaps = 32;
 
@@ -53,10 +54,31 @@ __host__ __device__ inline uint32_t make_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 }
 
+// Sum over the 32 lanes of a warp of 16 per-lane values at once ("transposed" butterfly: every exchange step halves the number of
+// values a lane still carries, 8+4+2+1+1 = 16 shuffles instead of 16 x 5): returns the warp total of value index (lane >> 1) & 15.
+__device__ __forceinline__ float warp_reduce16(float (&a)[16], int lane) {
+#pragma unroll
+    for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+        const bool hi = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const float send = hi ? a[i] : a[i + w];
+            const float keep = hi ? a[i + w] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+}
+
 // ---- the kernel -------------------------------------------------------------------------------------
+// stat_accum != NULL: BatchNorm-statistics epilogue.  The epilogue warps also add, per output channel c, sum (y - K_c) and
+// sum (y - K_c)^2 of the bf16-ROUNDED outputs into stat_accum[c] / stat_accum[Cout + c] (K = stat_shift, or 0): the "raw sums" of
+// csrc/bn.cu's BnFin protocol, so the BatchNorm that follows needs no statistics pass over the tensor (FFN norm2 behind the
+// dw + dw6 + dw12 GEMM: a 67 MB read per block and step).  Needs n_tiles == 1 and block_n <= 128.
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, ConvGeom g, ConvTaps taps) {
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, ConvGeom g, ConvTaps taps,
+                  float* __restrict__ stat_accum, const float* __restrict__ stat_shift) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t b_tile_bytes = (uint32_t)g.block_n * kBlockK * 2;
     const uint32_t a_bytes = (uint32_t)g.mm * kATileBytes;                 // mm sub-tiles of 128 rows, one TMA box (BH*mm image rows)
@@ -72,7 +94,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + g.stages + s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(bars + 2 * g.stages + s), 1); mbar_init(smem_u32(bars + 2 * g.stages + 2 + s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(bars + 2 * g.stages + s), 1); mbar_init(smem_u32(bars + 2 * g.stages + 2 + s), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
@@ -145,38 +167,105 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
         }
     } else {
-        // ================= epilogue: TMEM -> registers -> (+bias, bf16) -> global =================
+        // ================= epilogue: TMEM -> registers -> (+bias, bf16) -> global (+ BatchNorm raw sums) =================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                // of the two warps of a quarter: takes the chunks with (chunk & 1) == half
         const int row = q * 32 + lane;                   // tile row == TMEM lane
         uint32_t acc = 0, acc_phase = 0;
+        const bool stats = stat_accum != nullptr;
+        float ssum[8], ssq[8];                           // per 16-channel chunk: this lane's channel is chunk*16 + (lane >> 1)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
             const int tx = mt % g.tiles_x, ty = (mt / g.tiles_x) % g.tiles_y, b = mt / (g.tiles_x * g.tiles_y);
             const int n0 = nt * g.block_n;
             mbar_wait(smem_u32(bars + 2 * g.stages + acc), acc_phase);
             tc_fence_after();
-            for (int m = 0; m < g.mm; ++m) {
-                const int x = tx * g.BW + row % g.BW, y = (ty * g.mm + m) * g.BH + row / g.BW;
-                const bool live = x < g.W && y < g.H;
-                __nv_bfloat16* dst = out + (((size_t)b * g.H + y) * g.W + x) * g.Cout + n0;
-                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols + m * g.block_n;
-                for (int c0 = 0; c0 < g.block_n; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(t_row + c0, r);
-                    tmem_ld_wait();
-                    if (live) {
-                        float v[16];
+            if (!stats) {
+                for (int m = 0; m < g.mm; ++m) {
+                    const int x = tx * g.BW + row % g.BW, y = (ty * g.mm + m) * g.BH + row / g.BW;
+                    const bool live = x < g.W && y < g.H;
+                    __nv_bfloat16* dst = out + (((size_t)b * g.H + y) * g.W + x) * g.Cout + n0;
+                    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols + m * g.block_n;
+                    for (int c0 = half * 16; c0 < g.block_n; c0 += 32) {
+                        uint32_t r[16];
+                        tmem_ld16(t_row + c0, r);
+                        tmem_ld_wait();
+                        if (live) {
+                            float v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (bias ? bias[n0 + c0 + i] : 0.f);
-                        store8(dst + c0, v);
-                        store8(dst + c0 + 8, v + 8);
+                            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (bias ? bias[n0 + c0 + i] : 0.f);
+                            store8(dst + c0, v);
+                            store8(dst + c0 + 8, v + 8);
+                        }
+                    }
+                }
+            } else {
+                // chunk-major order: both M sub-tiles of a 16-channel chunk are folded into one warp reduction
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const int c0 = ch * 16;
+                    if ((ch & 1) == half && c0 < g.block_n) {
+                        float bs[16], s16[16], q16[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            bs[i] = bias ? bias[c0 + i] : 0.f;
+                            s16[i] = 0.f; q16[i] = 0.f;
+                        }
+                        for (int m = 0; m < g.mm; ++m) {
+                            const int x = tx * g.BW + row % g.BW, y = (ty * g.mm + m) * g.BH + row / g.BW;
+                            const bool live = x < g.W && y < g.H;
+                            __nv_bfloat16* dst = out + (((size_t)b * g.H + y) * g.W + x) * g.Cout;
+                            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols + m * g.block_n;
+                            uint32_t r[16];
+                            tmem_ld16(t_row + c0, r);
+                            tmem_ld_wait();
+                            if (live) {
+                                float v[16];
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bs[i];
+                                store8(dst + c0, v);
+                                store8(dst + c0 + 8, v + 8);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const float d = __bfloat162float(__float2bfloat16_rn(v[i])) - (stat_shift ? stat_shift[c0 + i] : 0.f);
+                                    s16[i] += d;
+                                    q16[i] += d * d;
+                                }
+                            }
+                        }
+                        ssum[ch] += warp_reduce16(s16, lane);
+                        ssq[ch] += warp_reduce16(q16, lane);
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(bars + 2 * g.stages + 2 + acc));           // 4 warps -> count 4
+            if (lane == 0) mbar_arrive(smem_u32(bars + 2 * g.stages + 2 + acc));           // 8 warps -> count 8
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (stats) {
+            // every MMA of this CTA has completed (the last accumulator was committed before its epilogue began), so the pipeline's
+            // shared memory is free: the epilogue warps combine their channel totals there, then one atomic per channel and CTA
+            float* red = reinterpret_cast<float*>(smem);                 // [4 quarters][2][128]; a (quarter, chunk) has one owner warp
+            if ((lane & 1) == 0) {
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    if ((ch & 1) == half) {
+                        red[(q * 2 + 0) * 128 + ch * 16 + (lane >> 1)] = ssum[ch];
+                        red[(q * 2 + 1) * 128 + ch * 16 + (lane >> 1)] = ssq[ch];
+                    }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");               // the 8 epilogue warps only
+            const int c = (int)threadIdx.x - 64;
+            if (c < g.block_n) {
+                float s = 0.f, qq = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) { s += red[(w * 2 + 0) * 128 + c]; qq += red[(w * 2 + 1) * 128 + c]; }
+                atomicAdd(stat_accum + c, s);
+                atomicAdd(stat_accum + g.Cout + c, qq);
+            }
         }
     }
     tc_fence_before();
@@ -335,9 +424,12 @@ extern "C" int rss_conv_pack_weights(const float* const* weights, const float* c
 
 // y[b,y,x,:] = bias + sum_tap W_tap . x[b, y+dy_tap, x+dx_tap, :]   (zero outside the image); bf16 in/out, fp32 accumulate.
 // w_packed: bf16 [n_taps][Cout][Cin].  For a data gradient call it with (x=dY, Cin<->Cout swapped, transposed pack).
-extern "C" int rss_conv_igemm(const void* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int Cin, int Cout,
-                              int n_taps, const int* taps_dy, const int* taps_dx, cudaStream_t st) {
+// stat_accum / stat_shift: BatchNorm-statistics epilogue (see conv_igemm_kernel); Cout <= 128 only.
+extern "C" int rss_conv_igemm_stats(const void* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int Cin, int Cout,
+                                    int n_taps, const int* taps_dy, const int* taps_dx, float* stat_accum, const float* stat_shift,
+                                    cudaStream_t st) {
     if (!rss_conv_igemm_supported(B, H, W, Cin, Cout) || n_taps < 1 || n_taps > kMaxTaps) return RSS_ERR_SHAPE;
+    if (stat_accum && Cout > 128) return RSS_ERR_SHAPE;
     ConvGeom g;
     g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
     g.BW = W >= 128 ? 128 : W; g.BH = kBlockM / g.BW;
@@ -374,6 +466,11 @@ extern "C" int rss_conv_igemm(const void* x, const void* w_packed, const float* 
     int grid = num_sms();
     const int total_tiles = g.m_tiles * g.n_tiles;
     if (grid > total_tiles) grid = total_tiles;
-    conv_igemm_kernel<<<grid, kConvThreads, smem, st>>>(ma, mb, bias, (__nv_bfloat16*)y, g, taps);
+    conv_igemm_kernel<<<grid, kConvThreads, smem, st>>>(ma, mb, bias, (__nv_bfloat16*)y, g, taps, stat_accum, stat_shift);
     return check_launch();
+}
+
+extern "C" int rss_conv_igemm(const void* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int Cin, int Cout,
+                              int n_taps, const int* taps_dy, const int* taps_dx, cudaStream_t st) {
+    return rss_conv_igemm_stats(x, w_packed, bias, y, B, H, W, Cin, Cout, n_taps, taps_dy, taps_dx, nullptr, nullptr, st);
 }

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .conv import conv2d, conv_sum
+from .conv import conv2d, conv_sum, conv_sum_stats_ok
 
 BN_MOMENTUM = 0.1        # _hrnet_rssformer.py:27
 CL = torch.channels_last
@@ -172,9 +172,15 @@ class MlpDWBN(nn.Module):
     def forward_nchw(self, x):
         bg = not self.training       # every bias here feeds a training-mode BN: its gradient is identically zero
         x = self.norm1.after_conv(x, self.fc1.weight, self.fc1.bias)
-        c = conv_sum(x, [(self.dw.weight, self.dw.bias, 1, 1), (self.dw6.weight, self.dw6.bias, 3, 6),
-                         (self.dw12.weight, self.dw12.bias, 3, 12)], bias_grad=bg)
-        x = self.norm2(c)
+        convs = [(self.dw.weight, self.dw.bias, 1, 1), (self.dw6.weight, self.dw6.bias, 3, 6), (self.dw12.weight, self.dw12.bias, 3, 12)]
+        n2 = self.norm2
+        if conv_sum_stats_ok(x, n2.num_features) and ops.bn_accepts_raw_sums(x, n2.training, True if n2.sync else None, n2._scratch,
+                                                                             n2.num_features):
+            # norm2's statistics come out of the GEMM's epilogue: the 67 MB sum is written once and read once (by the apply pass)
+            c = conv_sum(x, convs, bias_grad=bg, stats=(n2._scratch, n2.running_mean))
+            x = n2(c, aff=ops.RAW_SUMS)
+        else:
+            x = n2(conv_sum(x, convs, bias_grad=bg))
         return self.norm3.after_conv(x, self.fc2.weight, self.fc2.bias)
 
     def forward(self, x, H, W):

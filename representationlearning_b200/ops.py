@@ -285,6 +285,22 @@ class WindowAttention(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 # BatchNorm(+SyncBN) + activation (+ residual)
 # ----------------------------------------------------------------------------------------------
+# BNAct(aff=RAW_SUMS): the layer's scratch already holds sum (x-K), sum (x-K)^2 with K = the running mean, produced by the epilogue of
+# the convolution that wrote x (rss_conv_igemm_stats): the statistics pass over x is skipped and the apply kernel (one rank) or the
+# peer-memory exchange kernel (SyncBN under a process group) finalises them.  Callers check bn_accepts_raw_sums() first.
+RAW_SUMS = "raw-sums"
+
+
+def bn_accepts_raw_sums(x, training, group, scratch, C):
+    if not training or scratch is None or scratch.numel() < 2 + 2 * C or not x.is_cuda:
+        return False
+    world = _world(group)
+    if world == 1:
+        return True
+    ex = sync_exchange(group, x.device, C)
+    return ex is not None and ex.channel(scratch) is not None
+
+
 class BNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, residual, gamma, beta, running_mean, running_var, training, momentum, eps, act, group, scratch=None,
@@ -304,7 +320,10 @@ class BNAct(torch.autograd.Function):
         rows = B * H * W
         dev, dt, st = x.device, _dt(x), _st()
         g, b = _f32(gamma), _f32(beta)
-        have_aff = aff is not None
+        raw_ready = isinstance(aff, str) and aff == RAW_SUMS
+        have_aff = aff is not None and not raw_ready
+        if raw_ready and not bn_accepts_raw_sums(x, training, group, scratch, C):
+            raise _lib.RssError("BNAct(aff=RAW_SUMS): this layer / process group cannot finalise raw sums")
         if not have_aff:
             aff = torch.empty(4, C, device=dev, dtype=torch.float32)      # mean, invstd, scale, shift
         world = _world(group) if training else 1
@@ -315,16 +334,17 @@ class BNAct(torch.autograd.Function):
                 raise _lib.RssError("pre_bias folding is only valid for training-mode BatchNorm")
             pre_bias = _f32(pre_bias)
         y = torch.empty_like(x, memory_format=CL)
-        account("bn", None if (have_aff or not training) else x, x, residual, y)     # statistics pass + apply pass
+        account("bn", None if (have_aff or raw_ready or not training) else x, x, residual, y)     # statistics pass + apply pass
         raw = False
         if have_aff:
             pass
         elif training and world == 1:
             if scratch is None or scratch.numel() < 2 + 2 * C:      # [0] last-block ticket, [2:] accumulators; kernel leaves zeros
                 scratch = torch.zeros(2 + 2 * C, device=dev, dtype=torch.float32)
-            raw = BN_RAW["on"]
+            raw = BN_RAW["on"] or raw_ready
             if raw:
-                check(lib.rss_bn_stats_raw(_p(x), _p(scratch[2:]), rows, C, dt, _p(running_mean), _p(pre_bias), st), "rss_bn_stats_raw")
+                if not raw_ready:
+                    check(lib.rss_bn_stats_raw(_p(x), _p(scratch[2:]), rows, C, dt, _p(running_mean), _p(pre_bias), st), "rss_bn_stats_raw")
                 check(lib.rss_bn_act_fwd_raw(_p(x), _p(residual), _p(y), _p(scratch[2:]), _p(scratch), rows, C, act, dt, _p(g), _p(b),
                                              _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
                                              _p(aff[3]), _p(pre_bias), st), "rss_bn_act_fwd_raw")
@@ -341,7 +361,8 @@ class BNAct(torch.autograd.Function):
             # SyncBN: raw local sums -> one-shot exchange over NVLink peer memory, finalised by the same one-CTA kernel
             ex = sync_exchange(group, dev, C)
             off, cnt = ex.channel(scratch)
-            check(lib.rss_bn_stats_raw(_p(x), _p(scratch[2:]), rows, C, dt, _p(running_mean), _p(pre_bias), st), "rss_bn_stats_raw")
+            if not raw_ready:
+                check(lib.rss_bn_stats_raw(_p(x), _p(scratch[2:]), rows, C, dt, _p(running_mean), _p(pre_bias), st), "rss_bn_stats_raw")
             check(lib.rss_sync_bn_finalize(_p(ex.bases), off, ex.rank, ex.world, cnt, _p(scratch[2:]), C, rows, _p(g), _p(b),
                                            _p(running_mean), _p(running_var), momentum, eps, _p(aff[0]), _p(aff[1]), _p(aff[2]),
                                            _p(aff[3]), _p(pre_bias), st), "rss_sync_bn_finalize")

@@ -1181,3 +1181,40 @@ def test_training_trajectory_graph_replay_vs_oracle(P, report):
     errs = {"loss_step%d" % i: abs(a - b) / abs(b) for i, (a, b) in enumerate(zip(losses, ref_losses))}
     report["trajectory_fp32_graph"] = dict(errs, losses=losses, ref=ref_losses)
     assert errs["loss_step0"] < 1e-4 and max(errs.values()) < 3e-2, (losses, ref_losses)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 32, 32, 32), (1, 32, 64, 128), (16, 32, 128, 128)])
+def test_ffn_norm2_statistics_from_the_gemm_epilogue(P, report, shape):
+    """MlpDWBN with norm2's batch statistics produced by the dw + dw6 + dw12 GEMM's epilogue (rss_conv_igemm_stats -> raw sums ->
+    rss_bn_act_fwd_raw) against the same module with the separate statistics pass: outputs, input gradient, running statistics and
+    parameter gradients; last shape = the benched layer (16 x 128 x 128 tokens)"""
+    from representationlearning_b200 import conv
+    B, C, H, W = shape
+    torch.manual_seed(11)
+    x0 = torch.randn(B, H * W, C, device=DEV).to(torch.bfloat16)
+    dy = torch.randn(B, H * W, C, device=DEV).to(torch.bfloat16)
+    res = {}
+    for mode in (True, False):
+        torch.manual_seed(5)
+        m = P.MlpDWBN(C, 4 * C, C).to(DEV).train()
+        with torch.no_grad():
+            m.norm2.running_mean.normal_(0, 0.3)
+        conv.ENGINE["igemm_stats"] = mode
+        try:
+            assert conv.conv_sum_stats_ok(torch.empty(B, 4 * C, H, W, device=DEV, dtype=torch.bfloat16), 4 * C) == mode
+            x = x0.clone().requires_grad_(True)
+            y = m(x, H, W)
+            y.backward(dy)
+            conv.join_wgrad()
+            torch.cuda.synchronize()
+        finally:
+            conv.ENGINE["igemm_stats"] = True
+        res[mode] = dict(y=y.detach().float(), dx=x.grad.float(), rm=m.norm2.running_mean.clone(), rv=m.norm2.running_var.clone(),
+                         g2=m.norm2.weight.grad.clone(), w6=m.dw6.weight.grad.clone().float(), scratch=m.norm2._scratch.clone())
+    assert float(res[True]["scratch"].abs().max()) == 0.0                    # the consumer left the layer's scratch zeroed
+    l2 = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-12))
+    errs = {k: l2(res[True][k], res[False][k]) for k in ("y", "dx", "rm", "rv", "g2", "w6")}
+    report["ffn_stats_epilogue_%s" % "x".join(map(str, shape))] = errs
+    # same rounded tensor, same statistics up to the order of the fp32 sums
+    assert errs["rm"] < 1e-5 and errs["rv"] < 1e-4 and errs["y"] < 2e-3 and errs["dx"] < 5e-3 and errs["g2"] < 5e-3 and errs["w6"] < 5e-3, errs
