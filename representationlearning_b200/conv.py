@@ -274,6 +274,35 @@ def _pack(weights, biases, ksizes, dils, Cout, Cin, transpose, dev):
     return packed, bias_sum, nt.value, dy, dx, (ws, bs)
 
 
+def prepack_sum(x_like, convs, want_bwd=True):
+    """Both weight operands of conv_sum's igemm launch (forward pack; transposed pack for the data gradient) produced NOW on a side
+    stream, for a convolution that runs later on the current stream: the two rss_conv_pack_weights launches (~10 us each) leave the
+    critical chain (a transformer block calls this before its attention half).  -> opaque dict for conv_sum(..., prepacked=) or None
+    when the igemm kernel does not cover the geometry.  x_like: a tensor with the conv input's batch / spatial shape and dtype."""
+    Cout, Cin = convs[0][0].shape[0], convs[0][0].shape[1]
+    B, _, H, W = x_like.shape
+    if not (ENGINE["igemm"] and x_like.dtype == torch.bfloat16 and x_like.is_cuda and os.environ.get("RSS_IGEMM_PREPACK", "1") != "0"
+            and bool(_lib.load().rss_conv_igemm_supported(B, H, W, Cin, Cout))):
+        return None
+    dev = x_like.device
+    weights, biases = [c[0] for c in convs], [c[1] for c in convs]
+    ksizes, dils = [c[2] for c in convs], [c[3] for c in convs]
+    cur, side = torch.cuda.current_stream(dev), wgrad_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        fwd = _pack(weights, biases, ksizes, dils, Cout, Cin, False, dev)
+        bwd = _pack(weights, [None] * len(convs), ksizes, dils, Cout, Cin, True, dev) if want_bwd else None
+        ev = torch.cuda.Event()
+        ev.record(side)
+    for pk in (fwd, bwd):
+        if pk is not None:
+            pk[0].record_stream(cur)
+            if pk[1] is not None:
+                pk[1].record_stream(cur)
+    WGRAD["used"].add(dev)
+    return {"fwd": fwd, "bwd": bwd, "event": ev, "ids": tuple(id(w) for w in weights)}
+
+
 class _ConvIgemm(torch.autograd.Function):
     """sum_s conv2d(x, w_s, b_s, stride 1, padding = dil_s*(k_s//2), dilation dil_s) as ONE tcgen05 implicit GEMM.
     Data gradient: same kernel on the transposed pack.  Weight gradient: library kernel per source (for now)."""
@@ -282,13 +311,20 @@ class _ConvIgemm(torch.autograd.Function):
     def forward(ctx, x, cfg, *wb):
         ksizes, dils, bias_grad = cfg[:3]
         stats = cfg[3] if len(cfg) > 3 else None         # (scratch, running_mean): BatchNorm raw sums from the GEMM's epilogue
+        pre = cfg[4] if len(cfg) > 4 else None           # prepack_sum(): operands packed earlier on a side stream
         n = len(ksizes)
         weights, biases = wb[:n], wb[n:]
         lib = _lib.load()
         x = ops.nhwc(x)
         B, Cin, H, W = x.shape
         Cout = weights[0].shape[0]
-        packed, bias_sum, nt, dy, dx, keep = _pack(weights, biases, ksizes, dils, Cout, Cin, False, x.device)
+        if pre is not None and pre["ids"] == tuple(id(w) for w in weights):
+            torch.cuda.current_stream(x.device).wait_event(pre["event"])
+            packed, bias_sum, nt, dy, dx, keep = pre["fwd"]
+            ctx.pre_bwd = pre["bwd"]
+        else:
+            packed, bias_sum, nt, dy, dx, keep = _pack(weights, biases, ksizes, dils, Cout, Cin, False, x.device)
+            ctx.pre_bwd = None
         y = torch.empty((B, Cout, H, W), device=x.device, dtype=x.dtype, memory_format=CL)
         with ops.timed("rss_conv_igemm"):
             if stats is not None:
@@ -327,7 +363,8 @@ class _ConvIgemm(torch.autograd.Function):
             gw.append(dw); gb.append(db)
         dx = None
         if ctx.needs_input_grad[0]:
-            packed, _, nt, tdy, tdx, keep = _pack(weights, [None] * n, ksizes, dils, Cout, Cin, True, x.device)
+            packed, _, nt, tdy, tdx, keep = ctx.pre_bwd if ctx.pre_bwd is not None else _pack(weights, [None] * n, ksizes, dils, Cout, Cin,
+                                                                                            True, x.device)
             dx = torch.empty_like(x, memory_format=CL)
             with ops.timed("rss_conv_igemm"):
                 ops.check(lib.rss_conv_igemm(dy_.data_ptr(), packed.data_ptr(), None, dx.data_ptr(), B, H, W, Cout, Cin, nt, tdy, tdx,
@@ -498,7 +535,7 @@ def conv_sum_stats_ok(x, Cout):
     return ENGINE["igemm_stats"] and Cout <= 128 and _igemm_ok(x, Cout)
 
 
-def conv_sum(x, convs, bias_grad=True, stats=None):
+def conv_sum(x, convs, bias_grad=True, stats=None, prepacked=None):
     """sum of parallel stride-1 'same' convolutions of the same input (the FFN's dw + dw6 + dw12): one igemm launch when the
     geometry is supported, else the library convs added up.  convs: list of (weight, bias, ksize, dilation).
     stats = (scratch, running_mean) of the BatchNorm that consumes the sum: its raw sums are produced by the GEMM's epilogue
@@ -507,7 +544,9 @@ def conv_sum(x, convs, bias_grad=True, stats=None):
     if stats is not None and not conv_sum_stats_ok(x, Cout):
         raise _lib.RssError("conv_sum: statistics epilogue requested for a geometry the igemm kernel does not cover")
     if _igemm_ok(x, Cout):
-        cfg = (tuple(c[2] for c in convs), tuple(c[3] for c in convs), bias_grad) + ((stats,) if stats is not None else ())
+        cfg = (tuple(c[2] for c in convs), tuple(c[3] for c in convs), bias_grad)
+        if stats is not None or prepacked is not None:
+            cfg = cfg + (stats, prepacked)
         return _ConvIgemm.apply(x, cfg, *[c[0] for c in convs], *[c[1] for c in convs])
     out = None
     for w, b, k, d in convs:

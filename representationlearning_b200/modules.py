@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .conv import conv2d, conv_sum, conv_sum_stats_ok
+from .conv import conv2d, conv_sum, conv_sum_stats_ok, prepack_sum
 
 BN_MOMENTUM = 0.1        # _hrnet_rssformer.py:27
 CL = torch.channels_last
@@ -169,18 +169,28 @@ class MlpDWBN(nn.Module):
         self.fc2 = nn.Conv2d(hidden_features, out_features, kernel_size=1)
         self.norm3 = FusedBNAct(out_features, _lib.ACT_GELU, sync=True)
 
-    def forward_nchw(self, x):
+    def _dw_convs(self):
+        return [(self.dw.weight, self.dw.bias, 1, 1), (self.dw6.weight, self.dw6.bias, 3, 6), (self.dw12.weight, self.dw12.bias, 3, 12)]
+
+    def prepack(self, x):
+        """weight operands of the dw + dw6 + dw12 GEMM (and of its data gradient) packed on a side stream; x: the block input
+        (B,C,H,W) -- only its batch / spatial shape, dtype and device matter.  None when the igemm kernel will not run."""
+        B, _, H, W = x.shape
+        like = torch.empty((B, 0, H, W), device=x.device, dtype=x.dtype)
+        return prepack_sum(like, self._dw_convs(), want_bwd=self.training and torch.is_grad_enabled())
+
+    def forward_nchw(self, x, prepacked=None):
         bg = not self.training       # every bias here feeds a training-mode BN: its gradient is identically zero
         x = self.norm1.after_conv(x, self.fc1.weight, self.fc1.bias)
-        convs = [(self.dw.weight, self.dw.bias, 1, 1), (self.dw6.weight, self.dw6.bias, 3, 6), (self.dw12.weight, self.dw12.bias, 3, 12)]
+        convs = self._dw_convs()
         n2 = self.norm2
         if conv_sum_stats_ok(x, n2.num_features) and ops.bn_accepts_raw_sums(x, n2.training, True if n2.sync else None, n2._scratch,
                                                                              n2.num_features):
             # norm2's statistics come out of the GEMM's epilogue: the 67 MB sum is written once and read once (by the apply pass)
-            c = conv_sum(x, convs, bias_grad=bg, stats=(n2._scratch, n2.running_mean))
+            c = conv_sum(x, convs, bias_grad=bg, stats=(n2._scratch, n2.running_mean), prepacked=prepacked)
             x = n2(c, aff=ops.RAW_SUMS)
         else:
-            x = n2(conv_sum(x, convs, bias_grad=bg))
+            x = n2(conv_sum(x, convs, bias_grad=bg, prepacked=prepacked))
         return self.norm3.after_conv(x, self.fc2.weight, self.fc2.bias)
 
     def forward(self, x, H, W):
@@ -212,12 +222,13 @@ class GeneralTransformerBlock(nn.Module):
     def forward(self, x, y, mask=None, relu=False):
         """relu=True additionally applies the ReLU that HighResolutionModule puts on the block output
         (_hrnet_rssformer.py:435), fused with the residual add."""
+        pre = self.mlp.prepack(x) if x.is_cuda else None          # the FFN GEMM's weight packs overlap the attention half
         # attention half: LN1(x), LN1(y), gate, window attention, + x  — one fused region
         t = ops.WindowAttention.apply(x, y, self.norm1.eps, True, self.norm1.weight, self.norm1.bias,
                                       *self.attn.gate_params(), *self.attn.attn.proj_params())
         # FFN half: LN2 -> MlpDWBN -> + t (-> ReLU)
         u = ops.LayerNormNHWC.apply(t, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        return ops.fuse_sum([t, self.mlp.forward_nchw(u)], [0, 0], relu)
+        return ops.fuse_sum([t, self.mlp.forward_nchw(u, prepacked=pre)], [0, 0], relu)
 
     def extra_repr(self):
         return "num_heads={}, window_size={}, mlp_ratio={}".format(self.num_heads, self.window_size, self.mlp_ratio)
