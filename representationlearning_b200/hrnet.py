@@ -36,6 +36,8 @@ _SIDE = {}
 # Measured on the B=16 step: 479 img/s with priorities vs 490 without -- the weight gradients pile up behind the chain and the
 # step ends with a serial tail -- so it is OFF by default.
 CHAIN_PRIORITY = -1 if os.environ.get("RSS_PRIORITY", "0") != "0" else 0
+FUSE_ORDER_DESC = os.environ.get("RSS_FUSE_ORDER", "1") != "0"      # see HighResolutionModule.flow
+FUSE_CHAIN_STREAMS = os.environ.get("RSS_FUSE_CHAIN_STREAMS", "0") != "0"
 
 
 def _side_streams(dev, n):
@@ -367,10 +369,27 @@ class HighResolutionModule(nn.Module):
         x_fuse = [None] * rows
         for i in range(rows - 1, 0, -1):
             with torch.cuda.stream(S[i]):
-                terms, ks = [], []
-                for j in range(nb):
-                    t, k = (out[j], 0) if i == j else self._fuse(i, j, _bring(out[j], S[i], cur))
-                    terms.append(t); ks.append(k)
+                # Issued finest source LAST: autograd replays a stream's nodes in reverse, so the stride-2 chain coming from branch 0
+                # (f_i0, the longest: i convolutions) runs FIRST in the backward pass.  Its result is the gradient stream 0's chain
+                # waits for; issued first (j ascending) it sat behind the chains of the other sources on this stream -- on the
+                # coarsest stream 6 conv+BN pairs instead of 3, a 214 us stall of the critical chain per stage-4 module
+                # (profiles/timeline_r2_final_526_summary.txt).  The sum keeps its term order.  RSS_FUSE_ORDER=0: ascending.
+                tk = [None] * nb
+                order = range(nb - 1, -1, -1) if FUSE_ORDER_DESC else range(nb)
+                for j in order:
+                    if i == j:
+                        tk[j] = (out[j], 0)
+                    elif FUSE_CHAIN_STREAMS and j < i:
+                        # RSS_FUSE_CHAIN_STREAMS=1: every stride-2 chain f_ij is its own branch of the graph (own stream, joined into
+                        # row i's stream by the sum), so that in the backward pass f_i0 does not queue behind its siblings
+                        sc = _side_streams(dev, nb - 1 + 8)[nb - 1 + (i * (i - 1)) // 2 + j]
+                        with torch.cuda.stream(sc):
+                            t, k = self._fuse(i, j, _bring(out[j], sc, cur))
+                            _mark(t, sc)
+                        tk[j] = (_bring(t, S[i], cur), k)
+                    else:
+                        tk[j] = self._fuse(i, j, _bring(out[j], S[i], cur))
+                terms, ks = [t for t, _ in tk], [k for _, k in tk]
                 x_fuse[i] = _mark(ops.fuse_sum(terms, ks, relu=True), S[i])      # (:433,435)
         low = ops.fuse_sum([_bring(t, cur, cur) for t, _ in terms0], [k for _, k in terms0], relu=False)
         x_fuse[0] = _mark(self.transformer(low, out[0], relu=True), cur)         # (:430-431,435)
