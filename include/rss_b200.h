@@ -194,12 +194,13 @@ int rss_conv_igemm(const void* x, const void* w_packed, const float* bias /*may 
                    int Cin, int Cout, int n_taps, const int* taps_dy, const int* taps_dx, cudaStream_t stream);
 /* the same GEMM with a BatchNorm-statistics epilogue (ffn_block.py:250-258: dw + dw6 + dw12 -> norm2): besides y, adds per output
  * channel c sum (y - K_c) into stat_accum[c] and sum (y - K_c)^2 into stat_accum[Cout + c] over the bf16-rounded outputs (K =
- * stat_shift[Cout], NULL = 0; the layer's running mean keeps E[d^2] - E[d]^2 well conditioned) -- the "raw sums" contract of
+ * stat_shift - stat_shift_sub, each [Cout] or NULL = 0: the layer's running mean, minus the bias of the producing convolution when
+ * that bias is left out of y (fc1 -> norm1, fc2 -> norm3: ffn_block.py:246-263); keeps E[d^2] - E[d]^2 well conditioned) -- the "raw sums" contract of
  * rss_bn_stats_raw, consumed by rss_bn_act_fwd_raw / rss_sync_bn_finalize, so no statistics pass reads the tensor again.
  * stat_accum: the layer's persistent zeroed scratch (the consumer clears it); Cout <= 128. */
 int rss_conv_igemm_stats(const void* x, const void* w_packed, const float* bias /*may be NULL*/, void* y, int B, int H, int W,
                          int Cin, int Cout, int n_taps, const int* taps_dy, const int* taps_dx, float* stat_accum,
-                         const float* stat_shift /*may be NULL*/, cudaStream_t stream);
+                         const float* stat_shift /*may be NULL*/, const float* stat_shift_sub /*may be NULL*/, cudaStream_t stream);
 
 /* ---- fused tcgen05 convolution of the HRNet family (BasicBlock/Bottleneck 3x3 and 1x1 stride-1 convs and their data gradients:
  *      _hrnet_rssformer.py:209-287):  y = E(conv(T(x)) + add)

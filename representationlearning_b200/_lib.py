@@ -78,7 +78,7 @@ SIGNATURES = {
     "rss_conv_pack_weights": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int,
                                       P, P, POINTER(c_int), POINTER(c_int), POINTER(c_int), P]),
     "rss_conv_igemm": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P]),
-    "rss_conv_igemm_stats": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P, P, P]),
+    "rss_conv_igemm_stats": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P, P, P, P]),
     "rss_conv_cf_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "rss_conv_cf": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int, c_int,
                             P, P, c_int, POINTER(ConvCfEpilogue), P]),

@@ -331,7 +331,7 @@ class _ConvIgemm(torch.autograd.Function):
                 scratch, shift = stats
                 ops.check(lib.rss_conv_igemm_stats(x.data_ptr(), packed.data_ptr(), None if bias_sum is None else bias_sum.data_ptr(),
                                                    y.data_ptr(), B, H, W, Cin, Cout, nt, dy, dx, scratch[2:].data_ptr(), ops._p(shift),
-                                                   ops._st()), "rss_conv_igemm_stats")
+                                                   None, ops._st()), "rss_conv_igemm_stats")
             else:
                 ops.check(lib.rss_conv_igemm(x.data_ptr(), packed.data_ptr(), None if bias_sum is None else bias_sum.data_ptr(),
                                              y.data_ptr(), B, H, W, Cin, Cout, nt, dy, dx, ops._st()), "rss_conv_igemm")
@@ -533,6 +533,12 @@ ENGINE["igemm_stats"] = os.environ.get("RSS_IGEMM_STATS", "1") != "0"
 def conv_sum_stats_ok(x, Cout):
     """True when conv_sum(x, ..., stats=...) would run the igemm kernel with the statistics epilogue"""
     return ENGINE["igemm_stats"] and Cout <= 128 and _igemm_ok(x, Cout)
+
+
+# (fc1 -> norm1 and fc2 -> norm3 through the same kernel -- a (Cout,Cin,1,1) bf16 weight IS its [tap][Cout][Cin] operand -- with the
+#  statistics epilogue were measured at 521.2 vs 525.2 img/s with cuBLAS + the separate statistics pass: K = 32 / N = 32 GEMMs leave the
+#  128-row tcgen05 tile store-bound, 40-48 us vs 18-22 us for nvjet; not kept.  rss_conv_igemm_stats keeps the stat_shift_sub operand
+#  that path needed: K = running_mean - bias for a convolution whose bias is left to the BatchNorm.)
 
 
 def conv_sum(x, convs, bias_grad=True, stats=None, prepacked=None):

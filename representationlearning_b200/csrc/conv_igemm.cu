@@ -72,13 +72,13 @@ __device__ __forceinline__ float warp_reduce16(float (&a)[16], int lane) {
 
 // ---- the kernel -------------------------------------------------------------------------------------
 // stat_accum != NULL: BatchNorm-statistics epilogue.  The epilogue warps also add, per output channel c, sum (y - K_c) and
-// sum (y - K_c)^2 of the bf16-ROUNDED outputs into stat_accum[c] / stat_accum[Cout + c] (K = stat_shift, or 0): the "raw sums" of
+// sum (y - K_c)^2 of the bf16-ROUNDED outputs into stat_accum[c] / stat_accum[Cout + c] (K = stat_shift - stat_shift_sub, NULL = 0): the "raw sums" of
 // csrc/bn.cu's BnFin protocol, so the BatchNorm that follows needs no statistics pass over the tensor (FFN norm2 behind the
 // dw + dw6 + dw12 GEMM: a 67 MB read per block and step).  Needs n_tiles == 1 and block_n <= 128.
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, ConvGeom g, ConvTaps taps,
-                  float* __restrict__ stat_accum, const float* __restrict__ stat_shift) {
+                  float* __restrict__ stat_accum, const float* __restrict__ stat_shift, const float* __restrict__ stat_shift_sub) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t b_tile_bytes = (uint32_t)g.block_n * kBlockK * 2;
     const uint32_t a_bytes = (uint32_t)g.mm * kATileBytes;                 // mm sub-tiles of 128 rows, one TMA box (BH*mm image rows)
@@ -207,10 +207,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 for (int ch = 0; ch < 8; ++ch) {
                     const int c0 = ch * 16;
                     if ((ch & 1) == half && c0 < g.block_n) {
-                        float bs[16], s16[16], q16[16];
+                        float bs[16], kk[16], s16[16], q16[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             bs[i] = bias ? bias[c0 + i] : 0.f;
+                            kk[i] = (stat_shift ? stat_shift[c0 + i] : 0.f) - (stat_shift_sub ? stat_shift_sub[c0 + i] : 0.f);
                             s16[i] = 0.f; q16[i] = 0.f;
                         }
                         for (int m = 0; m < g.mm; ++m) {
@@ -229,7 +230,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                 store8(dst + c0 + 8, v + 8);
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) {
-                                    const float d = __bfloat162float(__float2bfloat16_rn(v[i])) - (stat_shift ? stat_shift[c0 + i] : 0.f);
+                                    const float d = __bfloat162float(__float2bfloat16_rn(v[i])) - kk[i];
                                     s16[i] += d;
                                     q16[i] += d * d;
                                 }
@@ -427,7 +428,7 @@ extern "C" int rss_conv_pack_weights(const float* const* weights, const float* c
 // stat_accum / stat_shift: BatchNorm-statistics epilogue (see conv_igemm_kernel); Cout <= 128 only.
 extern "C" int rss_conv_igemm_stats(const void* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int Cin, int Cout,
                                     int n_taps, const int* taps_dy, const int* taps_dx, float* stat_accum, const float* stat_shift,
-                                    cudaStream_t st) {
+                                    const float* stat_shift_sub, cudaStream_t st) {
     if (!rss_conv_igemm_supported(B, H, W, Cin, Cout) || n_taps < 1 || n_taps > kMaxTaps) return RSS_ERR_SHAPE;
     if (stat_accum && Cout > 128) return RSS_ERR_SHAPE;
     ConvGeom g;
@@ -466,11 +467,11 @@ extern "C" int rss_conv_igemm_stats(const void* x, const void* w_packed, const f
     int grid = num_sms();
     const int total_tiles = g.m_tiles * g.n_tiles;
     if (grid > total_tiles) grid = total_tiles;
-    conv_igemm_kernel<<<grid, kConvThreads, smem, st>>>(ma, mb, bias, (__nv_bfloat16*)y, g, taps, stat_accum, stat_shift);
+    conv_igemm_kernel<<<grid, kConvThreads, smem, st>>>(ma, mb, bias, (__nv_bfloat16*)y, g, taps, stat_accum, stat_shift, stat_shift_sub);
     return check_launch();
 }
 
 extern "C" int rss_conv_igemm(const void* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int Cin, int Cout,
                               int n_taps, const int* taps_dy, const int* taps_dx, cudaStream_t st) {
-    return rss_conv_igemm_stats(x, w_packed, bias, y, B, H, W, Cin, Cout, n_taps, taps_dy, taps_dx, nullptr, nullptr, st);
+    return rss_conv_igemm_stats(x, w_packed, bias, y, B, H, W, Cin, Cout, n_taps, taps_dy, taps_dx, nullptr, nullptr, nullptr, st);
 }
