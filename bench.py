@@ -185,6 +185,7 @@ FAMILIES = (
     ("conv_igemm_kernel", "tcgen05 implicit GEMM (conv_igemm_kernel: FFN 19-tap conv)"),
     ("win_attn_fwd", "window attention forward"), ("win_attn_bwd", "window attention backward"), ("gate_", "saliency gate"),
     ("ln_", "layernorm"), ("conv_wgrad", "own weight-gradient kernels"), ("fuse_sum", "multi-resolution fuse"),
+    ("stem_conv", "stem conv (stem_conv_{fwd,wgrad}_kernel: 3->64 stride-2 conv from the planar image, cast + layout + BN sums fused)"),
     ("neck_gather", "neck gather"), ("head_", "head"), ("seg_loss", "loss"), ("sgd_step", "optimiser"), ("sumsq", "optimiser"),
     ("shadow_", "optimiser"), ("cutlass", "library conv (cuDNN cutlass3x / xmma)"), ("xmma", "library conv (cuDNN cutlass3x / xmma)"),
     ("cudnn", "library conv (cuDNN cutlass3x / xmma)"), ("nvjet", "library GEMM (cuBLAS nvjet: 1x1 convs)"),
@@ -462,7 +463,7 @@ def main():
         for f, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             ent = {"ms": t / 1e3, "share": t / tot, "launches": int(round(c))}
             key = "bn" if f.startswith("batchnorm") else ("cf" if f.startswith("fused tcgen05") else ("attn_fwd" if f == "window attention forward"
-                  else ("attn_bwd" if f == "window attention backward" else None)))
+                  else ("attn_bwd" if f == "window attention backward" else ("stem" if f.startswith("stem conv") else None))))
             if key and acct.get(key):
                 gbs = acct[key] / (t / 1e6) / 1e9
                 ent.update({"bound": "hbm", "algorithmic_bytes": acct[key], "achieved_gbs": gbs, "peak_gbs": pk["hbm"], "frac": gbs / pk["hbm"]})

@@ -262,6 +262,16 @@ int rss_neck_gather_fwd(const void* f0, const void* f1, const void* f2, const vo
 int rss_neck_gather_bwd(const void* dcat, void* d0, void* d1, void* d2, void* d3,
                         int B, const int* C, const int* h, const int* w, int dtype, cudaStream_t stream);
 
+/* ---- HRNet stem, first convolution: _hrnet_rssformer.py:467-470 Conv2d(3,64,3,stride 2,padding 1,bias=False) read straight
+ *      from the (B,3,H,W) planar fp32 (or bf16) image batch the reference model receives (csrc/stem.cu): the cast, the
+ *      NCHW->NHWC change, the convolution and -- optionally -- the BatchNorm raw sums of bn1 in one launch.
+ *      y: (B,Ho,Wo,64) bf16 NHWC, Ho=(H-1)/2+1, Wo=(W-1)/2+1.  stat_accum (NULL or [2][64] fp32, zero or holding earlier partial
+ *      sums) += sum (y-K), sum (y-K)^2 over the bf16-rounded outputs, K = stat_shift[c] (NULL: 0): the operand of
+ *      rss_bn_act_fwd_raw.  No data gradient (the image needs none); dw_acc (64,3,3,3) fp32 += weight gradient. ---- */
+int rss_stem_conv_fwd(const void* x, const float* w /*(64,3,3,3)*/, void* y, int B, int H, int W, int in_dtype,
+                      float* stat_accum, const float* stat_shift, cudaStream_t stream);
+int rss_stem_conv_wgrad(const void* x, const void* dy, float* dw_acc, int B, int H, int W, int in_dtype, cudaStream_t stream);
+
 /* ---- head: hrnet_aux.py:78-81 (Conv2d(480,7,1)); logits are kept at LOW resolution, (pixels, 8) fp32
  *      (class 7 is padding); the x4 UpsamplingBilinear2d is fused into rss_seg_loss_fwd / rss_head_probs ---- */
 int rss_head_fwd(const void* x, const float* w /*(7,C)*/, const float* bias, float* logits_lr, int64_t pixels, int C,

@@ -88,6 +88,8 @@ SIGNATURES = {
     "rss_conv_wgrad_tc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P]),
     "rss_neck_gather_fwd": (c_int, [P, P, P, P, P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, P]),
     "rss_neck_gather_bwd": (c_int, [P, P, P, P, P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, P]),
+    "rss_stem_conv_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "rss_stem_conv_wgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "rss_head_fwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, P]),
     "rss_head_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, P]),
     "rss_head_probs": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),

@@ -38,10 +38,28 @@ _SIDE = {}
 CHAIN_PRIORITY = -1 if os.environ.get("RSS_PRIORITY", "0") != "0" else 0
 FUSE_ORDER_DESC = os.environ.get("RSS_FUSE_ORDER", "1") != "0"      # see HighResolutionModule.flow
 FUSE_CHAIN_STREAMS = os.environ.get("RSS_FUSE_CHAIN_STREAMS", "0") != "0"
+# RSS_FUSE_ROW_STREAMS (default on): fuse row i >= 1 (its stride-2 / 1x1 chains and its sum) runs on a stream of its own, R[i],
+# instead of on branch i's stream S[i].  Forward it is the same DAG.  Backward it removes a FALSE dependency that autograd's stream
+# contract creates: gradients for a tensor with several consumers are accumulated on the stream of the tensor's PRODUCER node, at
+# the moment the engine hands them over (issue order).  out[i] (branch i's output, produced on S[i]) is consumed by every row, so
+# the accumulation "d out[3] += f_13^T(..)" -- and with it a wait for row 1's whole backward chain -- was queued on S[3] BEFORE the
+# engine issued row 3's own backward nodes on that same stream: the rows' backward chains ran one after the other (row 1, row 2,
+# row 3) although they are independent, and stream 0, which needs f_30^T from the LAST of them, idled ~450 us per stage-4 module
+# (profiles/timeline_r2_final_526_summary.txt: "879:287 add", "873:307 add").  With R[i] only true dependencies are queued in front
+# of a row's backward.
+FUSE_ROW_STREAMS = os.environ.get("RSS_FUSE_ROW_STREAMS", "1") != "0"
+_ROW = {}
 
 
 def _side_streams(dev, n):
     lst = _SIDE.setdefault(dev, [])
+    while len(lst) < n:
+        lst.append(torch.cuda.Stream(dev, priority=CHAIN_PRIORITY))
+    return lst
+
+
+def _row_streams(dev, n):
+    lst = _ROW.setdefault(dev, [])
     while len(lst) < n:
         lst.append(torch.cuda.Stream(dev, priority=CHAIN_PRIORITY))
     return lst
@@ -367,8 +385,9 @@ class HighResolutionModule(nn.Module):
                 terms0.append((_mark(t, S[j]), k))
         rows = len(self.fuse_layers)
         x_fuse = [None] * rows
+        R = ([cur] + _row_streams(dev, rows - 1)[:rows - 1]) if FUSE_ROW_STREAMS else S
         for i in range(rows - 1, 0, -1):
-            with torch.cuda.stream(S[i]):
+            with torch.cuda.stream(R[i]):
                 # Issued finest source LAST: autograd replays a stream's nodes in reverse, so the stride-2 chain coming from branch 0
                 # (f_i0, the longest: i convolutions) runs FIRST in the backward pass.  Its result is the gradient stream 0's chain
                 # waits for; issued first (j ascending) it sat behind the chains of the other sources on this stream -- on the
@@ -378,7 +397,7 @@ class HighResolutionModule(nn.Module):
                 order = range(nb - 1, -1, -1) if FUSE_ORDER_DESC else range(nb)
                 for j in order:
                     if i == j:
-                        tk[j] = (out[j], 0)
+                        tk[j] = (_bring(out[j], R[i], cur), 0)
                     elif FUSE_CHAIN_STREAMS and j < i:
                         # RSS_FUSE_CHAIN_STREAMS=1: every stride-2 chain f_ij is its own branch of the graph (own stream, joined into
                         # row i's stream by the sum), so that in the backward pass f_i0 does not queue behind its siblings
@@ -386,11 +405,11 @@ class HighResolutionModule(nn.Module):
                         with torch.cuda.stream(sc):
                             t, k = self._fuse(i, j, _bring(out[j], sc, cur))
                             _mark(t, sc)
-                        tk[j] = (_bring(t, S[i], cur), k)
+                        tk[j] = (_bring(t, R[i], cur), k)
                     else:
-                        tk[j] = self._fuse(i, j, _bring(out[j], S[i], cur))
+                        tk[j] = self._fuse(i, j, _bring(out[j], R[i], cur))
                 terms, ks = [t for t, _ in tk], [k for _, k in tk]
-                x_fuse[i] = _mark(ops.fuse_sum(terms, ks, relu=True), S[i])      # (:433,435)
+                x_fuse[i] = _mark(ops.fuse_sum(terms, ks, relu=True), R[i])      # (:433,435)
         low = ops.fuse_sum([_bring(t, cur, cur) for t, _ in terms0], [k for _, k in terms0], relu=False)
         x_fuse[0] = _mark(self.transformer(low, out[0], relu=True), cur)         # (:430-431,435)
         return x_fuse
@@ -528,8 +547,25 @@ class HighResolutionNet(nn.Module):
                 x_list.append(_mark(self._transition(transitions[i], _bring(src, S[i], cur)), S[i]))
         return x_list
 
+    stem_dtype = None      # set by model.HRNetFusion: activation dtype of the model when forward() is handed the raw image batch
+
+    def _stem1(self, x):
+        """conv1 + bn1 + ReLU (:467-470, 531-533).  On a bf16 model the planar image batch, exactly as the reference model receives
+        it, goes through csrc/stem.cu: cast, NCHW -> NHWC, the 3 -> 64 stride-2 convolution and bn1's raw sums in ONE launch (the
+        library path needs a cast, a permute, a 3 -> 8 channel padding kernel and a legacy implicit GEMM: 224 us vs the 184 MB the
+        layer has to move).  Anything else (fp32 strict-parity model, channels-last input, RSS_STEM=0) takes the library conv."""
+        dt = self.stem_dtype
+        if dt is torch.bfloat16 and ops.stem_conv_ok(x, self.conv1.weight):
+            bn = self.bn1
+            raw = ops.STEM["stats"] and ops.bn_accepts_raw_sums(x, bn.training, True if bn.sync else None, bn._scratch, bn.num_features)
+            y = ops.StemConv.apply(x, self.conv1.weight, (bn._scratch, bn.running_mean) if raw else None)
+            return bn(y, aff=ops.RAW_SUMS if raw else None)
+        if dt is not None and x.dtype != dt:
+            x = x.to(dt)
+        return _run(self.conv1, self.bn1, ops.nhwc(x))
+
     def forward(self, x):
-        x = _run(self.conv1, self.bn1, x)
+        x = self._stem1(x)
         x = _run(self.conv2, self.bn2, x)
         x = self.layer1(x)
         x_list = self._next_inputs(self.transition1, [x], self.stage2_cfg["num_branches"])

@@ -145,7 +145,9 @@ class HRNetFusion(ERModule):
         self.compute_dtype = torch.bfloat16          # activation dtype inside the model (fp32 for strict-parity runs)
 
     def forward(self, x, y=None):
-        x = ops.nhwc(x.to(self.compute_dtype))
+        # the image batch goes to the backbone as it came in ((B,3,H,W), usually planar fp32): the stem casts it -- inside its first
+        # convolution kernel when that applies (hrnet.HighResolutionNet._stem1)
+        self.backbone.hrnet.stem_dtype = self.compute_dtype
         feats = self.backbone(x)
         fused, f0 = self.neck(feats)
         aux = ops.headaux(f0, self.headaux[0].weight, self.headaux[0].bias)

@@ -570,6 +570,61 @@ class NeckGather(torch.autograd.Function):
         return tuple(ds)
 
 
+# HRNet stem conv1 from the planar image batch (csrc/stem.cu).  RSS_STEM=0: library path (cast + permute + padded legacy conv);
+# RSS_STEM_STATS=0: bn1's statistics from the separate pass instead of the conv epilogue.
+STEM = {"on": os.environ.get("RSS_STEM", "1") != "0", "stats": os.environ.get("RSS_STEM_STATS", "1") != "0"}
+
+
+def stem_conv_ok(x, weight):
+    """True when StemConv covers this call: planar (B,3,H,W) fp32/bf16 CUDA input that needs no gradient, (64,3,3,3) weight."""
+    return (STEM["on"] and x.is_cuda and x.dim() == 4 and x.shape[1] == 3 and x.dtype in (torch.float32, torch.bfloat16)
+            and x.is_contiguous() and not x.requires_grad and tuple(weight.shape) == (64, 3, 3, 3))
+
+
+class StemConv(torch.autograd.Function):
+    """_hrnet_rssformer.py:467 conv1 = Conv2d(3,64,3,stride 2,padding 1,bias=False) on the image batch as the reference model
+    receives it ((B,3,H,W) planar, fp32 or bf16) -> (B,64,Ho,Wo) bf16 channels_last.  stats = (scratch, running_mean) of the
+    BatchNorm that follows: its raw sums come out of the same launch (call the BatchNorm with aff=RAW_SUMS)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stats):
+        _lib.require_device()
+        lib = _lib.load()
+        if not stem_conv_ok(x, weight):
+            raise _lib.RssError("StemConv: planar (B,3,H,W) fp32/bf16 input without gradient and a (64,3,3,3) weight expected")
+        B, _, H, W = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((B, 64, Ho, Wo), device=x.device, dtype=torch.bfloat16, memory_format=CL)
+        acc = shift = None
+        if stats is not None:
+            scratch, shift = stats
+            if scratch.numel() < 2 + 2 * 64:
+                raise _lib.RssError("StemConv: BatchNorm scratch too small for the statistics epilogue")
+            acc = scratch[2:]
+        account("stem", x, y)
+        check(lib.rss_stem_conv_fwd(_p(x), _p(_f32(weight)), _p(y), B, H, W, _dt(x), _p(acc), _p(shift), _st()), "rss_stem_conv_fwd")
+        ctx.save_for_backward(x)
+        ctx.refs = (weight,)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, = ctx.saved_tensors
+        weight = ctx.refs[0]
+        if not ctx.needs_input_grad[1]:
+            return None, None, None
+        dy = nhwc(dy)
+        if dy.dtype != torch.bfloat16:
+            dy = dy.to(torch.bfloat16)
+        B, _, H, W = x.shape
+        sink = grad_sink(weight)
+        dw = sink if sink is not None else torch.zeros(64, 3, 3, 3, device=x.device, dtype=torch.float32)
+        account("stem", x, dy)
+        check(lib.rss_stem_conv_wgrad(_p(x), _p(dy), _p(dw), B, H, W, _dt(x), _st()), "rss_stem_conv_wgrad")
+        return None, (None if sink is not None else dw.to(weight.dtype)), None
+
+
 class HeadConv(torch.autograd.Function):
     """(B,C,h,w) channels_last -> low-resolution logits (B,h,w,8) fp32 (class 7 = padding)."""
 
