@@ -316,7 +316,9 @@ int rss_confusion_matrix(const uint8_t* pred, const int64_t* truth, unsigned lon
 /* dst_e[i] += (float)src_e[i] for a list of tensors in ONE launch (fp32 accumulation of the library's bf16 weight gradients into the
  * flat gradient buffer).  table[e] = {src device pointer (bf16), dst device pointer (f32), numel, Cin, kk}: kk = 0 same element
  * order, kk = kh*kw > 0: src in the library's channels-last (Cout,kh,kw,Cin) order, dst in parameter order (Cout,Cin,kh,kw).
- * chunk_start[e] = index of the first 4096-element chunk of entry e, chunk_start[n_entries] = total_chunks.  Device memory. */
+ * chunk_start[e] = index of the first chunk of entry e, chunk_start[n_entries] = total_chunks (device memory); entry e has
+ * rss_accum_chunks(numel, Cin, kk) chunks: 4096 elements each, or whole (Cin*kk)-element rows when kk > 0 and a row fits. */
+int64_t rss_accum_chunks(int64_t numel, int64_t cin, int64_t kk);
 int rss_accum_bf16_list(const int64_t* table, const int64_t* chunk_start, int n_entries, int64_t total_chunks, cudaStream_t stream);
 /* transposed bf16 copies for the data-gradient operand of rss_conv_cf: weight e = fp32 (Cout,Cin,kh,kw) at params + table[e][0]
  * -> bf16 [Cin][kh*kw][Cout] at shadow_t + table[e][1]; table[e] = {src offset, dst offset, Cout, Cin, kh*kw} (int64). */

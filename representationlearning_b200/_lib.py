@@ -102,6 +102,7 @@ SIGNATURES = {
     "rss_shadow_cl_refresh": (c_int, [P, P, P, P, c_int, c_int, P]),
     "rss_shadow_t_refresh": (c_int, [P, P, P, c_int, P]),
     "rss_accum_bf16_list": (c_int, [P, P, c_int, c_int64, P]),
+    "rss_accum_chunks": (c_int64, [c_int64, c_int64, c_int64]),
     "rss_bilinear_resize": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, P]),
     "rss_confusion_matrix": (c_int, [P, P, P, c_int64, c_int, c_int, P]),
     "rss_bilateral_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

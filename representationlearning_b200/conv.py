@@ -62,7 +62,7 @@ def _flush_pending():
         rows, starts, c = [], [0], 0
         for src, dst, n, cin, kk in key:
             rows.append([src, dst, n, cin, kk])
-            c += (n + 4095) // 4096
+            c += int(_lib.load().rss_accum_chunks(n, cin, kk))
             starts.append(c)
         host = (torch.tensor(rows, dtype=torch.int64).pin_memory(), torch.tensor(starts, dtype=torch.int64).pin_memory())
         ent = PENDING["tables"][key] = (host, torch.empty_like(host[0], device=dev), torch.empty_like(host[1], device=dev), c)

@@ -231,11 +231,18 @@ __global__ void sgd_step_kernel(float* __restrict__ p, float* __restrict__ g, fl
 // chain).  One "row" = one output channel of one weight: Cin*kk contiguous floats in, Cin*kk contiguous bf16 out, permuted
 // through shared memory so both sides are coalesced.  table[e] = {src offset (floats), dst offset (elements), Cin, kk};
 // row_start[e] = first global row of entry e (row_start[n_entries] = total rows).
-__global__ void shadow_cl_kernel(const float* __restrict__ p, __nv_bfloat16* __restrict__ out, const int64_t* __restrict__ table,
-                                 const int64_t* __restrict__ row_start, int n_entries) {
-    extern __shared__ float row_sm[];
+// One WARP per row (round 2: one block per row with two block barriers -- 256 threads for rows of 288 floats -- took 119 us for
+// 108 MB in + 54 MB out): 16-byte loads into the warp's slab, 16-byte stores of 8 consecutive input channels of one tap; the lanes
+// walk the output vectors tap-fastest so that the stride-kk shared-memory reads of a warp fall into distinct banks.
+constexpr int kClWarps = 8;
+__global__ void __launch_bounds__(kClWarps * 32)
+shadow_cl_kernel(const float* __restrict__ p, __nv_bfloat16* __restrict__ out, const int64_t* __restrict__ table,
+                 const int64_t* __restrict__ row_start, int n_entries, int slab /*floats per warp, multiple of 4*/) {
+    extern __shared__ __align__(16) float row_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* sm = row_sm + (size_t)warp * slab;
     const int64_t total = row_start[n_entries];
-    for (int64_t row = blockIdx.x; row < total; row += gridDim.x) {
+    for (int64_t row = (int64_t)blockIdx.x * kClWarps + warp; row < total; row += (int64_t)gridDim.x * kClWarps) {
         int lo = 0, hi = n_entries - 1;                     // last entry with row_start <= row
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
@@ -246,13 +253,33 @@ __global__ void shadow_cl_kernel(const float* __restrict__ p, __nv_bfloat16* __r
         const int64_t local = row - row_start[lo];
         const float* src = p + e[0] + local * L;
         __nv_bfloat16* dst = out + e[1] + local * L;
-        for (int j = threadIdx.x; j < L; j += blockDim.x) row_sm[j] = src[j];
-        __syncthreads();
-        for (int j = threadIdx.x; j < L; j += blockDim.x) {
-            const int t = j / cin, ci = j - t * cin;
-            dst[j] = __float2bfloat16_rn(row_sm[ci * kk + t]);
+        if ((L & 3) == 0 && ((uintptr_t)src & 15) == 0) {
+            for (int j = lane; j < (L >> 2); j += 32)
+                reinterpret_cast<float4*>(sm)[j] = __ldg(reinterpret_cast<const float4*>(src) + j);
+        } else {
+            for (int j = lane; j < L; j += 32) sm[j] = src[j];
         }
-        __syncthreads();
+        __syncwarp();
+        if ((cin & 7) == 0 && ((uintptr_t)dst & 15) == 0) {
+            const int cchunks = cin >> 3;
+            for (int v = lane; v < cchunks * kk; v += 32) {
+                const int cc = v / kk, t = v - cc * kk;        // output vector: tap t, input channels cc*8 .. cc*8+7
+                const float* s8 = sm + (cc * 8) * kk + t;
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(s8[(2 * q) * kk], s8[(2 * q + 1) * kk]);
+                    w[q] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(dst + t * cin + cc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+            for (int j = lane; j < L; j += 32) {
+                const int t = j / cin, ci = j - t * cin;
+                dst[j] = __float2bfloat16_rn(sm[ci * kk + t]);
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -260,8 +287,19 @@ __global__ void shadow_cl_kernel(const float* __restrict__ p, __nv_bfloat16* __r
 // the flat gradient buffer (one torch elementwise launch per convolution before: 218 launches per step).
 // table[e] = {src pointer, dst pointer, numel, Cin, kk}: kk = 0: same element order; kk > 0: src is the (Cout,kh,kw,Cin) channels-last
 // layout the library returns for k x k weights, dst the (Cout,Cin,kh,kw) parameter order.
-// chunk_start[e] = first 4096-element chunk of entry e (chunk_start[n] = total chunks).
-__global__ void accum_list_kernel(const int64_t* __restrict__ table, const int64_t* __restrict__ chunk_start, int n_entries) {
+// chunk_start[e] = first chunk of entry e (chunk_start[n] = total chunks); a chunk is 4096 elements, or -- kk > 0 and a row of
+// Cin*kk elements fits -- max(1, 4096 / (Cin*kk)) whole rows (rss_accum_chunks() is the one definition, host and device).
+// Round 2 walked the k x k entries in destination order and gathered the bf16 source element by element (stride Cin, two integer
+// divisions each): 144 us for 54 MB in + 216 MB read-modify-write.  Whole rows are contiguous on BOTH sides, so a chunk of rows is
+// staged through shared memory: 16-byte source loads, 16-byte read-modify-writes.
+constexpr int kAccChunk = 4096;
+__host__ __device__ inline int64_t accum_rows_per_chunk(int64_t cin, int64_t kk) {
+    const int64_t L = cin * kk;
+    return (kk > 0 && L > 0 && L <= kAccChunk) ? (kAccChunk / L > 1 ? kAccChunk / L : 1) : 0;      // 0: element chunks
+}
+__global__ void __launch_bounds__(256)
+accum_list_kernel(const int64_t* __restrict__ table, const int64_t* __restrict__ chunk_start, int n_entries) {
+    __shared__ __align__(16) float stage[kAccChunk];
     const int64_t total = chunk_start[n_entries];
     for (int64_t chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
         int lo = 0, hi = n_entries - 1;                     // last entry with chunk_start <= chunk
@@ -272,18 +310,60 @@ __global__ void accum_list_kernel(const int64_t* __restrict__ table, const int64
         const int64_t* e = table + (int64_t)lo * 5;
         const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(e[0]);
         float* dst = reinterpret_cast<float*>(e[1]);
-        const int64_t n = e[2], base = (chunk - chunk_start[lo]) * 4096;
+        const int64_t n = e[2], cl = chunk - chunk_start[lo];
         const int cin = (int)e[3], kk = (int)e[4];
+        const int64_t rpc = accum_rows_per_chunk(cin, kk);
         if (kk == 0) {
-            for (int64_t i = base + threadIdx.x; i < n && i < base + 4096; i += blockDim.x) dst[i] += __bfloat162float(src[i]);
-        } else {
+            const int64_t base = cl * kAccChunk;
+            for (int64_t i = base + threadIdx.x; i < n && i < base + kAccChunk; i += blockDim.x) dst[i] += __bfloat162float(src[i]);
+        } else if (rpc == 0) {                              // rows longer than the staging buffer: element-wise gather
+            const int64_t base = cl * kAccChunk;
             const int row = cin * kk;
-            for (int64_t i = base + threadIdx.x; i < n && i < base + 4096; i += blockDim.x) {
+            for (int64_t i = base + threadIdx.x; i < n && i < base + kAccChunk; i += blockDim.x) {
                 const int co = (int)(i / row), rem = (int)(i - (int64_t)co * row), ci = rem / kk, t = rem - ci * kk;
                 dst[i] += __bfloat162float(src[((int64_t)co * kk + t) * cin + ci]);
             }
+        } else {
+            const int L = cin * kk;
+            const int64_t rows = n / L, r0 = cl * rpc;
+            const int nr = (int)(rows - r0 < rpc ? rows - r0 : rpc), E = nr * L;
+            const __nv_bfloat16* s = src + r0 * L;
+            float* d = dst + r0 * L;
+            __syncthreads();                                // the previous chunk's readers of `stage` are done
+            if ((E & 7) == 0 && ((uintptr_t)s & 15) == 0) {
+                for (int j = threadIdx.x; j < (E >> 3); j += blockDim.x) {
+                    float v[8];
+                    load8(s + j * 8, v);
+                    reinterpret_cast<float4*>(stage)[2 * j] = make_float4(v[0], v[1], v[2], v[3]);
+                    reinterpret_cast<float4*>(stage)[2 * j + 1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            } else {
+                for (int j = threadIdx.x; j < E; j += blockDim.x) stage[j] = __bfloat162float(s[j]);
+            }
+            __syncthreads();
+            auto permuted = [&](int j) {                    // destination element j (row, ci, t) -> its staged (row, t, ci) value
+                const int rr = j / L, rem = j - rr * L, ci = rem / kk, t = rem - ci * kk;
+                return stage[rr * L + t * cin + ci];
+            };
+            if ((E & 3) == 0 && ((uintptr_t)d & 15) == 0) {
+                for (int j = threadIdx.x; j < (E >> 2); j += blockDim.x) {
+                    float4 g = reinterpret_cast<float4*>(d)[j];
+                    g.x += permuted(4 * j); g.y += permuted(4 * j + 1); g.z += permuted(4 * j + 2); g.w += permuted(4 * j + 3);
+                    reinterpret_cast<float4*>(d)[j] = g;
+                }
+            } else {
+                for (int j = threadIdx.x; j < E; j += blockDim.x) d[j] += permuted(j);
+            }
         }
     }
+}
+
+// number of accum_list_kernel chunks of one table entry
+extern "C" int64_t rss_accum_chunks(int64_t numel, int64_t cin, int64_t kk) {
+    const int64_t rpc = accum_rows_per_chunk(cin, kk);
+    if (rpc == 0) return (numel + kAccChunk - 1) / kAccChunk;
+    const int64_t rows = numel / (cin * kk);
+    return (rows + rpc - 1) / rpc;
 }
 
 // transposed copies for the data-gradient operand of the fused conv: out[(ci*kk + t)*Cout + co] = w[(co*Cin + ci)*kk + t]
@@ -317,9 +397,18 @@ extern "C" int rss_shadow_t_refresh(const float* params, void* shadow_t, const i
 
 extern "C" int rss_shadow_cl_refresh(const float* params, void* shadow_cl, const int64_t* table, const int64_t* row_start,
                                      int n_entries, int max_row_floats, cudaStream_t st) {
-    if (n_entries <= 0 || max_row_floats <= 0 || max_row_floats > 12 * 1024) return RSS_ERR_SHAPE;
-    shadow_cl_kernel<<<num_sms() * 8, 256, (size_t)max_row_floats * sizeof(float), st>>>(params, (__nv_bfloat16*)shadow_cl, table,
-                                                                                          row_start, n_entries);
+    if (n_entries <= 0 || max_row_floats <= 0 || max_row_floats > 6 * 1024) return RSS_ERR_SHAPE;
+    const int slab = (max_row_floats + 3) & ~3;
+    const size_t smem = (size_t)kClWarps * slab * sizeof(float);
+    static size_t attr_smem[16] = {0};                      // per device: opt-in dynamic shared memory already granted
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && (dev < 0 || dev >= 16 || attr_smem[dev] < smem)) {
+        cudaError_t e = cudaFuncSetAttribute(shadow_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { g_last_cuda_error = (int)e; return RSS_ERR_CUDA; }
+        if (dev >= 0 && dev < 16) attr_smem[dev] = smem;
+    }
+    shadow_cl_kernel<<<num_sms() * 3, kClWarps * 32, smem, st>>>(params, (__nv_bfloat16*)shadow_cl, table, row_start, n_entries, slab);
     return check_launch();
 }
 
