@@ -215,9 +215,20 @@ def lowp_cl(weight, dtype):
 
 
 class _ConvLib(torch.autograd.Function):
+    """link (optional dict): residual-gradient hand-off inside a Bottleneck.  The block input x feeds this 1x1 convolution AND the
+    residual add behind bn3; autograd would sum the two gradients with one elementwise kernel over the 134 MB tensor (62 us x 3 on
+    the one-stream tail of the step).  Instead the BatchNorm backward deposits its residual gradient in link['dres'] (returning
+    None to autograd) and this node's data gradient is ONE GEMM with beta = 1 into that buffer."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, dilation, bias_grad):
+    def forward(ctx, x, weight, bias, stride, padding, dilation, bias_grad, link=None):
         x = ops.nhwc(x)
+        if link is not None:
+            if weight.shape[2] == 1 and weight.shape[3] == 1 and stride == 1 and padding == 0 and x.is_cuda and ctx.needs_input_grad[0]:
+                link["armed"] = True
+            else:
+                link = None
+        ctx.link = link
         w = _lowp(weight, x.dtype, channels_last=True).contiguous(memory_format=CL)     # no-op on the per-step channels-last shadow
         b = _lowp(bias, x.dtype)
         y = torch.ops.aten.convolution(x, w, b, [stride, stride], [padding, padding], [dilation, dilation], False, [0, 0], 1)
@@ -238,11 +249,19 @@ class _ConvLib(torch.autograd.Function):
         if first:
             dw, db = _wgrad(dy, x, w, ctx.refs[0], ctx.refs[1], has_bias and ctx.needs_input_grad[2], stride, padding, dilation, wdtype)
         if ctx.needs_input_grad[0]:
-            dx = torch.ops.aten.convolution_backward(dy, x, w, None, [stride, stride], [padding, padding], [dilation, dilation],
-                                                     False, [0, 0], 1, [True, False, False])[0]
+            acc = ctx.link.pop("dres", None) if ctx.link is not None else None
+            if acc is not None and acc.dtype == dy.dtype and acc.shape == x.shape and acc.is_contiguous(memory_format=CL):
+                Cout, Cin = w.shape[0], w.shape[1]
+                acc.permute(0, 2, 3, 1).reshape(-1, Cin).addmm_(dy.permute(0, 2, 3, 1).reshape(-1, Cout), w.reshape(Cout, Cin))
+                dx = acc
+            else:
+                dx = torch.ops.aten.convolution_backward(dy, x, w, None, [stride, stride], [padding, padding], [dilation, dilation],
+                                                         False, [0, 0], 1, [True, False, False])[0]
+                if acc is not None:
+                    dx = dx + acc.to(dx.dtype)
         if ctx.needs_input_grad[1] and not first:
             dw, db = _wgrad(dy, x, w, ctx.refs[0], ctx.refs[1], has_bias and ctx.needs_input_grad[2], stride, padding, dilation, wdtype)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 def _igemm_ok(x, Cout):
@@ -514,7 +533,7 @@ class _ConvCF(torch.autograd.Function):
         return dx, dw, None
 
 
-def conv_bn_stats(x, weight, stride, padding, dilation, bn_stats):
+def conv_bn_stats(x, weight, stride, padding, dilation, bn_stats, link=None):
     """conv (no bias) whose epilogue also yields the BatchNorm statistics of its output.  bn_stats = (gamma, beta, running_mean,
     running_var, momentum, eps, scratch) or None.  Returns (y, aff) with aff None when the statistics still have to be computed by
     the caller (library conv, unsupported geometry)."""
@@ -522,7 +541,7 @@ def conv_bn_stats(x, weight, stride, padding, dilation, bn_stats):
     if stride == 1 and dilation == 1 and padding == k // 2 and k in (1, 3) and _cf_ok(x, weight.shape[0], k, bn_stats is not None):
         out = _ConvCF.apply(x, weight, bn_stats)
         return out if bn_stats is not None else (out, None)
-    return _ConvLib.apply(x, weight, None, stride, padding, dilation, False), None
+    return _ConvLib.apply(x, weight, None, stride, padding, dilation, False, link), None
 
 
 # BatchNorm statistics of the FFN's norm2 from the epilogue of the dw + dw6 + dw12 GEMM (rss_conv_igemm_stats); RSS_IGEMM_STATS=0: the

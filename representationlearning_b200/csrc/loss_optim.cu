@@ -39,8 +39,9 @@ __global__ void __launch_bounds__(kTile * kTile)
 seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ acc,
                     float* __restrict__ gdir /*[B][h][w][8], zeroed*/, int B, int h, int w, int H, int W,
                     float sy, float sx, int ignore_index) {
-    __shared__ float G[kTile][kTile][kNC];          // per-pixel d CE / d z (0 where ignored / outside the image)
+    __shared__ float G[kTile][kTile * kNC + 1];     // per-pixel d CE / d z (0 where ignored / outside the image); [row][col*7 + class], odd pitch
     __shared__ float T[kTile][kFoot][kNC];          // after the x pass: [output row][low-res column][class]
+    __shared__ int nf[2];                           // low-resolution columns / rows this tile's footprint really covers (<= kFoot)
     __shared__ float red[3][kTile * kTile / 32];
     __shared__ int flags[2];
     // per output column / row: footprint-relative low source index (kBig outside the image), weight of the low and of the high
@@ -108,7 +109,7 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
         }
     }
 #pragma unroll
-    for (int k = 0; k < kNC; ++k) G[r][c][k] = gk[k];
+    for (int k = 0; k < kNC; ++k) G[r][c * kNC + k] = gk[k];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     ce = warp_sum(ce); nv = warp_sum(nv); A = warp_sum(A);
     if (lane == 0) { red[0][warp] = ce; red[1][warp] = nv; red[2][warp] = A; }
@@ -120,6 +121,11 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
         for (int i = 0; i < kTile; ++i) n += src[i] < rr ? 1 : 0;
         (which ? fy : fx)[rr] = n;
     }
+    if (threadIdx.x == 64 || threadIdx.x == 65) {     // footprint: source cell of the last column / row inside the image, plus its right neighbour
+        const int which = threadIdx.x - 64, lim = which ? H - ty0 : W - tx0, last = (lim < kTile ? lim : kTile) - 1;
+        const int n = (which ? cy0 : cx0)[last] + 2;
+        nf[which] = n < kFoot ? n : kFoot;
+    }
     if (threadIdx.x < 3) {
         float s = 0.f;
         for (int i = 0; i < kTile * kTile / 32; ++i) s += red[threadIdx.x][i];
@@ -129,25 +135,56 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
     if (threadIdx.x == 4 && flags[1]) atomicOr(reinterpret_cast<int*>(acc + 2 + 2 * B) + b, 1);
     __syncthreads();
     // ---- x pass: T[row][rx][k] = sum over the output columns whose bilinear footprint contains low-res column fx0 + rx:
-    //      columns with x0 == rx (low weight) and columns with x0 == rx - 1 (high weight)
-    for (int i = threadIdx.x; i < kTile * kFoot * kNC; i += blockDim.x) {
-        const int k = i % kNC, rx = (i / kNC) % kFoot, row = i / (kNC * kFoot);
-        float s = 0.f;
-        for (int cc = fx[rx]; cc < fx[rx + 1]; ++cc) s += wx0[cc] * G[row][cc][k];
+    //      columns with x0 == rx (low weight) and columns with x0 == rx - 1 (high weight).
+    //      One thread per (output row, low-res column INSIDE the footprint), the 7 classes in registers: at scale 4 a tile touches
+    //      ~10 of the kFoot = 18 columns, and one work item per (row, column, class) over all 18 -- 4032 items with an index decode
+    //      and two loop set-ups each -- was 39 % of the kernel's instructions (profiles/ncu_r2_seg_loss_source_lines.txt).
+    //      Same summation order per element as before: bit-identical.
+    const int nfx = nf[0], nfy = nf[1];
+    for (int i = threadIdx.x; i < kTile * nfx; i += blockDim.x) {
+        const int row = i / nfx, rx = i - row * nfx;
+        float s[kNC];
+#pragma unroll
+        for (int k = 0; k < kNC; ++k) s[k] = 0.f;
+        for (int cc = fx[rx]; cc < fx[rx + 1]; ++cc) {
+            const float wgt = wx0[cc];
+#pragma unroll
+            for (int k = 0; k < kNC; ++k) s[k] += wgt * G[row][cc * kNC + k];
+        }
         if (rx > 0)
-            for (int cc = fx[rx - 1]; cc < fx[rx]; ++cc) s += wx1[cc] * G[row][cc][k];
-        T[row][rx][k] = s;
+            for (int cc = fx[rx - 1]; cc < fx[rx]; ++cc) {
+                const float wgt = wx1[cc];
+#pragma unroll
+                for (int k = 0; k < kNC; ++k) s[k] += wgt * G[row][cc * kNC + k];
+            }
+#pragma unroll
+        for (int k = 0; k < kNC; ++k) T[row][rx][k] = s[k];
     }
     __syncthreads();
     // ---- y pass, straight into the global low-resolution gradient (cells on tile borders are shared with the neighbours)
-    for (int i = threadIdx.x; i < kFoot * kFoot * kNC; i += blockDim.x) {
-        const int k = i % kNC, rx = (i / kNC) % kFoot, ry = i / (kNC * kFoot);
-        float vsum = 0.f;
-        for (int rr = fy[ry]; rr < fy[ry + 1]; ++rr) vsum += wy0[rr] * T[rr][rx][k];
+    for (int i = threadIdx.x; i < nfy * nfx; i += blockDim.x) {
+        const int ry = i / nfx, rx = i - ry * nfx;
+        float vsum[kNC];
+#pragma unroll
+        for (int k = 0; k < kNC; ++k) vsum[k] = 0.f;
+        for (int rr = fy[ry]; rr < fy[ry + 1]; ++rr) {
+            const float wgt = wy0[rr];
+#pragma unroll
+            for (int k = 0; k < kNC; ++k) vsum[k] += wgt * T[rr][rx][k];
+        }
         if (ry > 0)
-            for (int rr = fy[ry - 1]; rr < fy[ry]; ++rr) vsum += wy1[rr] * T[rr][rx][k];
+            for (int rr = fy[ry - 1]; rr < fy[ry]; ++rr) {
+                const float wgt = wy1[rr];
+#pragma unroll
+                for (int k = 0; k < kNC; ++k) vsum[k] += wgt * T[rr][rx][k];
+            }
         const int yy = fy0 + ry, xx = fx0 + rx;
-        if (vsum != 0.f && yy < h && xx < w) atomicAdd(gdir + (((int64_t)b * h + yy) * w + xx) * kNCP + k, vsum);
+        if (yy < h && xx < w) {
+            float* gp = gdir + (((int64_t)b * h + yy) * w + xx) * kNCP;
+#pragma unroll
+            for (int k = 0; k < kNC; ++k)
+                if (vsum[k] != 0.f) atomicAdd(gp + k, vsum[k]);
+        }
     }
 }
 

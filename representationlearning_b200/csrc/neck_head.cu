@@ -65,50 +65,72 @@ __global__ void neck_gather_fwd_kernel(const T* __restrict__ f0, const T* __rest
     }
 }
 
-// gather-form transpose of the bilinear up-sampling: one thread per (input pixel, 8 channels)
+// Gather-form transpose of the bilinear up-sampling, ALL FOUR levels in one launch (coarsest first: its items are the longest).
+// One item = (input pixel, 8 channels); at the coarse levels an item is split over `parts` = 2 / 4 adjacent lanes that take every
+// parts-th output row of the pixel's footprint and are combined with shuffles (level 3 has only 131 k items of ~17 x 17 loads each:
+// one thread per item left 3.5 half-empty blocks per SM walking 441 candidates serially -- 136 us for a 134 MB read; the four
+// launches ran back to back, 370 us of the one-stream tail of the step).
+// align_corners=True makes the weight of output o on input cell i a tent, w = max(0, 1 - |min(s*o, in-1) - i|) -- the same numbers
+// as bilinear_src() + the (i0 == i, i1 == i) tests of round 1 in 4 instructions instead of ~15 per candidate.
+struct NeckBwdPlan { int blk_end[4]; int level[4]; int parts[4]; };
+
+__device__ __forceinline__ float tent_weight(int o, float s, int in, int i) {
+    return fmaxf(0.f, 1.f - fabsf(fminf(s * (float)o, (float)(in - 1)) - (float)i));
+}
+
 template <typename T>
-__global__ void neck_gather_bwd_kernel(const T* __restrict__ dcat, T* __restrict__ d0, T* __restrict__ d1,
-                                       T* __restrict__ d2, T* __restrict__ d3, NeckGeom g, int level) {
-    const int l = level, Cl = g.C[l], hl = g.h[l], wl = g.w[l], groups = Cl / 8;
+__global__ void __launch_bounds__(256)
+neck_gather_bwd_kernel(const T* __restrict__ dcat, T* __restrict__ d0, T* __restrict__ d1, T* __restrict__ d2, T* __restrict__ d3,
+                       NeckGeom g, NeckBwdPlan pl) {
+    int slot = 0;
+    while (slot < 3 && (int)blockIdx.x >= pl.blk_end[slot]) ++slot;
+    const int l = pl.level[slot], P = pl.parts[slot];
+    const int Cl = g.C[l], hl = g.h[l], wl = g.w[l], groups = Cl / 8;
     T* dst = l == 0 ? d0 : (l == 1 ? d1 : (l == 2 ? d2 : d3));
     const int64_t total = (int64_t)g.B * hl * wl * groups;
-    const bool small = total < 0x7fffffffLL;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const PixIdx q = split_pix(idx, groups, wl, hl, small);
-        const int grp = q.grp, ix = q.x, iy = q.y, b = q.b;
-        const int64_t pix = q.pix;
-        const T* src = dcat + (int64_t)b * g.H * g.W * g.Ctot + g.coff[l] + grp * 8;
-        float acc[8];
+    const int64_t item = ((int64_t)blockIdx.x - (slot ? pl.blk_end[slot - 1] : 0)) * blockDim.x + threadIdx.x;
+    const int part = (int)(item & (P - 1));
+    int64_t idx = item / P;
+    const bool live = idx < total;                      // dead lanes keep running: they take part in the shuffles
+    if (!live) idx = total - 1;
+    const PixIdx q = split_pix(idx, groups, wl, hl, total < 0x7fffffffLL);
+    const int grp = q.grp, ix = q.x, iy = q.y, b = q.b;
+    const T* src = dcat + (int64_t)b * g.H * g.W * g.Ctot + g.coff[l] + grp * 8;
+    float acc[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        if (l == 0) {
-            load8(src + ((int64_t)iy * g.W + ix) * g.Ctot, acc);
-        } else {
-            const float sy = g.sy[l], sx = g.sx[l];
-            int oy_lo = sy > 0.f ? (int)floorf((iy - 1) / sy) - 1 : 0, oy_hi = sy > 0.f ? (int)ceilf((iy + 1) / sy) + 1 : g.H - 1;
-            int ox_lo = sx > 0.f ? (int)floorf((ix - 1) / sx) - 1 : 0, ox_hi = sx > 0.f ? (int)ceilf((ix + 1) / sx) + 1 : g.W - 1;
-            if (oy_lo < 0) oy_lo = 0; if (ox_lo < 0) ox_lo = 0;
-            if (oy_hi > g.H - 1) oy_hi = g.H - 1; if (ox_hi > g.W - 1) ox_hi = g.W - 1;
-            for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-                int y0, y1; float ly;
-                bilinear_src(oy, sy, hl, y0, y1, ly);
-                const float wy = (y0 == iy ? 1.f - ly : 0.f) + (y1 == iy ? ly : 0.f);
-                if (wy == 0.f) continue;
-                for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-                    int x0, x1; float lx;
-                    bilinear_src(ox, sx, wl, x0, x1, lx);
-                    const float wx = (x0 == ix ? 1.f - lx : 0.f) + (x1 == ix ? lx : 0.f);
-                    if (wx == 0.f) continue;
-                    float v[8];
-                    load8(src + ((int64_t)oy * g.W + ox) * g.Ctot, v);
-                    const float wgt = wy * wx;
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (l == 0) {
+        if (live) load8(src + ((int64_t)iy * g.W + ix) * g.Ctot, acc);
+    } else if (live) {
+        const float sy = g.sy[l], sx = g.sx[l];
+        int oy_lo = sy > 0.f ? (int)floorf((iy - 1) / sy) - 1 : 0, oy_hi = sy > 0.f ? (int)ceilf((iy + 1) / sy) + 1 : g.H - 1;
+        int ox_lo = sx > 0.f ? (int)floorf((ix - 1) / sx) - 1 : 0, ox_hi = sx > 0.f ? (int)ceilf((ix + 1) / sx) + 1 : g.W - 1;
+        if (oy_lo < 0) oy_lo = 0; if (ox_lo < 0) ox_lo = 0;
+        if (oy_hi > g.H - 1) oy_hi = g.H - 1; if (ox_hi > g.W - 1) ox_hi = g.W - 1;
+        while (ox_lo < ox_hi && tent_weight(ox_lo, sx, wl, ix) == 0.f) ++ox_lo;      // trim the safety margins: the inner loop is branch-free
+        while (ox_hi > ox_lo && tent_weight(ox_hi, sx, wl, ix) == 0.f) --ox_hi;
+        for (int oy = oy_lo + part; oy <= oy_hi; oy += P) {
+            const float wy = tent_weight(oy, sy, hl, iy);
+            if (wy == 0.f) continue;
+            const T* rowp = src + (int64_t)oy * g.W * g.Ctot;
+#pragma unroll 4
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                float v[8];
+                load8(rowp + (int64_t)ox * g.Ctot, v);
+                const float wgt = wy * tent_weight(ox, sx, wl, ix);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i] += wgt * v[i];
-                }
+                for (int i = 0; i < 8; ++i) acc[i] += wgt * v[i];
             }
         }
-        store8(dst + pix * Cl + grp * 8, acc);
     }
+    if (P > 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+            if (P > 2) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
+        }
+    }
+    if (live && part == 0) store8(dst + q.pix * Cl + grp * 8, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -365,12 +387,19 @@ extern "C" int rss_neck_gather_bwd(const void* dcat, void* d0, void* d1, void* d
     if (B <= 0 || !C || !h || !w) return RSS_ERR_SHAPE;
     for (int l = 0; l < 4; ++l) if (C[l] <= 0 || C[l] % 8 || h[l] <= 0 || w[l] <= 0) return RSS_ERR_SHAPE;
     const NeckGeom g = neck_geom(B, h[0], w[0], C, h, w);
-    for (int l = 0; l < 4; ++l) {
-        const int64_t total = (int64_t)B * h[l] * w[l] * (C[l] / 8);
-        int grid = (int)((total + 255) / 256);
-        if (grid > num_sms() * 16) grid = num_sms() * 16;
-        RSS_DISPATCH_DTYPE(dtype, neck_gather_bwd_kernel<T><<<grid, 256, 0, st>>>((const T*)dcat, (T*)d0, (T*)d1, (T*)d2, (T*)d3, g, l));
+    NeckBwdPlan pl;
+    int64_t blocks = 0;
+    for (int s = 0; s < 4; ++s) {                        // coarsest level first
+        const int l = 3 - s;
+        const int ratio = h[l] > 0 ? h[0] / h[l] : 1;
+        pl.level[s] = l;
+        pl.parts[s] = l == 0 ? 1 : (ratio >= 8 ? 4 : (ratio >= 4 ? 2 : 1));
+        const int64_t items = (int64_t)B * h[l] * w[l] * (C[l] / 8) * pl.parts[s];
+        blocks += (items + 255) / 256;
+        if (blocks > 0x7fffffff) return RSS_ERR_SHAPE;
+        pl.blk_end[s] = (int)blocks;
     }
+    RSS_DISPATCH_DTYPE(dtype, neck_gather_bwd_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)dcat, (T*)d0, (T*)d1, (T*)d2, (T*)d3, g, pl));
     return check_launch();
 }
 

@@ -69,11 +69,17 @@ def _conv(cin, cout, k, stride=1, padding=0):
     return nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=padding, bias=False)
 
 
-def _run(conv, bn, x, residual=None):
+def _run(conv, bn, x, residual=None, link=None):
     """conv (no bias) -> fused BN(+act)(+residual); the batch statistics come out of the conv kernel's epilogue when the
-    geometry is one csrc/conv_cf.cu covers."""
-    y, aff = conv_bn_stats(x, conv.weight, conv.stride[0], conv.padding[0], conv.dilation[0], bn.stats_args())
-    return bn(y, residual, aff=aff)
+    geometry is one csrc/conv_cf.cu covers.  link: residual-gradient hand-off of a Bottleneck (conv._ConvLib): the call WITHOUT a
+    residual is the 1x1 convolution that consumes it, the call WITH a residual the BatchNorm that deposits it."""
+    y, aff = conv_bn_stats(x, conv.weight, conv.stride[0], conv.padding[0], conv.dilation[0], bn.stats_args(),
+                           link=link if residual is None else None)
+    return bn(y, residual, aff=aff, link=link if residual is not None else None)
+
+
+# RSS_RES_LINK=0: autograd sums the two gradients of a Bottleneck's input (1x1 conv + identity residual) with an elementwise kernel
+RES_LINK = os.environ.get("RSS_RES_LINK", "1") != "0"
 
 
 # RSS_BLOCK_FUSED (default on): stride-1 BasicBlocks without downsample whose geometry csrc/conv_cf.cu instantiates (C -> C 3x3, C in
@@ -245,9 +251,11 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         residual = x if self.downsample is None else _run(self.downsample[0], self.downsample[1], x)
-        out = _run(self.conv1, self.bn1, x)
+        # identity residual: x feeds conv1 and the add behind bn3 -- their two gradients are merged by conv1's data-gradient GEMM
+        link = {} if (RES_LINK and self.downsample is None and x.is_cuda and torch.is_grad_enabled() and x.requires_grad) else None
+        out = _run(self.conv1, self.bn1, x, link=link)
         out = _run(self.conv2, self.bn2, out)
-        return _run(self.conv3, self.bn3, out, residual)
+        return _run(self.conv3, self.bn3, out, residual, link=link)
 
 
 blocks_dict = {"BASIC": BasicBlock, "BOTTLENECK": Bottleneck}

@@ -38,14 +38,14 @@ class FusedBNAct(nn.Module):
 
     defer_counter = False      # set per INSTANCE by trainer.FlatSGD, which bumps the counters of the modules it owns with one foreach op per step
 
-    def forward(self, x, residual=None, pre_bias=None, aff=None):
+    def forward(self, x, residual=None, pre_bias=None, aff=None, link=None):
         """pre_bias (training mode only): bias of the conv that produced x, left out of x because BatchNorm cancels it.
         aff: statistics already produced by the conv kernel's epilogue (conv.conv_bn_stats)."""
         if self.training and not self.defer_counter:
             self.num_batches_tracked += 1
         return ops.BNAct.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
                                self.training, self.momentum, self.eps, self.act, True if self.sync else None, self._scratch,
-                               pre_bias, aff)
+                               pre_bias, aff, link)
 
     def stats_args(self):
         """what conv.conv_bn_stats needs to produce this layer's batch statistics in the conv epilogue (None: not applicable --

@@ -18,7 +18,7 @@ CL = torch.channels_last
 KERNELS_PER_CALL = {
     "rss_layernorm_fwd": 1, "rss_layernorm_bwd": 1, "rss_attn_fwd": 5, "rss_spatial_attention_fwd": 2, "rss_bilinear_resize": 1, "rss_confusion_matrix": 1, "rss_accum_bf16_list": 1, "rss_attn_bwd": 7, "rss_bn_stats": 1, "rss_bn_combine": 1,
     "rss_bn_finalize": 1, "rss_bn_eval_affine": 1, "rss_bn_act_fwd": 1, "rss_bn_bwd_reduce": 1, "rss_bn_bwd_apply": 1, "rss_sync_bn_finalize": 1, "rss_sync_allreduce_small": 1, "rss_bn_stats_raw": 1,
-    "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 4, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
+    "rss_neck_gather_fwd": 1, "rss_neck_gather_bwd": 1, "rss_head_fwd": 1, "rss_head_bwd": 1, "rss_head_probs": 1,
     "rss_headaux_fwd": 2, "rss_seg_loss_fwd": 2, "rss_seg_loss_bwd": 1, "rss_grad_sumsq": 1, "rss_sgd_step": 1,
     "rss_conv_igemm": 1, "rss_conv_pack_weights": 1, "rss_conv_wgrad": 1, "rss_conv_wgrad_tc": 1, "rss_conv_cf": 1, "rss_shadow_t_refresh": 1, "rss_shadow_cl_refresh": 1, "rss_fuse_sum_fwd": 1, "rss_fuse_sum_bwd": 1,
 }
@@ -304,7 +304,7 @@ def bn_accepts_raw_sums(x, training, group, scratch, C):
 class BNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, residual, gamma, beta, running_mean, running_var, training, momentum, eps, act, group, scratch=None,
-                pre_bias=None, aff=None):
+                pre_bias=None, aff=None, link=None):
         """aff: (4,C) mean/invstd/scale/shift already produced (and running statistics already updated) by the convolution
         kernel's epilogue (rss_conv_cf): the statistics pass is skipped.
         pre_bias: bias of the producing conv, NOT added to x (training mode only: a per-channel shift cancels in the
@@ -387,6 +387,8 @@ class BNAct(torch.autograd.Function):
         if not raw:
             check(lib.rss_bn_act_fwd(_p(x), _p(residual), _p(y), _p(aff[2]), _p(aff[3]), rows, C, act, dt, st), "rss_bn_act_fwd")
         ctx.scratch = scratch
+        # link: see conv._ConvLib -- the residual gradient is handed to the 1x1 convolution that shares the residual's source tensor
+        ctx.link = link if (link is not None and link.get("armed") and residual is not None) else None
         ctx.save_for_backward(x, y if (act == _lib.ACT_RELU and residual is not None) else None, aff)
         ctx.act, ctx.training, ctx.group, ctx.world, ctx.has_res = act, training, group, world, residual is not None
         ctx.refs = (gamma, beta)
@@ -394,6 +396,14 @@ class BNAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        out = BNAct._backward(ctx, dy) + (None,)
+        if ctx.link is not None and out[1] is not None:
+            ctx.link["dres"] = out[1]
+            out = (out[0], None) + out[2:]
+        return out
+
+    @staticmethod
+    def _backward(ctx, dy):
         lib = _lib.load()
         x, y, aff = ctx.saved_tensors
         dy = nhwc(dy)

@@ -53,3 +53,31 @@ def test_accum_bf16_list_bit_exact():
     torch.cuda.synchronize()
     for (sink, dw, cin, kk), w in zip(items, want):
         assert torch.equal(sink, w), (tuple(sink.shape), kk)
+
+
+def test_bottleneck_residual_link_equivalence(monkeypatch):
+    """_hrnet_rssformer.py:249-287 Bottleneck with identity residual: the gradient of the block input is d(conv1 path) + d(residual).
+    With the hand-off (hrnet.RES_LINK) conv1's data gradient is one GEMM with beta = 1 into bn3's residual gradient; without it
+    autograd adds the two tensors.  Same result up to one bf16 rounding."""
+    from representationlearning_b200 import hrnet
+    torch.manual_seed(11)
+    blk = hrnet.Bottleneck(256, 64).cuda().train()
+    x0 = torch.randn(2, 256, 24, 40, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(2, 256, 24, 40, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    res = {}
+    for on in (False, True):
+        monkeypatch.setattr(hrnet, "RES_LINK", on)
+        for p in blk.parameters():
+            p.grad = None
+        x = x0.clone().requires_grad_(True)
+        y = blk(x)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        res[on] = (y.detach().float(), x.grad.float(), blk.conv1.weight.grad.clone(), blk.bn3.weight.grad.clone())
+    # (the two runs are not bit-identical even in the forward pass: the BatchNorm sums are float atomics)
+    def close(a, b, tol):
+        return (a - b).norm().item() <= tol * b.norm().item()
+    assert close(res[True][0], res[False][0], 1e-2)
+    assert close(res[True][2], res[False][2], 2e-2) and close(res[True][3], res[False][3], 2e-2)
+    a, b = res[True][1], res[False][1]
+    assert close(a, b, 1e-2), (a - b).norm().item() / b.norm().item()      # bf16 rounding noise; a missing residual term would be O(1)

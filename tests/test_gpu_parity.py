@@ -205,13 +205,15 @@ def test_interlaced_pool_attention_module_interface(P, report):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_neck_gather(P, report, dtype):
+@pytest.mark.parametrize("sizes", [((24, 24), (12, 12), (6, 6), (3, 3)), ((20, 28), (10, 14), (5, 7), (3, 4)), ((128, 128), (64, 64), (32, 32), (16, 16))])
+def test_neck_gather(P, report, dtype, sizes):
+    """forward + the one-launch gather-form backward (items of the coarse levels split over 2 / 4 lanes) vs F.interpolate + cat"""
     from representationlearning_b200 import ops
     torch.manual_seed(5)
     B = 2
-    feats = [torch.randn(B, c, s, s).to(dtype).float() for c, s in ((32, 24), (64, 12), (128, 6), (256, 3))]
+    feats = [torch.randn(B, c, s[0], s[1]).to(dtype).float() for c, s in zip((32, 64, 128, 256), sizes)]
     fr = [f.clone().requires_grad_(True) for f in feats]
-    ups = [fr[0]] + [torch.nn.functional.interpolate(f, size=(24, 24), mode="bilinear", align_corners=True) for f in fr[1:]]
+    ups = [fr[0]] + [torch.nn.functional.interpolate(f, size=sizes[0], mode="bilinear", align_corners=True) for f in fr[1:]]
     cat = torch.cat(ups, 1)
     dcat = torch.randn_like(cat).to(dtype).float()
     cat.backward(dcat)
@@ -221,7 +223,7 @@ def test_neck_gather(P, report, dtype):
     errs = dict(out=rel(oc.float(), cat))
     for i in range(4):
         errs["d%d" % i] = rel(fc[i].grad.float(), fr[i].grad)
-    report["neck_gather_%s" % str(dtype)[6:]] = errs
+    report["neck_gather_%s_%dx%d" % (str(dtype)[6:], sizes[0][0], sizes[0][1])] = errs
     assert max(errs.values()) < (TOL_F32 if dtype == torch.float32 else TOL_BF16), errs
 
 
