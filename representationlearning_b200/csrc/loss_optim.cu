@@ -35,14 +35,17 @@ __device__ __forceinline__ void bilinear_src_l(int o, float scale, int in, int& 
 // The transpose is done as a GATHER in two separable passes over shared memory (x, then y): every low-resolution cell sums the
 // <= 9 output columns (rows) that touch it.  (A first version scattered with shared-memory float atomics: sm_100 has no native
 // shared fp32 add -- SASS showed ATOMS.CAST.SPIN loops, ~16-way contended -- and the kernel took 674 us for 37 MB of traffic.)
-__global__ void __launch_bounds__(kTile * kTile)
+// 512 threads per 32 x 32 tile (two output rows per thread in the per-pixel phase): at 1024 threads x 45 registers only ONE tile was
+// resident per SM and its three barriers + the thin gather passes ran unoverlapped (6 us per tile); two resident tiles overlap them.
+constexpr int kLossThreads = kTile * kTile / 2;
+__global__ void __launch_bounds__(kLossThreads, 2)
 seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ acc,
                     float* __restrict__ gdir /*[B][h][w][8], zeroed*/, int B, int h, int w, int H, int W,
                     float sy, float sx, int ignore_index) {
     __shared__ float G[kTile][kTile * kNC + 1];     // per-pixel d CE / d z (0 where ignored / outside the image); [row][col*7 + class], odd pitch
     __shared__ float T[kTile][kFoot][kNC];          // after the x pass: [output row][low-res column][class]
     __shared__ int nf[2];                           // low-resolution columns / rows this tile's footprint really covers (<= kFoot)
-    __shared__ float red[3][kTile * kTile / 32];
+    __shared__ float red[3][kLossThreads / 32];
     __shared__ int flags[2];
     // per output column / row: footprint-relative low source index (kBig outside the image), weight of the low and of the high
     // source cell (the high weight is folded into the low one where align_corners clamps both onto the last cell)
@@ -58,13 +61,14 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
     bilinear_src_l(tx0, sx, w, fx0, tmp, tl);
     if (threadIdx.x < 2) flags[threadIdx.x] = 0;
     __syncthreads();
-    const int r = threadIdx.x / kTile, c = threadIdx.x % kTile;
-    const int oy = ty0 + r, ox = tx0 + c;
+    const int c = threadIdx.x % kTile, ox = tx0 + c;
     float ce = 0.f, nv = 0.f, A = 0.f;
-    float gk[kNC];
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const int r = threadIdx.x / kTile + half * (kTile / 2), oy = ty0 + r;
+        float gk[kNC];
 #pragma unroll
-    for (int k = 0; k < kNC; ++k) gk[k] = 0.f;
-    {
+        for (int k = 0; k < kNC; ++k) gk[k] = 0.f;
         int y0, y1, x0, x1; float ly, lx;
         bilinear_src_l(oy < H ? oy : H - 1, sy, h, y0, y1, ly);
         bilinear_src_l(ox < W ? ox : W - 1, sx, w, x0, x1, lx);
@@ -98,18 +102,18 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
             float zt = 0.f, et = 0.f;
 #pragma unroll
             for (int k = 0; k < kNC; ++k) { zt = (k == t) ? z[k] : zt; et = (k == t) ? e[k] : et; }
-            A = 1.f - et * inv_s;
+            A += 1.f - et * inv_s;
             if (lbl > 0) flags[0] = 1; else flags[1] = 1;          // benign race: all writers store 1
             if (valid) {
-                ce = lse - zt;
-                nv = 1.f;
+                ce += lse - zt;
+                nv += 1.f;
 #pragma unroll
                 for (int k = 0; k < kNC; ++k) gk[k] = e[k] * inv_s - (k == t ? 1.f : 0.f);
             }
         }
-    }
 #pragma unroll
-    for (int k = 0; k < kNC; ++k) G[r][c * kNC + k] = gk[k];
+        for (int k = 0; k < kNC; ++k) G[r][c * kNC + k] = gk[k];
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     ce = warp_sum(ce); nv = warp_sum(nv); A = warp_sum(A);
     if (lane == 0) { red[0][warp] = ce; red[1][warp] = nv; red[2][warp] = A; }
@@ -128,7 +132,7 @@ seg_loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict_
     }
     if (threadIdx.x < 3) {
         float s = 0.f;
-        for (int i = 0; i < kTile * kTile / 32; ++i) s += red[threadIdx.x][i];
+        for (int i = 0; i < kLossThreads / 32; ++i) s += red[threadIdx.x][i];
         atomicAdd(threadIdx.x == 0 ? acc : (threadIdx.x == 1 ? acc + 1 : acc + 2 + b), s);
     }
     if (threadIdx.x == 3 && flags[0]) atomicOr(reinterpret_cast<int*>(acc + 2 + B) + b, 1);
@@ -460,7 +464,7 @@ extern "C" int rss_seg_loss_fwd(const float* logits_lr, const int64_t* labels, c
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return RSS_ERR_CUDA; }
     const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
     dim3 grid(((H + kTile - 1) / kTile) * ((W + kTile - 1) / kTile), B);
-    seg_loss_fwd_kernel<<<grid, kTile * kTile, 0, st>>>(logits_lr, labels, acc_ws, gdir, B, h, w, H, W, sy, sx, ignore_index);
+    seg_loss_fwd_kernel<<<grid, kLossThreads, 0, st>>>(logits_lr, labels, acc_ws, gdir, B, h, w, H, W, sy, sx, ignore_index);
     seg_loss_finalize_kernel<<<1, 32, 0, st>>>(acc_ws, aux_scores, out4, B);
     return check_launch();
 }

@@ -422,12 +422,19 @@ extern "C" int rss_head_bwd(const void* x, const float* dlogits_lr, const float*
                             int64_t pixels, int C, int dtype, cudaStream_t st) {
     if (pixels <= 0 || C <= 0 || C % 8) return RSS_ERR_SHAPE;
     const int cg = C / 8;
-    int rpb = 256 / cg; if (rpb < 1) rpb = 1; if (rpb > 4) rpb = 4;
+    // rows per block: RSS_HEAD_BWD_RPB (default 4).  The kernel holds 168 registers, so a 240-thread block (4 rows at C = 480) is alone
+    // on its SM; measured on the B=16 step: 120-thread blocks, three per SM, 247 us vs 219 us (1 row: slower still) -- the per-block
+    // shared-memory reduction + 3360 atomics of the weight gradient cost more than the extra warps hide.  A register double buffer
+    // of the next pixel's operands was measured at 252 us.  Kept at 4.
+    static int rpb_max = 0;
+    if (rpb_max == 0) { const char* e = getenv("RSS_HEAD_BWD_RPB"); rpb_max = e ? atoi(e) : 4; if (rpb_max < 1 || rpb_max > 4) rpb_max = 4; }
+    int rpb = 256 / cg; if (rpb < 1) rpb = 1; if (rpb > rpb_max) rpb = rpb_max;
     while (rpb > 1 && (size_t)rpb * kNC * C * sizeof(float) > 48 * 1024) --rpb;
     const size_t smem = (size_t)rpb * kNC * C * sizeof(float);
     if (smem > 48 * 1024) return RSS_ERR_SHAPE;
     int grid = (int)((pixels + rpb - 1) / rpb);
-    if (grid > num_sms() * 4) grid = num_sms() * 4;
+    const int per_sm = 16 / rpb > 4 ? 16 / rpb : 4;
+    if (grid > num_sms() * per_sm) grid = num_sms() * per_sm;
     RSS_DISPATCH_DTYPE(dtype, head_bwd_kernel<T><<<grid, cg * rpb, smem, st>>>((const T*)x, dlogits_lr, w, (T*)dx, dw_acc, db_acc, pixels, C, cg, rpb));
     return check_launch();
 }
