@@ -26,10 +26,13 @@ static inline int bn_ticket_bpsm() {
     if (v == 0) { const char* e = getenv("RSS_BN_TICKET_BPSM"); v = e ? atoi(e) : 2; if (v < 1 || v > 8) v = 2; }
     return v;
 }
-// blocks per SM of the streaming apply kernels (RSS_BN_APPLY_BPSM, default 8)
+// blocks per SM of the streaming apply kernels (RSS_BN_APPLY_BPSM, default 4).  8 blocks x 256 threads fill every thread slot of an SM:
+// while such a kernel runs, the kernels the other streams of the step have ready cannot become resident, and the step is a
+// multi-stream DAG of ~15 us kernels (average concurrency 1.8).  Measured on the B=16 step, same box, back to back:
+// 8 -> 532.0 / 534.8, 6 -> 533.3, 4 -> 541.7, 3 -> 539.8, 2 -> 537.5, 16 -> 526.9 img/s.
 static inline int bn_apply_bpsm() {
     static int v = 0;
-    if (v == 0) { const char* e = getenv("RSS_BN_APPLY_BPSM"); v = e ? atoi(e) : 8; if (v < 1 || v > 16) v = 8; }
+    if (v == 0) { const char* e = getenv("RSS_BN_APPLY_BPSM"); v = e ? atoi(e) : 4; if (v < 1 || v > 16) v = 4; }
     return v;
 }
 // the ticket kernels on BIG tensors (the 67 MB hidden activations of the FFN): 2 blocks per SM keep only ~32 KB of loads in flight per

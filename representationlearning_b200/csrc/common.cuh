@@ -182,6 +182,15 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through check_launch()
 }
 
+// Resident blocks per SM granted to the element-wise streaming kernels of the multi-stream part of the step (fuse sums, LayerNorm).
+// A grid of 8 x 256-thread blocks per SM takes every thread slot, so kernels of the step's other streams cannot start beside it;
+// see bn.cu bn_apply_bpsm() for the measurement that set the BatchNorm kernels to 4.  RSS_STREAM_BPSM overrides `dflt`.
+inline int stream_bpsm(int dflt) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RSS_STREAM_BPSM"); v = e ? atoi(e) : 0; if (v < 0 || v > 32) v = 0; }
+    return v > 0 ? v : dflt;
+}
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {

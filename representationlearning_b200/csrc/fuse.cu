@@ -86,7 +86,7 @@ extern "C" int rss_fuse_sum_fwd(const void* const* terms, const int* log2_up, in
     for (int j = 0; j < n_terms; ++j) if (t.k[j] < 0 || t.k[j] > 5 || (H & ((1 << t.k[j]) - 1)) || (W & ((1 << t.k[j]) - 1))) return RSS_ERR_SHAPE;
     const int64_t total = (int64_t)B * H * W * (C / 8);
     int grid = (int)((total + 255) / 256);
-    if (grid > num_sms() * 16) grid = num_sms() * 16;
+    if (grid > num_sms() * stream_bpsm(16)) grid = num_sms() * stream_bpsm(16);
     RSS_DISPATCH_DTYPE(dtype, launch_k(fuse_sum_fwd_kernel<T>, grid, 256, 0, st, t, (T*)out, B, H, W, C, relu));
     return check_launch();
 }
@@ -97,7 +97,7 @@ extern "C" int rss_fuse_sum_bwd(const void* dout, const void* out, void* dterm, 
     if (relu && !out) return RSS_ERR_SHAPE;
     const int64_t total = (int64_t)B * (H >> log2_up) * (W >> log2_up) * (C / 8);
     int grid = (int)((total + 255) / 256);
-    if (grid > num_sms() * 16) grid = num_sms() * 16;
+    if (grid > num_sms() * stream_bpsm(16)) grid = num_sms() * stream_bpsm(16);
     if (grid < 1) grid = 1;
     RSS_DISPATCH_DTYPE(dtype, launch_k(fuse_sum_bwd_kernel<T>, grid, 256, 0, st, (const T*)dout, (const T*)out, (T*)dterm, B, H, W, C, log2_up, relu));
     return check_launch();

@@ -220,7 +220,7 @@ static int ln_fwd_launch(const void* x, void* y, float* mean, float* rstd, const
     const int tpt = C / 8;
     const int64_t rpb = 256 / tpt;
     int grid = (int)((rows + rpb - 1) / rpb);
-    const int cap = num_sms() * 16;
+    const int cap = num_sms() * stream_bpsm(16);
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
 #define LN_CASE(TPT) case TPT: launch_k(ln_fwd_kernel<T, TPT>, grid, 256, 0, st, (const T*)x, (T*)y, mean, rstd, gamma, beta, eps, rows); break;
@@ -235,7 +235,7 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const
     const int tpt = C / 8;
     const int64_t rpb = 256 / tpt;
     int grid = (int)((rows + rpb - 1) / rpb);
-    const int cap = num_sms() * 8;
+    const int cap = num_sms() * stream_bpsm(8);
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
 #define LN_CASE(TPT) case TPT: launch_k(ln_bwd_kernel<T, TDY, TPT>, grid, 256, 0, st, (const TDY*)dy, (const T*)x, mean, rstd, gamma, (const T*)dx_add, (T*)dx, dgamma, dbeta, rows); break;

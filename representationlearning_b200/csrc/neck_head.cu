@@ -425,7 +425,7 @@ extern "C" int rss_head_bwd(const void* x, const float* dlogits_lr, const float*
     // rows per block: RSS_HEAD_BWD_RPB (default 4).  The kernel holds 168 registers, so a 240-thread block (4 rows at C = 480) is alone
     // on its SM; measured on the B=16 step: 120-thread blocks, three per SM, 247 us vs 219 us (1 row: slower still) -- the per-block
     // shared-memory reduction + 3360 atomics of the weight gradient cost more than the extra warps hide.  A register double buffer
-    // of the next pixel's operands was measured at 252 us.  Kept at 4.
+    // of the next pixel's operands was measured at 252 us, two pixels per iteration with all loads issued first at 315 us.  Kept at 4.
     static int rpb_max = 0;
     if (rpb_max == 0) { const char* e = getenv("RSS_HEAD_BWD_RPB"); rpb_max = e ? atoi(e) : 4; if (rpb_max < 1 || rpb_max > 4) rpb_max = 4; }
     int rpb = 256 / cg; if (rpb < 1) rpb = 1; if (rpb > rpb_max) rpb = rpb_max;
