@@ -192,7 +192,7 @@ class FlatSGD:
         comm.wait_stream(torch.cuda.current_stream(dev))
         if self._main_stream is not None:
             comm.wait_stream(self._main_stream)
-        for s in hrnet._SIDE.get(dev, []):
+        for s in hrnet._SIDE.get(dev, []) + hrnet._ROW.get(dev, []):      # branch streams and fuse-row streams
             comm.wait_stream(s)
         for s in conv.WGRAD["streams"].get(dev, []):
             comm.wait_stream(s)
