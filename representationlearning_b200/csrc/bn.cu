@@ -18,30 +18,40 @@ struct BnGeom { int cg; int rpb; int threads; };
 static inline BnGeom bn_geom(int C) {
     BnGeom g; g.cg = C / 8; g.rpb = 256 / g.cg; if (g.rpb < 1) g.rpb = 1; g.threads = g.cg * g.rpb; return g;
 }
-// blocks per SM of the kernels that end in a device-wide ticket (statistics, backward reduce): every block pays one same-address
-// atomic round trip at its end, so fewer, fatter blocks shorten the tail (RSS_BN_TICKET_BPSM; measured on the B=16 step:
-// 1 -> 457, 2 -> 465, 4 -> 459, 8 -> 456 img/s; default 2)
+// Grid sizes of the BatchNorm kernels: resident 256-thread blocks per SM.  The step is a multi-stream DAG of ~2800 short kernels
+// (average concurrency 1.8): a grid of 8 blocks per SM takes every thread slot, and while it runs the kernels the other streams
+// have ready cannot become resident.  Smaller grids cost a little per kernel and win for the step.  Measured on the B=16 step
+// (img/s, each row on one box, back to back; round 2, after the stem / tail kernels):
+//   apply = big, ticket 2:   8 -> 532.0 / 534.8   6 -> 533.3   4 -> 541.7   3 -> 539.8   2 -> 537.5   16 -> 526.9
+//   apply 4, ticket 2, big:  8 -> 537.6           4 -> 542.2   3 -> 540.9   2 -> 539.9
+//   apply 4, big 4, ticket:  3 -> 541.9           2 -> 542.2   1 -> 548.4
+//   ticket 1, big 4, apply:  4 -> 545.3           3 -> 545.6   2 -> 549.5
+// (round 1, with the library stem and the old tail, had found ticket 1 -> 457, 2 -> 465, 4 -> 459, 8 -> 456.)
+//
+// RSS_BN_TICKET_BPSM (default 1): kernels that end in a device-wide ticket (statistics, backward reduce) on tensors < 24 MB: every
+// block pays one same-address atomic round trip at its end, so fewer, fatter blocks also shorten the tail.
 static inline int bn_ticket_bpsm() {
     static int v = 0;
-    if (v == 0) { const char* e = getenv("RSS_BN_TICKET_BPSM"); v = e ? atoi(e) : 2; if (v < 1 || v > 8) v = 2; }
+    if (v == 0) { const char* e = getenv("RSS_BN_TICKET_BPSM"); v = e ? atoi(e) : 1; if (v < 1 || v > 8) v = 1; }
     return v;
 }
-// blocks per SM of the streaming apply kernels (RSS_BN_APPLY_BPSM, default 4).  8 blocks x 256 threads fill every thread slot of an SM:
-// while such a kernel runs, the kernels the other streams of the step have ready cannot become resident, and the step is a
-// multi-stream DAG of ~15 us kernels (average concurrency 1.8).  Measured on the B=16 step, same box, back to back:
-// 8 -> 532.0 / 534.8, 6 -> 533.3, 4 -> 541.7, 3 -> 539.8, 2 -> 537.5, 16 -> 526.9 img/s.
+// RSS_BN_APPLY_BPSM (default 2): the streaming apply kernels on tensors < 24 MB (L2-resident layers of the multi-stream part)
 static inline int bn_apply_bpsm() {
     static int v = 0;
-    if (v == 0) { const char* e = getenv("RSS_BN_APPLY_BPSM"); v = e ? atoi(e) : 4; if (v < 1 || v > 16) v = 4; }
+    if (v == 0) { const char* e = getenv("RSS_BN_APPLY_BPSM"); v = e ? atoi(e) : 2; if (v < 1 || v > 16) v = 2; }
     return v;
 }
-// the ticket kernels on BIG tensors (the 67 MB hidden activations of the FFN): 2 blocks per SM keep only ~32 KB of loads in flight per
-// SM (statistics pass: 37 us for a 67 MB read = 1.8 TB/s, ncu: 27 % of DRAM throughput); there the ticket tail is noise next to the
-// streaming time, so they get the apply kernels' grid
-static inline int bn_ticket_bpsm_for(int64_t rows, int C, int dtype) {
-    const int64_t bytes = rows * C * (dtype == RSS_F32 ? 4 : 2);
-    return bytes >= ((int64_t)24 << 20) ? bn_apply_bpsm() : bn_ticket_bpsm();
+// RSS_BN_BIG_BPSM (default 4): every BatchNorm kernel on tensors >= 24 MB (stem, layer1, the FFN's 67 MB hidden activations, the
+// neck): HBM-bound passes that need bytes in flight -- 2 blocks per SM kept only ~32 KB of loads in flight per SM (37 us for a
+// 67 MB read) -- but even these lose at 8 (the weight-gradient streams run beside them)
+static inline int bn_big_bpsm() {
+    static int v = 0;
+    if (v == 0) { const char* e = getenv("RSS_BN_BIG_BPSM"); v = e ? atoi(e) : 4; if (v < 1 || v > 16) v = 4; }
+    return v;
 }
+static inline bool bn_is_big(int64_t rows, int C, int dtype) { return rows * C * (dtype == RSS_F32 ? 4 : 2) >= ((int64_t)24 << 20); }
+static inline int bn_ticket_bpsm_for(int64_t rows, int C, int dtype) { return bn_is_big(rows, C, dtype) ? bn_big_bpsm() : bn_ticket_bpsm(); }
+static inline int bn_apply_bpsm_for(int64_t rows, int C, int dtype) { return bn_is_big(rows, C, dtype) ? bn_big_bpsm() : bn_apply_bpsm(); }
 static inline int bn_grid(int64_t rows, int rpb, int per_sm) {
     int64_t g = (rows + rpb - 1) / rpb;
     const int64_t cap = (int64_t)num_sms() * per_sm;
@@ -699,7 +709,7 @@ extern "C" int rss_bn_act_fwd(const void* x, const void* residual, void* y, cons
     if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
     if (residual && act == RSS_ACT_GELU) return RSS_ERR_SHAPE;   // not a pattern of the reference (backward would need the residual)
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
+    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm_for(rows, C, dtype));
     RSS_DISPATCH_DTYPE(dtype, BN_ACT_LAUNCH(bn_act_fwd_kernel, residual != nullptr, grid, g.threads, 0, st, (const T*)x, (const T*)residual, (T*)y, scale, shift, rows, C, g.cg, g.rpb, BnFin{}));
     return check_launch();
 }
@@ -724,7 +734,7 @@ extern "C" int rss_bn_act_fwd_raw(const void* x, const void* residual, void* y, 
     if (C <= 0 || C % 8 || rows <= 0 || !accum_scratch || !ticket) return RSS_ERR_SHAPE;
     if (residual && act == RSS_ACT_GELU) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
+    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm_for(rows, C, dtype));
     BnFin fin;
     fin.accum = accum_scratch; fin.ticket = ticket; fin.gamma = gamma; fin.beta = beta; fin.running_mean = running_mean;
     fin.running_var = running_var; fin.momentum = momentum; fin.eps = eps; fin.mean_out = mean_out; fin.invstd_out = invstd_out;
@@ -763,7 +773,7 @@ extern "C" int rss_bn_bwd_apply(const void* x, const void* y, const void* dy, co
     if (C <= 0 || C % 8 || rows <= 0) return RSS_ERR_SHAPE;
     if (act == RSS_ACT_RELU && dres && !y) return RSS_ERR_SHAPE;     // residual layers must pass the saved output
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
+    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm_for(rows, C, dtype));
     RSS_DISPATCH_DTYPE(dtype, BN_ACT_LAUNCH(bn_bwd_apply_kernel, y != nullptr && act == RSS_ACT_RELU, grid, g.threads, 0, st, (const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, sums, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
                                             local_sums, dgamma_acc, dbeta_acc, (float*)nullptr, (unsigned int*)nullptr, (float*)nullptr));
     return check_launch();
@@ -778,7 +788,7 @@ extern "C" int rss_bn_bwd_apply_raw(const void* x, const void* y, const void* dy
     if (C <= 0 || C % 8 || rows <= 0 || !accum_scratch || !ticket) return RSS_ERR_SHAPE;
     if (act == RSS_ACT_RELU && dres && !y) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
+    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm_for(rows, C, dtype));
     RSS_DISPATCH_DTYPE(dtype, BN_ACT_SWITCH(bn_bwd_apply_kernel, y != nullptr && act == RSS_ACT_RELU, <<<grid, g.threads, 0, st>>>((const T*)x, (const T*)y, (const T*)dy, scale, shift, mean, invstd, nullptr, inv_count, (T*)dx, (T*)dres, rows, C, g.cg, g.rpb,
                                                                                                            nullptr, dgamma_acc, dbeta_acc, accum_scratch, ticket, sums_out)));
     return check_launch();
@@ -790,7 +800,7 @@ extern "C" int rss_bn_bwd_apply_dz(const void* x, const void* dz, const float* s
                                    const float* local_sums, float* dgamma_acc, float* dbeta_acc, cudaStream_t st) {
     if (C <= 0 || C % 8 || rows <= 0 || !dz) return RSS_ERR_SHAPE;
     const BnGeom g = bn_geom(C);
-    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm());
+    const int grid = bn_grid(rows, g.rpb * 4, bn_apply_bpsm_for(rows, C, dtype));
     RSS_DISPATCH_DTYPE(dtype, launch_k(bn_bwd_apply_dz_kernel<T>, grid, g.threads, 0, st, (const T*)x, (const T*)dz, scale, mean, invstd, sums,
                        inv_count, (T*)dx, rows, C, g.cg, g.rpb, local_sums, dgamma_acc, dbeta_acc));
     return check_launch();
