@@ -180,12 +180,12 @@ def gpu_eager_baseline(dev, batch, size, steps=5, warmup=2):
 
 # kernel-name substring -> family, for the CUPTI summary of the replayed step
 FAMILIES = (
+    ("stem_conv", "stem conv (stem_conv_{fwd,wgrad}_kernel: 3->64 stride-2 conv from the planar image, cast + layout + BN sums fused)"),
     ("bn_", "batchnorm (rss bn_* kernels: statistics / apply / backward reduce / backward apply)"),
     ("conv_cf_kernel", "fused tcgen05 conv (conv_cf_kernel: HRNet branch-0 BasicBlocks)"),
     ("conv_igemm_kernel", "tcgen05 implicit GEMM (conv_igemm_kernel: FFN 19-tap conv)"),
     ("win_attn_fwd", "window attention forward"), ("win_attn_bwd", "window attention backward"), ("gate_", "saliency gate"),
     ("ln_", "layernorm"), ("conv_wgrad", "own weight-gradient kernels"), ("fuse_sum", "multi-resolution fuse"),
-    ("stem_conv", "stem conv (stem_conv_{fwd,wgrad}_kernel: 3->64 stride-2 conv from the planar image, cast + layout + BN sums fused)"),
     ("neck_gather", "neck gather"), ("head_", "head"), ("seg_loss", "loss"), ("sgd_step", "optimiser"), ("sumsq", "optimiser"),
     ("shadow_", "optimiser"), ("cutlass", "library conv (cuDNN cutlass3x / xmma)"), ("xmma", "library conv (cuDNN cutlass3x / xmma)"),
     ("cudnn", "library conv (cuDNN cutlass3x / xmma)"), ("nvjet", "library GEMM (cuBLAS nvjet: 1x1 convs)"),
