@@ -192,3 +192,25 @@ def test_stream_schedule_switches_are_inert_on_cpu():
     assert not hrnet._dataflow(torch.zeros(1))               # the data-flow schedule only engages for CUDA tensors
     t = [torch.zeros(2), torch.zeros(2)]
     assert not hasattr(t[0], "_rss_home")
+
+
+def test_accum_chunk_rule_is_the_one_definition():
+    """rss_accum_chunks (host function of the library) is the only definition of how rss_accum_bf16_list splits a table entry:
+    4096-element chunks for same-order entries, whole (Cin*kk)-element rows for k x k entries whose row fits the staging buffer."""
+    from representationlearning_b200 import _lib
+    lib = _lib.load()
+    for n in (1, 5, 4096, 4097, 70000):
+        assert lib.rss_accum_chunks(n, 1, 0) == -(-n // 4096)
+    for cout, cin, kk in ((32, 32, 9), (256, 256, 9), (480, 40, 9), (1, 2, 49), (64, 3, 9), (5, 24, 9), (3, 600, 9)):
+        L, n = cin * kk, cout * cin * kk
+        want = -(-cout // max(1, 4096 // L)) if L <= 4096 else -(-n // 4096)
+        assert lib.rss_accum_chunks(n, cin, kk) == want, (cout, cin, kk)
+
+
+def test_stem_entry_points_reject_bad_geometry_before_touching_the_device():
+    """shape / dtype errors of the stem kernels are reported by the host side (no launch, so this runs without a GPU)"""
+    from representationlearning_b200 import _lib
+    lib = _lib.load()
+    assert lib.rss_stem_conv_fwd(None, None, None, 0, 8, 8, 0, None, None, None) == -1          # RSS_ERR_SHAPE
+    assert lib.rss_stem_conv_wgrad(None, None, None, 2, 0, 8, 0, None) == -1
+    assert lib.rss_stem_conv_fwd(None, None, ctypes.c_void_p(8), 1, 8, 8, 0, None, None, None) == -1   # y not 16-byte aligned
