@@ -186,7 +186,7 @@ FAMILIES = (
     ("conv_igemm_kernel", "tcgen05 implicit GEMM (conv_igemm_kernel: FFN 19-tap conv)"),
     ("win_attn_fwd", "window attention forward"), ("win_attn_bwd", "window attention backward"), ("gate_", "saliency gate"),
     ("ln_", "layernorm"), ("conv_wgrad", "own weight-gradient kernels"), ("fuse_sum", "multi-resolution fuse"),
-    ("neck_gather", "neck gather"), ("head_", "head"), ("seg_loss", "loss"), ("sgd_step", "optimiser"), ("sumsq", "optimiser"),
+    ("neck_gather", "neck gather"), ("head_", "head"), ("seg_loss", "loss"), ("sgd_step", "optimiser"), ("sumsq", "optimiser"), ("accum_list", "optimiser"),
     ("shadow_", "optimiser"), ("cutlass", "library conv (cuDNN cutlass3x / xmma)"), ("xmma", "library conv (cuDNN cutlass3x / xmma)"),
     ("cudnn", "library conv (cuDNN cutlass3x / xmma)"), ("nvjet", "library GEMM (cuBLAS nvjet: 1x1 convs)"),
     ("splitKreduce", "library GEMM (cuBLAS nvjet: 1x1 convs)"), ("elementwise", "torch elementwise (gradient accumulation adds)"),
