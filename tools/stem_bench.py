@@ -1,5 +1,5 @@
-"""Per-launch time of the fused stem kernels (csrc/stem.cu) at the benched geometry next to the library path they replace
-(cast + permute + ATen convolution / convolution_backward), CUDA events on the launching stream, L2 flushed between launches.
+"""Per-kernel time of the fused stem kernels (csrc/stem.cu) at the benched geometry next to the library path they replace
+(cast + permute + ATen convolution / convolution_backward): CUPTI kernel durations (torch.profiler), L2 flushed between calls.
 One JSON line per variant on stdout."""
 import json
 import os
@@ -17,23 +17,6 @@ w = (torch.randn(64, 3, 3, 3, device=dev) * 0.2).requires_grad_(True)
 scratch = torch.zeros(130, device=dev)
 shift = torch.zeros(64, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) if os.path.exists(
-    os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {}
-
-
-def timeit(fn, n=20):
-    for _ in range(3):
-        fn()
-    ts = []
-    for _ in range(n):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e3)
-    ts.sort()
-    return ts[len(ts) // 2]
-
 
 y = ops.StemConv.apply(x, w, None)
 dy = torch.randn_like(y)
